@@ -1,0 +1,123 @@
+"""CPU: pin the oracle against golden vectors produced by the reference's own modules."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import superdiff_oracle as O
+
+
+def _seeded_input(seed, shape):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g)
+
+
+def _draw_noise_stack(seed, shape, T):
+    torch.manual_seed(seed)
+    st = [torch.randn(shape)]
+    for _ in range(T - 1):
+        st.append(torch.randn_like(st[0]))
+    return torch.stack(st, 0)
+
+
+@pytest.fixture(scope="module")
+def fwd_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "unet_forward.npz"))
+
+
+@pytest.fixture(scope="module")
+def sample_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "ddpm_sample.npz"))
+
+
+def test_param_checksum(fwd_golden):
+    for w in (0, 1):
+        p = O.init_unet_params(w)
+        cs = float(sum(v.double().abs().sum().item() for v in p.values()))
+        assert cs == float(fwd_golden[f"param_checksum_w{w}"])
+        assert len(p) == 54  # 54 state-dict tensors
+
+
+def test_k1_unet_forward_matches_reference(fwd_golden):
+    keys = [k for k in fwd_golden.files if k.startswith("fwd_")]
+    assert len(keys) == 14
+    for k in keys:
+        _, w, xs, B, R, t = k.split("_")
+        w, xs, B, R, t = int(w[1:]), int(xs[1:]), int(B[1:]), int(R[1:]), int(t[1:])
+        p = O.init_unet_params(w)
+        x = _seeded_input(xs, (B, 1, R, R))
+        with torch.no_grad():
+            y = O.unet_forward(p, x, torch.full((B,), t, dtype=torch.long))
+        ref = torch.from_numpy(fwd_golden[k])
+        # same ATen kernels, same thread count may differ -> allow reduction-order noise only
+        assert torch.allclose(y, ref, rtol=0, atol=2e-5), (k, (y - ref).abs().max())
+
+
+def test_schedule(sample_golden):
+    s = O.Schedule(1000)
+    assert np.array_equal(s.betas.numpy(), sample_golden["sched1000_betas"])
+    assert np.array_equal(s.alpha_bars.numpy(), sample_golden["sched1000_alpha_bars"])
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_k2_replay_matches_reference_sample(sample_golden, name):
+    wseed, nseed, T, *shape = [int(v) for v in sample_golden[f"sample_{name}_meta"]]
+    p = O.init_unet_params(wseed)
+    st = _draw_noise_stack(nseed, tuple(shape), T)
+    y = O.ddpm_sample_replay(p, O.Schedule(T), st)
+    ref = torch.from_numpy(sample_golden[f"sample_{name}"])
+    assert torch.allclose(y, ref, rtol=0, atol=5e-4), (y - ref).abs().max()
+
+
+def test_k3_self_superposition_is_ddpm_sample():
+    """superposed_sample([m, m]) == DDPM.sample(m) bit-for-bit; kappa == 1/2; logq equal."""
+    p = O.init_unet_params(0)
+    T, shape = 12, (2, 1, 16, 16)
+    st = _draw_noise_stack(7, shape, T)
+    s = O.Schedule(T)
+    y1 = O.ddpm_sample_replay(p, s, st)
+    y2, kap, lq = O.superposed_sample([p, p], s, st)
+    assert torch.equal(y1, y2)
+    assert torch.equal(kap, torch.full_like(kap, 0.5))
+    assert torch.equal(lq[..., 0], lq[..., 1])
+    assert torch.equal(lq[0], torch.zeros_like(lq[0]))
+
+
+def test_k4_kappa_properties():
+    torch.manual_seed(0)
+    B, D, M = 3, 64, 2
+    x = torch.randn(B, 1, 8, 8)
+    eps = [torch.randn(B, 1, 8, 8) for _ in range(M)]
+    z = torch.randn(B, 1, 8, 8)
+    s = O.Schedule(10)
+    logq = torch.randn(B, M) * 5
+    x1, lq1, k1 = O.superpose_step(x, eps, z, logq, s.alphas[5], s.alpha_bars[5], s.betas[5])
+    assert torch.allclose(k1.sum(1), torch.ones(B), atol=1e-6)
+    x2, lq2, k2 = O.superpose_step(x, eps, z, logq + 3.25, s.alphas[5], s.alpha_bars[5], s.betas[5])
+    assert torch.allclose(k1, k2, atol=1e-6)
+    assert torch.allclose(x1, x2, atol=1e-5)
+    # two different models: increments differ
+    assert not torch.allclose(lq1[:, 0] - logq[:, 0], lq1[:, 1] - logq[:, 1])
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, exp in kat:
+        r = O.philox4x32_10(np.array([ctr], dtype=np.uint32), np.array(key, dtype=np.uint32))
+        assert tuple(int(v) for v in r[0]) == exp
+
+
+def test_philox_normal_moments_and_sharding():
+    a = O.philox_normal(1234, np.arange(4), 3, 4096)
+    assert abs(a.mean()) < 0.02 and abs(a.std() - 1) < 0.02
+    b = O.philox_normal(1234, np.array([2, 3]), 3, 4096)
+    assert np.array_equal(a[2:], b)  # keyed by global sample id -> shard invariant
+    c = O.philox_normal(1234, np.arange(4), 4, 4096)
+    assert not np.array_equal(a, c)
