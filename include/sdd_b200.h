@@ -1,0 +1,131 @@
+/* sdd_b200.h -- C ABI of the B200-native SuperDiff sampling hot path.
+ *
+ * The reference (mo-rsa24/super-diff-disease) has NO plugin / FFI boundary for this path:
+ * it is pure Python over stock PyTorch.  The entry points below are
+ * therefore what a binding for the reference's Python objects needs, one per reference call:
+ *
+ *   sdd_unet_create / sdd_unet_forward   <->  UNet.__init__ / UNet.forward     src/models/unet.py:38,57
+ *   sdd_sampler_* (M = 1)                <->  DDPM.sample                      src/models/ddpm.py:31-45
+ *   sdd_sampler_* (M >= 2)               <->  src/sampling.py (0 bytes in the reference; the
+ *                                             superposed sampler the README describes, README.md:5,9)
+ *   sdd_superpose_update                 <->  the per-step x update, ddpm.py:42-44, extended with
+ *                                             the kappa softmax / Ito log-density increment (A7)
+ *
+ * Conventions: plain pointers and sizes only.  All data pointers are DEVICE pointers unless the
+ * parameter name ends in _host.  `stream` is a cudaStream_t passed as void*.  Every function
+ * returns 0 on success or an SDD_E* code; sdd_last_error() gives the message (thread-local).
+ * Nothing here falls back to the CPU: without an sm_100 device every call fails with SDD_ENODEV.
+ * The library never frees or retains caller memory beyond the call, except where stated.
+ */
+#ifndef SDD_B200_H
+#define SDD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDD_ABI_VERSION 1
+
+enum {
+  SDD_OK = 0,
+  SDD_EINVAL = 1,   /* bad argument / unsupported shape */
+  SDD_ENODEV = 2,   /* no CUDA device of compute capability 10.x */
+  SDD_ECUDA = 3,    /* a CUDA runtime / driver call failed */
+  SDD_ENOMEM = 4
+};
+
+/* Number of fp32 tensors in a reference UNet state_dict (unet.py:40-55) and their order:
+ * exactly the order torch's state_dict() yields for the reference module:
+ *   time_mlp.1.{weight,bias}, time_mlp.3.{weight,bias}, then for each block in
+ *   downs.0, downs.1, mid, ups.0, ups.1:
+ *     block.0.{weight,bias} (GN1), block.2.{weight,bias} (conv1, [Cout,Cin,3,3]),
+ *     block.3.{weight,bias} (GN2), block.5.{weight,bias} (conv2), time_emb.{weight,bias}. */
+#define SDD_UNET_NUM_TENSORS 54
+
+typedef struct sdd_unet sdd_unet_t;
+typedef struct sdd_sampler sdd_sampler_t;
+
+int sdd_abi_version(void);
+const char* sdd_last_error(void);
+/* 0 iff the current CUDA device is compute capability 10.x. */
+int sdd_device_check(void);
+
+/* ---- UNet (unet.py:37-65; default architecture only: in=out=1, time_emb_dim=256, base=64) ---- */
+
+/* Build device-resident kernel-layout weights (bf16 conv operands, fp32 everything else) from the
+ * 54 fp32 state-dict tensors (device pointers, contiguous, reference shapes).  The inputs are only
+ * read during the call (stream-ordered); the handle owns its own copies. */
+int sdd_unet_create(sdd_unet_t** out, const float* const* tensors, int num_tensors, void* stream);
+int sdd_unet_destroy(sdd_unet_t* u);
+
+/* eps_out[B,1,H,W] = UNet(x[B,1,H,W], t[B]); fp32 in/out, t is int64 as in unet.py:57.
+ * H % 16 == 0 and W % 8 == 0 are required (SDD_EINVAL otherwise).  Workspace is owned by the
+ * handle and grown on demand (so the first call at a new shape is not graph-capturable). */
+int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps_out,
+                     int B, int H, int W, void* stream);
+
+/* ---- Fused superposition update (A7): one HBM pass per step ----
+ * kappa = softmax_m(temperature * logq[b,:] + bias);  eps_bar = sum_m kappa_m eps[m,b,:]
+ * x_out = alpha^-1/2 (x_in - (1-alpha)/sqrt(1-alpha_bar) eps_bar) + sqrt(beta) z        (ddpm.py:42-44)
+ * logq[b,m] += <s_m, x_out-x_in> - beta D/2 - beta/2 <x_in, s_m> - beta/2 |s_m|^2,  s_m = -eps_m/sqrt(1-alpha_bar)
+ * z: noise[B,D] if non-NULL; else Philox4x32-10 keyed (seed; element/4, sample_offset+b, draw_index)
+ * if draw_index >= 0; else zero (the t == 0 step, ddpm.py:36).
+ * x_out may alias x_in.  kappa_out[B,M] / logq_out[B,M] / xstats_out[B,2] (mean, rstd of x_out for the
+ * next GroupNorm(1,1)) may be NULL; logq_out may alias logq.  M <= 4.  D % 4 == 0.
+ * workspace: sdd_superpose_update_workspace(B, D, M) bytes, zero-initialised once by the caller. */
+size_t sdd_superpose_update_workspace(int B, int D, int M);
+int sdd_superpose_update(const float* x_in, float* x_out, const float* eps, const float* noise,
+                         const float* logq, float* logq_out, float* kappa_out, float* xstats_out,
+                         int B, int D, int M, float alpha, float alpha_bar, float beta,
+                         float temperature, const float* bias,
+                         uint64_t seed, int64_t sample_offset, int draw_index,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Philox standard normals, same definition as the in-kernel noise (for x_T and for tests). */
+int sdd_philox_normal(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw_index,
+                      void* stream);
+
+/* ---- Sampler: the whole reverse loop (ddpm.py:31-45 for M = 1; superposed for M >= 2) ---- */
+typedef struct {
+  const float* noise_stack; /* device [T,B,D] (stack[0] = x_T, stack[k] = k-th in-loop draw) or NULL = Philox */
+  uint64_t seed;            /* Philox key when noise_stack == NULL */
+  int64_t sample_offset;    /* global index of local sample 0 (batch sharding) */
+  float temperature;        /* 1.0 */
+  const float* bias;        /* device [M] or NULL */
+  float* x_out;             /* device [B,D] */
+  float* kappa_traj;        /* device [T,B,M] or NULL */
+  float* logq_traj;         /* device [T+1,B,M] or NULL */
+  int use_graph;            /* 1: replay one captured step graph T times */
+} sdd_sample_args;
+
+/* models[M] are borrowed and must outlive the sampler.  alphas/alpha_bars/betas are HOST fp32[T]
+ * (ddpm.py:9-11).  All workspaces for (B,H,W) are allocated here. */
+int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M,
+                       const float* alphas_host, const float* alpha_bars_host, const float* betas_host,
+                       int T, int B, int H, int W, void* stream);
+int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream);
+int sdd_sampler_destroy(sdd_sampler_t* s);
+/* Kernel launches one sdd_sampler_run issues (for bench.py's gpu_launches). */
+int64_t sdd_sampler_launches_per_run(const sdd_sampler_t* s);
+
+/* ---- Operator-level entry points (used by the parity tests and the roofline bench) ---- */
+
+/* out[B,H,W,Cout] (bf16 NHWC) = conv3x3(act[B,H,W,Cin] bf16 NHWC, pad 1) + bias[b*bias_batch_stride + c].
+ * w: fp32 [Cout,Cin,3,3] (reference layout; converted internally).  Cin, Cout in {64,128}.
+ * impl 0 = tcgen05/TMA kernel, 1 = plain CUDA-core kernel (bring-up cross-check only).
+ * gn_meanrstd[B,4,2] (may be NULL) receives GroupNorm(4,Cout) mean / rstd of the output. */
+int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t bias_batch_stride,
+                     void* out, float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, int impl,
+                     void* stream);
+
+/* In place on bf16 NHWC act[B,H,W,C]: silu((v - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]), G = 4. */
+int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta,
+                      int B, int H, int W, int C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDD_B200_H */

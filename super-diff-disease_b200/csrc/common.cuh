@@ -1,0 +1,229 @@
+// Shared helpers: error plumbing, PTX wrappers for mbarrier / TMA / tcgen05 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/sdd_b200.h"
+
+namespace sdd {
+
+void set_error(const std::string& msg);
+
+#define SDD_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::sdd::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " +     \
+                       __FILE__ + ":" + std::to_string(__LINE__));                       \
+      return SDD_ECUDA;                                                                  \
+    }                                                                                    \
+  } while (0)
+
+#define SDD_CHECK(cond, msg)                                                             \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      ::sdd::set_error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" +          \
+                       std::to_string(__LINE__));                                        \
+      return SDD_EINVAL;                                                                 \
+    }                                                                                    \
+  } while (0)
+
+#define SDD_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != SDD_OK) return _r; \
+  } while (0)
+
+// Where the per-launch epilogue bias comes from: base + (*row_ptr) * row_stride + b * batch_stride.
+// row_ptr == nullptr means row 0.  Lets one captured step graph serve every timestep.
+struct BiasRef {
+  const float* base;
+  const int* row_ptr;
+  int64_t row_stride;
+  int64_t batch_stride;
+};
+
+__device__ __forceinline__ const float* bias_ptr(const BiasRef& r, int b) {
+  int64_t row = r.row_ptr ? (int64_t)(*r.row_ptr) : 0;
+  return r.base + row * r.row_stride + (int64_t)b * r.batch_stride;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic cross-CTA GroupNorm statistics: every producer CTA writes one fp32 (sum, sumsq)
+// pair per group into partials[b][part][g][2]; the CTA that arrives last for sample b reduces
+// them in a FIXED order (so the result does not depend on which CTA was last) and writes
+// meanrstd[b][g] = (mean, rstd).  The counter resets itself for the next launch.
+// Call with one full warp; returns after the warp has (possibly) finalised.
+__device__ __forceinline__ void gn_publish_and_finalize_warp(
+    const float* my_sums /* lane 0: [G*2] */, float* partials, int* counters, float* meanrstd,
+    int b, int part, int nparts, int G, float count_per_group, float eps) {
+  const int lane = threadIdx.x & 31;
+  float* dst = partials + ((size_t)b * nparts + part) * G * 2;
+  int is_last = 0;
+  if (lane == 0) {
+    for (int i = 0; i < G * 2; ++i) __stcg(dst + i, my_sums[i]);
+    __threadfence();
+    int prev = atomicAdd(&counters[b], 1);
+    is_last = (prev == nparts - 1);
+  }
+  is_last = __shfl_sync(0xffffffffu, is_last, 0);
+  if (!is_last) return;
+  __threadfence();
+  const float* src = partials + (size_t)b * nparts * G * 2;
+  for (int g = 0; g < G; ++g) {
+    double s = 0.0, ss = 0.0;
+    for (int p = lane; p < nparts; p += 32) {
+      s += (double)__ldcg(src + ((size_t)p * G + g) * 2 + 0);
+      ss += (double)__ldcg(src + ((size_t)p * G + g) * 2 + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      double mean = s / (double)count_per_group;
+      double var = ss / (double)count_per_group - mean * mean;
+      if (var < 0.0) var = 0.0;
+      meanrstd[((size_t)b * G + g) * 2 + 0] = (float)mean;
+      meanrstd[((size_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  if (lane == 0) counters[b] = 0;
+}
+
+__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+// ----------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (error returned to the host) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t i = 0; i < (1u << 24); ++i) {
+    if (mbar_try_wait(bar, parity)) return;
+  }
+  printf("sdd: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
+         (int)threadIdx.x, bar, parity);
+  __trap();
+}
+
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// tcgen05
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// All previously issued MMAs of this thread arrive on the mbarrier when they complete.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> lane base+i).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B; 8-row
+// swizzle atoms 1024 B apart).  Field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+}  // namespace sdd

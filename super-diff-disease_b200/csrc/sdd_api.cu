@@ -1,0 +1,749 @@
+// C ABI (include/sdd_b200.h): handles, workspaces, launch orchestration, step-graph capture.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "unet_kernels.cuh"
+#include "update.cuh"
+
+namespace sdd {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+static thread_local int64_t g_launches = 0;  // kernels launched by this thread since last reset
+#define SDD_LAUNCH_CHECK()                 \
+  do {                                     \
+    ++::sdd::g_launches;                   \
+    SDD_CUDA(cudaGetLastError());          \
+  } while (0)
+
+// ------------------------------------------------------------------------------- device check
+static int device_check() {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return SDD_ENODEV;
+  }
+  cudaDeviceProp p;
+  e = cudaGetDeviceProperties(&p, dev);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    cudaGetLastError();
+    return SDD_ENODEV;
+  }
+  if (p.major != 10) {
+    set_error("device is sm_" + std::to_string(p.major) + std::to_string(p.minor) +
+              "; this library contains sm_100a code only (no fallback)");
+    return SDD_ENODEV;
+  }
+  return SDD_OK;
+}
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+// act bf16 [N][H][W][C]  ->  box (64 c, 8 w, 18 h, 1 n), 128-byte swizzle, zero fill out of bounds
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C) {
+  EncodeTiledFn enc = get_encode();
+  SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + 2), 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(act) failed: " + std::to_string((int)r));
+    return SDD_ECUDA;
+  }
+  return SDD_OK;
+}
+// wt bf16 [9 = kx*3+ky][Cout][Cin]  ->  box (64 ci, Cout, 3 taps)
+static int make_wt_map(CUtensorMap* m, const void* base, int Cout, int Cin) {
+  EncodeTiledFn enc = get_encode();
+  SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)Cout, 3};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(wt) failed: " + std::to_string((int)r));
+    return SDD_ECUDA;
+  }
+  return SDD_OK;
+}
+
+// ------------------------------------------------------------------------------- conv launchers
+struct GnScratch {
+  float* partials;
+  int* counters;
+  float* meanrstd;
+};
+
+static int conv_tc_init() {
+  static bool done = false;
+  if (done) return SDD_OK;
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<64>::kSmemBytes));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<128>::kSmemBytes));
+  done = true;
+  return SDD_OK;
+}
+
+static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, __nv_bfloat16* out, BiasRef bias,
+                          GnScratch gn, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
+  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
+  ConvTcArgs a;
+  a.out = out; a.bias = bias;
+  a.partials = gn.partials; a.counters = gn.counters; a.meanrstd = gn.meanrstd;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+  a.tiles_w = W / kTileW;
+  a.tiles_per_sample = (H / kTileH) * a.tiles_w;
+  a.num_tiles = B * a.tiles_per_sample;
+  int grid = std::min(a.num_tiles, num_sms());
+  SDD_TRY(conv_tc_init());
+  if (Cout == 64)
+    conv3x3_tc_kernel<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(tmA, tmB, a);
+  else
+    conv3x3_tc_kernel<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(tmA, tmB, a);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+static int launch_apply(__nv_bfloat16* act, const float* meanrstd, const float* gamma, const float* beta, int B,
+                        int H, int W, int C, cudaStream_t st) {
+  size_t nvec = (size_t)H * W * C / 8;
+  int blocks = (int)std::min<size_t>((nvec + 256 * 8 - 1) / (256 * 8), 4096);
+  if (blocks < 1) blocks = 1;
+  gn_silu_apply_kernel<<<dim3(blocks, B), 256, 0, st>>>(act, meanrstd, gamma, beta, H * W, C);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+}  // namespace sdd
+
+using namespace sdd;
+
+// =============================================================================== UNet handle
+namespace {
+
+struct BlockParams {
+  int cin, cout;
+  const float *gn1_w, *gn1_b, *conv1_w, *conv1_b, *gn2_w, *gn2_b, *conv2_w, *conv2_b, *temb_w, *temb_b;
+  __nv_bfloat16 *conv1_wt, *conv2_wt;  // bf16 [kx][ky][Cout][Cin] (tensor-core convs only)
+  CUtensorMap tm_w1, tm_w2;
+};
+
+constexpr int kBiasRow = 64 + 128 + 128 + 64 + 1;  // 385: per-block (conv2 bias + time_emb) rows
+constexpr int kBiasOff[5] = {0, 64, 192, 320, 384};
+constexpr int kBlkCin[5] = {1, 64, 128, 128, 64};
+constexpr int kBlkCout[5] = {64, 128, 128, 64, 1};
+constexpr int kTimeDim = 256;
+
+struct Workspace {
+  int cap_b = 0, H = 0, W = 0;  // chunk capacity and image size the buffers were built for
+  int64_t generation = 0;       // bumped on every (re)allocation; captured graphs check it
+  __nv_bfloat16* act[2] = {nullptr, nullptr};
+  float* e1 = nullptr;
+  float* partials = nullptr;
+  int* counters = nullptr;
+  float* meanrstd = nullptr;  // 10 x [cap_b][4][2]
+  float* xstats = nullptr;    // [cap_b][2] (used when the caller has no stats of x)
+  CUtensorMap tm_act[2][2];   // [buffer][Cin == 128]
+  void release() {
+    cudaFree(act[0]); cudaFree(act[1]); cudaFree(e1); cudaFree(partials); cudaFree(counters);
+    cudaFree(meanrstd); cudaFree(xstats);
+    int64_t g = generation;
+    *this = Workspace();
+    generation = g;
+  }
+};
+
+}  // namespace
+
+struct sdd_unet {
+  float* params = nullptr;  // one arena holding all 54 fp32 tensors
+  __nv_bfloat16* wt = nullptr;
+  float* freq = nullptr;    // [128]
+  const float *time_w1, *time_b1, *time_w2, *time_b2;
+  BlockParams blk[5];
+  Workspace ws;
+  // scratch for per-call time embeddings (forward with explicit t)
+  int tscratch_n = 0;
+  float *t_emb0 = nullptr, *t_h1 = nullptr, *t_emb = nullptr, *t_bias = nullptr;
+};
+
+namespace {
+
+int chunk_for(int B, int H, int W) {
+  if (const char* e = getenv("SDD_CHUNK")) {
+    int c = atoi(e);
+    if (c > 0) return std::min(c, B);
+  }
+  // keep the two ping-pong activation tensors of a chunk inside L2 (~126 MB): 2 * c * H*W*128*2 B <= 96 MB
+  size_t per_sample = (size_t)H * W * 128 * 2 * 2;
+  int c = (int)std::max<size_t>(1, (96u << 20) / per_sample);
+  return std::min(c, B);
+}
+
+int ensure_workspace(sdd_unet* u, int B, int H, int W) {
+  int need = chunk_for(B, H, W);
+  Workspace& ws = u->ws;
+  if (ws.cap_b >= need && ws.H == H && ws.W == W) return SDD_OK;
+  ws.release();
+  size_t act_bytes = (size_t)need * H * W * 128 * sizeof(__nv_bfloat16);
+  SDD_CUDA(cudaMalloc(&ws.act[0], act_bytes));
+  SDD_CUDA(cudaMalloc(&ws.act[1], act_bytes));
+  SDD_CUDA(cudaMalloc(&ws.e1, (size_t)need * H * W * sizeof(float)));
+  int parts = std::max({(H / kTileH) * (W / kTileW), ((H + kCinTH - 1) / kCinTH) * ((W + kCinTW - 1) / kCinTW),
+                        kStatsBlocks});
+  SDD_CUDA(cudaMalloc(&ws.partials, (size_t)need * parts * 8 * sizeof(float)));
+  SDD_CUDA(cudaMalloc(&ws.counters, (size_t)need * sizeof(int)));
+  SDD_CUDA(cudaMemset(ws.counters, 0, (size_t)need * sizeof(int)));
+  SDD_CUDA(cudaMalloc(&ws.meanrstd, (size_t)10 * need * 8 * sizeof(float)));
+  SDD_CUDA(cudaMalloc(&ws.xstats, (size_t)need * 2 * sizeof(float)));
+  for (int bi = 0; bi < 2; ++bi) {
+    SDD_TRY(make_act_map(&ws.tm_act[bi][0], ws.act[bi], need, H, W, 64));
+    SDD_TRY(make_act_map(&ws.tm_act[bi][1], ws.act[bi], need, H, W, 128));
+  }
+  ws.cap_b = need; ws.H = H; ws.W = W;
+  ++ws.generation;
+  return SDD_OK;
+}
+
+// rows[n][385] = conv2.bias + time_emb(time_mlp(t_i)) for every block (unet.py:33, :58)
+int time_bias_rows(sdd_unet* u, const int64_t* t_dev, int n, float* emb0, float* h1, float* emb, float* rows,
+                   cudaStream_t st) {
+  sinusoid_kernel<<<n, 128, 0, st>>>(t_dev, u->freq, emb0, n, kTimeDim / 2);
+  SDD_LAUNCH_CHECK();
+  auto lin = [&](const float* x, const float* Wm, const float* b, const float* extra, float* y, int K, int O,
+                 int64_t ldy, int silu) {
+    int warps = n * O;
+    int blocks = (warps * 32 + 255) / 256;
+    linear_kernel<<<blocks, 256, 0, st>>>(x, Wm, b, extra, y, n, K, O, ldy, silu);
+  };
+  lin(emb0, u->time_w1, u->time_b1, nullptr, h1, kTimeDim, 4 * kTimeDim, 4 * kTimeDim, 1);
+  SDD_LAUNCH_CHECK();
+  lin(h1, u->time_w2, u->time_b2, nullptr, emb, 4 * kTimeDim, kTimeDim, kTimeDim, 0);
+  SDD_LAUNCH_CHECK();
+  for (int i = 0; i < 5; ++i) {
+    lin(emb, u->blk[i].temb_w, u->blk[i].temb_b, u->blk[i].conv2_b, rows + kBiasOff[i], kTimeDim, kBlkCout[i],
+        kBiasRow, 0);
+    SDD_LAUNCH_CHECK();
+  }
+  return SDD_OK;
+}
+
+// One UNet forward over B samples, chunked so that a chunk's activations stay L2-resident.
+// xstats: (mean, rstd) of each x sample for the first GroupNorm(1,1), or nullptr to compute here.
+// tb: per-block bias rows; tb.base points at column 0 of the 385-wide row.
+int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef tb, float* eps_out, int B, int H,
+                      int W, cudaStream_t st) {
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
+  Workspace& ws = u->ws;
+  SDD_CHECK(ws.cap_b >= 1 && ws.H == H && ws.W == W, "workspace not prepared");
+  const int HW = H * W;
+  const int chunk = ws.cap_b;
+  const dim3 egrid((W + kCinTW - 1) / kCinTW, (H + kCinTH - 1) / kCinTH, 1);
+  const int tiles_ps = (H / kTileH) * (W / kTileW);
+  (void)tiles_ps;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    const int nb = std::min(chunk, B - b0);
+    const float* xc = x + (size_t)b0 * HW;
+    auto mr = [&](int i) { return ws.meanrstd + (size_t)i * ws.cap_b * 8; };
+    auto gn = [&](int i) { return GnScratch{ws.partials, ws.counters, mr(i)}; };
+    auto bias_const = [&](const float* p) { return BiasRef{p, nullptr, 0, 0}; };
+    auto bias_time = [&](int blk) {
+      return BiasRef{tb.base + kBiasOff[blk] + (int64_t)b0 * tb.batch_stride, tb.row_ptr, tb.row_stride,
+                     tb.batch_stride};
+    };
+    const float* xs = xstats ? xstats + (size_t)b0 * 2 : nullptr;
+    if (!xs) {
+      stats_x_kernel<<<dim3(kStatsBlocks, nb), 256, 0, st>>>(xc, HW, ws.partials, ws.counters, ws.xstats);
+      SDD_LAUNCH_CHECK();
+      xs = ws.xstats;
+    }
+    dim3 eg = egrid; eg.z = nb;
+    // downs.0: GN(1,1)+SiLU fused into the 1->64 conv; result raw in act[0], stats -> mr(0)
+    const BlockParams& d0 = u->blk[0];
+    conv_in_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
+                                       ws.partials, ws.counters, mr(0), H, W);
+    SDD_LAUNCH_CHECK();
+    SDD_TRY(launch_apply(ws.act[0], mr(0), d0.gn2_w, d0.gn2_b, nb, H, W, 64, st));
+    SDD_TRY(launch_conv_tc(ws.tm_act[0][0], d0.tm_w2, ws.act[1], bias_time(0), gn(1), nb, H, W, 64, 64, st));
+    // downs.1, mid, ups.0: two tensor-core convs each, ping-ponging act[1] -> act[0] -> act[1]
+    int cur = 1, gi = 1;
+    for (int bi = 1; bi <= 3; ++bi) {
+      const BlockParams& p = u->blk[bi];
+      SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn1_w, p.gn1_b, nb, H, W, p.cin, st));
+      SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cin == 128], p.tm_w1, ws.act[cur ^ 1], bias_const(p.conv1_b),
+                             gn(gi + 1), nb, H, W, p.cin, p.cout, st));
+      cur ^= 1; ++gi;
+      SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn2_w, p.gn2_b, nb, H, W, p.cout, st));
+      SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cout == 128], p.tm_w2, ws.act[cur ^ 1], bias_time(bi), gn(gi + 1), nb,
+                             H, W, p.cout, p.cout, st));
+      cur ^= 1; ++gi;
+    }
+    // ups.1: GN(4,64)+SiLU apply, 64->1 conv, then GN(1,1)+SiLU fused into the 1->1 conv (+ time bias)
+    const BlockParams& u1 = u->blk[4];
+    SDD_TRY(launch_apply(ws.act[cur], mr(gi), u1.gn1_w, u1.gn1_b, nb, H, W, 64, st));
+    conv_out1_kernel<<<eg, 256, 0, st>>>(ws.act[cur], u1.conv1_w, u1.conv1_b, ws.e1, ws.partials, ws.counters,
+                                         mr(gi + 1), H, W);
+    SDD_LAUNCH_CHECK();
+    conv_out2_kernel<<<eg, 256, 0, st>>>(ws.e1, mr(gi + 1), u1.gn2_w, u1.gn2_b, u1.conv2_w, bias_time(4),
+                                         eps_out + (size_t)b0 * HW, H, W);
+    SDD_LAUNCH_CHECK();
+  }
+  return SDD_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int sdd_abi_version(void) { return SDD_ABI_VERSION; }
+const char* sdd_last_error(void) { return g_err.c_str(); }
+int sdd_device_check(void) { return device_check(); }
+
+int sdd_unet_create(sdd_unet_t** out, const float* const* tensors, int num_tensors, void* stream) {
+  SDD_CHECK(out && tensors, "null argument");
+  SDD_CHECK(num_tensors == SDD_UNET_NUM_TENSORS, "expected the 54 tensors of the reference UNet state_dict");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  // element counts in state_dict order
+  std::vector<size_t> n;
+  n.insert(n.end(), {(size_t)1024 * 256, 1024, (size_t)256 * 1024, 256});
+  for (int i = 0; i < 5; ++i) {
+    size_t ci = kBlkCin[i], co = kBlkCout[i];
+    n.insert(n.end(), {ci, ci, co * ci * 9, co, co, co, co * co * 9, co, co * 256, co});
+  }
+  size_t total = 0;
+  std::vector<size_t> off(n.size());
+  for (size_t i = 0; i < n.size(); ++i) { off[i] = total; total += (n[i] + 3) & ~(size_t)3; }
+  sdd_unet* u = new sdd_unet();
+  auto fail = [&](int code) { sdd_unet_destroy(u); return code; };
+  if (cudaMalloc(&u->params, total * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc(params) failed"); return fail(SDD_ENOMEM); }
+  for (size_t i = 0; i < n.size(); ++i) {
+    if (cudaMemcpyAsync(u->params + off[i], tensors[i], n[i] * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("copying state-dict tensor " + std::to_string(i) + " failed (device pointers expected)");
+      return fail(SDD_ECUDA);
+    }
+  }
+  const float* P = u->params;
+  u->time_w1 = P + off[0]; u->time_b1 = P + off[1]; u->time_w2 = P + off[2]; u->time_b2 = P + off[3];
+  size_t wt_elems = 0;
+  for (int i = 0; i < 5; ++i) {
+    BlockParams& b = u->blk[i];
+    const size_t* o = &off[4 + 10 * i];
+    b.cin = kBlkCin[i]; b.cout = kBlkCout[i];
+    b.gn1_w = P + o[0]; b.gn1_b = P + o[1]; b.conv1_w = P + o[2]; b.conv1_b = P + o[3];
+    b.gn2_w = P + o[4]; b.gn2_b = P + o[5]; b.conv2_w = P + o[6]; b.conv2_b = P + o[7];
+    b.temb_w = P + o[8]; b.temb_b = P + o[9];
+    b.conv1_wt = b.conv2_wt = nullptr;
+    if (b.cin >= 64 && b.cout >= 64) wt_elems += (size_t)9 * b.cin * b.cout;
+    if (b.cout >= 64) wt_elems += (size_t)9 * b.cout * b.cout;
+  }
+  if (cudaMalloc(&u->wt, wt_elems * sizeof(__nv_bfloat16)) != cudaSuccess) { set_error("cudaMalloc(wt) failed"); return fail(SDD_ENOMEM); }
+  __nv_bfloat16* wp = u->wt;
+  for (int i = 0; i < 5; ++i) {
+    BlockParams& b = u->blk[i];
+    auto conv = [&](const float* w, int cout, int cin, __nv_bfloat16** dst, CUtensorMap* tm) -> int {
+      int total_w = 9 * cout * cin;
+      conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wp, cout, cin);
+      SDD_LAUNCH_CHECK();
+      *dst = wp;
+      SDD_TRY(make_wt_map(tm, wp, cout, cin));
+      wp += total_w;
+      return SDD_OK;
+    };
+    if (b.cin >= 64 && b.cout >= 64) { int r = conv(b.conv1_w, b.cout, b.cin, &b.conv1_wt, &b.tm_w1); if (r) return fail(r); }
+    if (b.cout >= 64) { int r = conv(b.conv2_w, b.cout, b.cout, &b.conv2_wt, &b.tm_w2); if (r) return fail(r); }
+  }
+  // sinusoid frequencies exactly as unet.py:14 evaluates them in fp32
+  float hf[kTimeDim / 2];
+  const float step = -(std::log(10000.0f) / (float)(kTimeDim / 2 - 1));
+  for (int k = 0; k < kTimeDim / 2; ++k) hf[k] = std::exp((float)k * step);
+  if (cudaMalloc(&u->freq, sizeof(hf)) != cudaSuccess) { set_error("cudaMalloc(freq) failed"); return fail(SDD_ENOMEM); }
+  if (cudaMemcpyAsync(u->freq, hf, sizeof(hf), cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("freq upload failed"); return fail(SDD_ECUDA); }
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("sync after unet_create failed"); return fail(SDD_ECUDA); }
+  *out = u;
+  return SDD_OK;
+}
+
+int sdd_unet_destroy(sdd_unet_t* u) {
+  if (!u) return SDD_OK;
+  u->ws.release();
+  cudaFree(u->params); cudaFree(u->wt); cudaFree(u->freq);
+  cudaFree(u->t_emb0); cudaFree(u->t_h1); cudaFree(u->t_emb); cudaFree(u->t_bias);
+  delete u;
+  return SDD_OK;
+}
+
+int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps_out, int B, int H, int W,
+                     void* stream) {
+  SDD_CHECK(u && x && t && eps_out, "null argument");
+  SDD_CHECK(B >= 1 && H >= 16 && W >= 8, "bad shape");
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  SDD_TRY(ensure_workspace(u, B, H, W));
+  if (u->tscratch_n < B) {
+    cudaFree(u->t_emb0); cudaFree(u->t_h1); cudaFree(u->t_emb); cudaFree(u->t_bias);
+    u->t_emb0 = u->t_h1 = u->t_emb = u->t_bias = nullptr; u->tscratch_n = 0;
+    SDD_CUDA(cudaMalloc(&u->t_emb0, (size_t)B * kTimeDim * sizeof(float)));
+    SDD_CUDA(cudaMalloc(&u->t_h1, (size_t)B * 4 * kTimeDim * sizeof(float)));
+    SDD_CUDA(cudaMalloc(&u->t_emb, (size_t)B * kTimeDim * sizeof(float)));
+    SDD_CUDA(cudaMalloc(&u->t_bias, (size_t)B * kBiasRow * sizeof(float)));
+    u->tscratch_n = B;
+  }
+  SDD_TRY(time_bias_rows(u, t, B, u->t_emb0, u->t_h1, u->t_emb, u->t_bias, st));
+  BiasRef tb{u->t_bias, nullptr, 0, kBiasRow};
+  return unet_forward_impl(u, x, nullptr, tb, eps_out, B, H, W, st);
+}
+
+// ------------------------------------------------------------------------------- fused update
+size_t sdd_superpose_update_workspace(int B, int D, int M) { return update_workspace_bytes(B, D, M); }
+
+}  // extern "C"
+
+namespace sdd {
+int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st) {
+  SDD_CHECK(a.M >= 1 && a.M <= kMaxModels, "1 <= M <= 4");
+  SDD_CHECK(a.D % 4 == 0 && a.D > 0 && a.B > 0, "D must be a positive multiple of 4");
+  a.nblk = update_blocks_per_sample(a.D);
+  size_t part = (size_t)a.B * a.nblk * kPartialsPerBlock * sizeof(float);
+  part = (part + 255) & ~(size_t)255;
+  a.partials = reinterpret_cast<float*>(workspace);
+  a.counters = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + part);
+  dim3 grid(a.nblk, a.B);
+  switch (a.M) {
+    case 1: superpose_update_kernel<1><<<grid, kUpdThreads, 0, st>>>(a); break;
+    case 2: superpose_update_kernel<2><<<grid, kUpdThreads, 0, st>>>(a); break;
+    case 3: superpose_update_kernel<3><<<grid, kUpdThreads, 0, st>>>(a); break;
+    default: superpose_update_kernel<4><<<grid, kUpdThreads, 0, st>>>(a); break;
+  }
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+__global__ void philox_normal_kernel(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw) {
+  const int nq = D >> 2;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * nq) return;
+  int b = (int)(i / nq), q = (int)(i % nq);
+  float4 v = philox_normal4(seed, (uint32_t)q, (uint32_t)(sample_offset + b), (uint32_t)draw);
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+__global__ void copy_f32_kernel(float* dst, const float* src, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+}  // namespace sdd
+
+extern "C" {
+
+int sdd_superpose_update(const float* x_in, float* x_out, const float* eps, const float* noise, const float* logq,
+                         float* logq_out, float* kappa_out, float* xstats_out, int B, int D, int M, float alpha,
+                         float alpha_bar, float beta, float temperature, const float* bias, uint64_t seed,
+                         int64_t sample_offset, int draw_index, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  SDD_CHECK(x_in && x_out && eps && logq && logq_out && workspace, "null argument");
+  SDD_CHECK(workspace_bytes >= update_workspace_bytes(B, D, M), "workspace too small");
+  SDD_TRY(device_check());
+  UpdateArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_in = x_in; a.x_out = x_out; a.eps = eps; a.noise = noise; a.noise_step_stride = 0;
+  a.logq = logq; a.logq_out = logq_out; a.kappa_out = kappa_out; a.xstats_out = xstats_out;
+  a.sc.alpha = alpha; a.sc.alpha_bar = alpha_bar; a.sc.beta = beta;
+  a.sc.draw_index = noise ? 0 : draw_index;
+  a.temperature = temperature; a.bias = bias; a.seed = seed; a.sample_offset = sample_offset;
+  a.B = B; a.D = D; a.M = M;
+  return launch_superpose_update(a, workspace, (cudaStream_t)stream);
+}
+
+int sdd_philox_normal(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw_index, void* stream) {
+  SDD_CHECK(out && B > 0 && D > 0 && D % 4 == 0, "bad argument");
+  SDD_TRY(device_check());
+  size_t n = (size_t)B * (D / 4);
+  philox_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, B, D, seed, sample_offset,
+                                                                                     draw_index);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+}  // extern "C"
+
+// =============================================================================== sampler
+struct sdd_sampler {
+  int M = 0, T = 0, B = 0, H = 0, W = 0, D = 0;
+  sdd_unet* models[kMaxModels] = {nullptr, nullptr, nullptr, nullptr};
+  float* tables[kMaxModels] = {nullptr, nullptr, nullptr, nullptr};  // [T][385], row = loop iteration
+  StepScalars* sched = nullptr;  // [T], row = loop iteration (t = T-1-row)
+  int* step = nullptr;
+  float *x = nullptr, *eps = nullptr, *logq = nullptr, *xstats = nullptr;
+  void* upd_ws = nullptr;
+  float* stat_partials = nullptr; int* stat_counters = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  sdd_sample_args captured;  // arguments baked into `exec`
+  int64_t captured_gen[kMaxModels] = {0, 0, 0, 0};
+  int64_t launches_per_step = 0, launches_fixed = 0;
+};
+
+namespace {
+
+int enqueue_step(sdd_sampler* s, const sdd_sample_args& ar, cudaStream_t st) {
+  for (int m = 0; m < s->M; ++m) {
+    BiasRef tb{s->tables[m], s->step, kBiasRow, 0};
+    SDD_TRY(unet_forward_impl(s->models[m], s->x, s->xstats, tb, s->eps + (size_t)m * s->B * s->D, s->B, s->H, s->W,
+                              st));
+  }
+  UpdateArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_in = s->x; a.x_out = s->x; a.eps = s->eps;
+  a.noise = ar.noise_stack; a.noise_step_stride = (int64_t)s->B * s->D;
+  a.logq = s->logq; a.logq_out = s->logq; a.kappa_out = nullptr; a.xstats_out = s->xstats;
+  a.kappa_traj = ar.kappa_traj; a.logq_traj = ar.logq_traj;
+  a.table = s->sched; a.step_ptr = s->step;
+  a.temperature = ar.temperature; a.bias = ar.bias; a.seed = ar.seed; a.sample_offset = ar.sample_offset;
+  a.B = s->B; a.D = s->D; a.M = s->M;
+  SDD_TRY(launch_superpose_update(a, s->upd_ws, st));
+  advance_step_kernel<<<1, 1, 0, st>>>(s->step);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+bool same_args(const sdd_sample_args& a, const sdd_sample_args& b) {
+  return a.noise_stack == b.noise_stack && a.seed == b.seed && a.sample_offset == b.sample_offset &&
+         a.temperature == b.temperature && a.bias == b.bias && a.kappa_traj == b.kappa_traj &&
+         a.logq_traj == b.logq_traj;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, const float* alphas_host,
+                       const float* alpha_bars_host, const float* betas_host, int T, int B, int H, int W,
+                       void* stream) {
+  SDD_CHECK(out && models && alphas_host && alpha_bars_host && betas_host, "null argument");
+  SDD_CHECK(M >= 1 && M <= kMaxModels, "1 <= M <= 4");
+  SDD_CHECK(T >= 1 && B >= 1, "bad T or B");
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0 && H >= 16 && W >= 8, "H must be a multiple of 16 and W of 8");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  sdd_sampler* s = new sdd_sampler();
+  s->M = M; s->T = T; s->B = B; s->H = H; s->W = W; s->D = H * W;
+  auto fail = [&](int code) { sdd_sampler_destroy(s); return code; };
+#define S_CUDA(expr) do { if ((expr) != cudaSuccess) { set_error(#expr " failed"); return fail(SDD_ECUDA); } } while (0)
+  const size_t BD = (size_t)B * s->D;
+  S_CUDA(cudaMalloc(&s->x, BD * sizeof(float)));
+  S_CUDA(cudaMalloc(&s->eps, (size_t)M * BD * sizeof(float)));
+  S_CUDA(cudaMalloc(&s->logq, (size_t)B * M * sizeof(float)));
+  S_CUDA(cudaMalloc(&s->xstats, (size_t)B * 2 * sizeof(float)));
+  S_CUDA(cudaMalloc(&s->step, sizeof(int)));
+  size_t uw = update_workspace_bytes(B, s->D, M);
+  S_CUDA(cudaMalloc(&s->upd_ws, uw));
+  S_CUDA(cudaMemsetAsync(s->upd_ws, 0, uw, st));
+  S_CUDA(cudaMalloc(&s->stat_partials, (size_t)B * kStatsBlocks * 2 * sizeof(float)));
+  S_CUDA(cudaMalloc(&s->stat_counters, (size_t)B * sizeof(int)));
+  S_CUDA(cudaMemsetAsync(s->stat_counters, 0, (size_t)B * sizeof(int), st));
+  // schedule rows indexed by loop iteration: row k <-> t = T-1-k (ddpm.py:34)
+  std::vector<StepScalars> sc(T);
+  std::vector<int64_t> trev(T);
+  for (int k = 0; k < T; ++k) {
+    int t = T - 1 - k;
+    sc[k].alpha = alphas_host[t]; sc[k].alpha_bar = alpha_bars_host[t]; sc[k].beta = betas_host[t];
+    sc[k].draw_index = t > 0 ? k + 1 : -1;  // ddpm.py:36: no noise at t == 0
+    trev[k] = t;
+  }
+  S_CUDA(cudaMalloc(&s->sched, T * sizeof(StepScalars)));
+  S_CUDA(cudaMemcpyAsync(s->sched, sc.data(), T * sizeof(StepScalars), cudaMemcpyHostToDevice, st));
+  int64_t* t_dev = nullptr;
+  float *emb0 = nullptr, *h1 = nullptr, *emb = nullptr;
+  S_CUDA(cudaMalloc(&t_dev, T * sizeof(int64_t)));
+  S_CUDA(cudaMemcpyAsync(t_dev, trev.data(), T * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+  S_CUDA(cudaMalloc(&emb0, (size_t)T * kTimeDim * sizeof(float)));
+  S_CUDA(cudaMalloc(&h1, (size_t)T * 4 * kTimeDim * sizeof(float)));
+  S_CUDA(cudaMalloc(&emb, (size_t)T * kTimeDim * sizeof(float)));
+  int rc = SDD_OK;
+  for (int m = 0; m < M && rc == SDD_OK; ++m) {
+    s->models[m] = models[m];
+    if (!models[m]) { set_error("null model"); rc = SDD_EINVAL; break; }
+    if (cudaMalloc(&s->tables[m], (size_t)T * kBiasRow * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc(table) failed"); rc = SDD_ENOMEM; break; }
+    // every timestep's (conv2 bias + time embedding) rows, once: t is batch-uniform in sampling (ddpm.py:35)
+    rc = time_bias_rows(models[m], t_dev, T, emb0, h1, emb, s->tables[m], st);
+    if (rc == SDD_OK) rc = ensure_workspace(models[m], B, H, W);
+  }
+  cudaError_t se = cudaStreamSynchronize(st);
+  cudaFree(t_dev); cudaFree(emb0); cudaFree(h1); cudaFree(emb);
+  if (rc != SDD_OK) return fail(rc);
+  if (se != cudaSuccess) { set_error(std::string("sampler_create sync: ") + cudaGetErrorString(se)); return fail(SDD_ECUDA); }
+#undef S_CUDA
+  *out = s;
+  return SDD_OK;
+}
+
+int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream) {
+  SDD_CHECK(s && args && args->x_out, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t BD = (size_t)s->B * s->D;
+  const int64_t l0 = g_launches;
+  // --- x_T, logq = 0, step = 0, GN(1,1) stats of x_T
+  SDD_CUDA(cudaMemsetAsync(s->step, 0, sizeof(int), st));
+  SDD_CUDA(cudaMemsetAsync(s->logq, 0, (size_t)s->B * s->M * sizeof(float), st));
+  if (args->logq_traj) SDD_CUDA(cudaMemsetAsync(args->logq_traj, 0, (size_t)s->B * s->M * sizeof(float), st));
+  if (args->noise_stack) {
+    SDD_CUDA(cudaMemcpyAsync(s->x, args->noise_stack, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    size_t n = BD / 4;
+    philox_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->x, s->B, s->D, args->seed,
+                                                                      args->sample_offset, 0);
+    SDD_LAUNCH_CHECK();
+  }
+  stats_x_kernel<<<dim3(kStatsBlocks, s->B), 256, 0, st>>>(s->x, s->D, s->stat_partials, s->stat_counters, s->xstats);
+  SDD_LAUNCH_CHECK();
+  const int64_t l1 = g_launches;
+  for (int m = 0; m < s->M; ++m) SDD_TRY(ensure_workspace(s->models[m], s->B, s->H, s->W));
+  // --- T steps.  Step 0 always runs eagerly (so every kernel is loaded before a capture begins).
+  {
+    const int64_t lk = g_launches;
+    SDD_TRY(enqueue_step(s, *args, st));
+    s->launches_per_step = g_launches - lk;
+  }
+  if (args->use_graph && s->T > 1) {
+    bool stale = !s->exec || !same_args(s->captured, *args);
+    for (int m = 0; m < s->M; ++m) stale = stale || s->captured_gen[m] != s->models[m]->ws.generation;
+    if (stale) {
+      if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      SDD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_step(s, *args, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (rc != SDD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      SDD_CUDA(ce);
+      ce = cudaGraphInstantiate(&s->exec, graph, 0);
+      cudaGraphDestroy(graph);
+      SDD_CUDA(ce);
+      s->captured = *args;
+      for (int m = 0; m < s->M; ++m) s->captured_gen[m] = s->models[m]->ws.generation;
+    }
+    for (int k = 1; k < s->T; ++k) SDD_CUDA(cudaGraphLaunch(s->exec, st));
+  } else {
+    for (int k = 1; k < s->T; ++k) SDD_TRY(enqueue_step(s, *args, st));
+  }
+  s->launches_fixed = (l1 - l0) + 1;
+  int blocks = (int)std::min<size_t>((BD + 255) / 256, 2048);
+  copy_f32_kernel<<<blocks, 256, 0, st>>>(args->x_out, s->x, BD);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+int64_t sdd_sampler_launches_per_run(const sdd_sampler_t* s) {
+  return s ? s->launches_fixed + (int64_t)s->T * s->launches_per_step : 0;
+}
+
+int sdd_sampler_destroy(sdd_sampler_t* s) {
+  if (!s) return SDD_OK;
+  if (s->exec) cudaGraphExecDestroy(s->exec);
+  for (int m = 0; m < kMaxModels; ++m) cudaFree(s->tables[m]);
+  cudaFree(s->sched); cudaFree(s->step); cudaFree(s->x); cudaFree(s->eps); cudaFree(s->logq); cudaFree(s->xstats);
+  cudaFree(s->upd_ws); cudaFree(s->stat_partials); cudaFree(s->stat_counters);
+  delete s;
+  return SDD_OK;
+}
+
+// ------------------------------------------------------------------------------- operator entry points
+int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t bias_batch_stride, void* out,
+                     float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, int impl, void* stream) {
+  SDD_CHECK(act && w && bias && out, "null argument");
+  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "Cin, Cout must be 64 or 128");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* wt = nullptr;
+  float* partials = nullptr; int* counters = nullptr; float* mr = nullptr;
+  const int total_w = 9 * Cout * Cin;
+  SDD_CUDA(cudaMalloc(&wt, (size_t)total_w * sizeof(__nv_bfloat16)));
+  conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
+  ++g_launches;
+  BiasRef br{bias, nullptr, 0, bias_batch_stride};
+  int rc = SDD_OK;
+  if (impl == 0) {
+    const int tiles_ps = (H / kTileH) * (W / kTileW);
+    CUtensorMap tmA, tmB;
+    rc = (H % kTileH == 0 && W % kTileW == 0) ? SDD_OK : SDD_EINVAL;
+    if (rc != SDD_OK) set_error("H must be a multiple of 16 and W a multiple of 8");
+    if (rc == SDD_OK && cudaMalloc(&partials, (size_t)B * tiles_ps * 8 * sizeof(float)) != cudaSuccess) rc = SDD_ENOMEM;
+    if (rc == SDD_OK && cudaMalloc(&counters, (size_t)B * sizeof(int)) != cudaSuccess) rc = SDD_ENOMEM;
+    if (rc == SDD_OK && cudaMalloc(&mr, (size_t)B * 8 * sizeof(float)) != cudaSuccess) rc = SDD_ENOMEM;
+    if (rc == SDD_OK) cudaMemsetAsync(counters, 0, (size_t)B * sizeof(int), st);
+    if (rc == SDD_OK) rc = make_act_map(&tmA, act, B, H, W, Cin);
+    if (rc == SDD_OK) rc = make_wt_map(&tmB, wt, Cout, Cin);
+    if (rc == SDD_OK)
+      rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
+    if (rc == SDD_OK && gn_meanrstd)
+      cudaMemcpyAsync(gn_meanrstd, mr, (size_t)B * 8 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  } else {
+    size_t total = (size_t)B * H * W * Cout;
+    conv3x3_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)act, wt, br,
+                                                                        (__nv_bfloat16*)out, B, H, W, Cin, Cout);
+    ++g_launches;
+    if (gn_meanrstd) {
+      gn_stats_nhwc_kernel<<<B * 4, 256, 0, st>>>((const __nv_bfloat16*)out, gn_meanrstd, H * W, Cout);
+      ++g_launches;
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr);
+  if (rc != SDD_OK) return rc;
+  if (e != cudaSuccess) { set_error(std::string("conv3x3: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string("conv3x3 launch: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
+  return SDD_OK;
+}
+
+int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta, int B, int H, int W,
+                      int C, void* stream) {
+  SDD_CHECK(act && meanrstd && gamma && beta, "null argument");
+  SDD_CHECK(C == 64 || C == 128, "C must be 64 or 128");
+  SDD_TRY(device_check());
+  return launch_apply((__nv_bfloat16*)act, meanrstd, gamma, beta, B, H, W, C, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,358 @@
+// CUDA-core kernels of the UNet forward (everything except the 64/128-channel 3x3 convs):
+// time-embedding MLP, GroupNorm statistics / apply, the 1->64, 64->1 and 1->1 edge convs,
+// weight re-layout, and a plain CUDA-core 3x3 conv used only to cross-check the tcgen05 kernel.
+// Reference semantics: /root/reference/src/models/unet.py:11-16, :21-34, :40-45, :57-65.
+#pragma once
+#include "common.cuh"
+
+namespace sdd {
+
+constexpr float kGnEps = 1e-5f;
+
+// ------------------------------------------------------------------ time embedding (unet.py:11-16,40-45)
+// emb[i][k] = sin(t_i * f_k), emb[i][k+half] = cos(t_i * f_k); t_i = t[i] or i when t == nullptr.
+__global__ void sinusoid_kernel(const int64_t* t, const float* freq, float* emb, int n, int half) {
+  int i = blockIdx.x;
+  for (int k = threadIdx.x; k < half; k += blockDim.x) {
+    float tv = t ? (float)t[i] : (float)i;
+    float arg = tv * freq[k];
+    emb[(size_t)i * 2 * half + k] = sinf(arg);
+    emb[(size_t)i * 2 * half + half + k] = cosf(arg);
+  }
+}
+
+// y[i, o] = act(sum_k x[i,k] W[o,k] + b[o]) + extra[o]; one warp per (i, o).
+__global__ void linear_kernel(const float* __restrict__ x, const float* __restrict__ W, const float* __restrict__ b,
+                              const float* __restrict__ extra, float* __restrict__ y, int n, int K, int O,
+                              int64_t ldy, int silu) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= n * O) return;
+  int i = warp / O, o = warp % O;
+  const float* xr = x + (size_t)i * K;
+  const float* wr = W + (size_t)o * K;
+  float acc = 0.0f;
+  for (int k = lane; k < K; k += 32) acc = fmaf(xr[k], wr[k], acc);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+  if (lane == 0) {
+    float v = acc + b[o];
+    if (silu) v = v / (1.0f + expf(-v));
+    if (extra) v += extra[o];
+    y[(size_t)i * ldy + o] = v;
+  }
+}
+
+// ------------------------------------------------------------------ weight re-layout
+// fp32 [Cout][Cin][3][3] -> bf16 [kx][ky][Cout][Cin] (K-major rows for the UMMA B operand).
+__global__ void conv_weight_to_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout,
+                                           int Cin) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int total = 9 * Cout * Cin;
+  if (idx >= total) return;
+  int ci = idx % Cin;
+  int co = (idx / Cin) % Cout;
+  int tap = idx / (Cin * Cout);  // kx*3 + ky
+  int kx = tap / 3, ky = tap % 3;
+  o[idx] = __float2bfloat16_rn(w[(((size_t)co * Cin + ci) * 3 + ky) * 3 + kx]);
+}
+
+// ------------------------------------------------------------------ GroupNorm(1,1) statistics of x
+constexpr int kStatsBlocks = 16;  // per sample; fixed => shard-invariant reduction order
+__global__ void __launch_bounds__(256) stats_x_kernel(const float* __restrict__ x, int D, float* partials,
+                                                      int* counters, float* meanrstd) {
+  const int b = blockIdx.y, blk = blockIdx.x, tid = threadIdx.x;
+  const int nq = D >> 2;
+  const int per = (nq + gridDim.x - 1) / gridDim.x;
+  const int q0 = blk * per, q1 = min(nq, q0 + per);
+  const float4* x4 = reinterpret_cast<const float4*>(x + (size_t)b * D);
+  float s = 0.f, ss = 0.f;
+  for (int q = q0 + tid; q < q1; q += 256) {
+    float4 v = x4[q];
+    s += (v.x + v.y) + (v.z + v.w);
+    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+  }
+  __shared__ float red[8][2];
+  __shared__ float sums[2];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+  if ((tid & 31) == 0) { red[tid >> 5][0] = s; red[tid >> 5][1] = ss; }
+  __syncthreads();
+  if (tid < 32) {
+    if (tid == 0) {
+      float a = 0.f, c = 0.f;
+      for (int w = 0; w < 8; ++w) { a += red[w][0]; c += red[w][1]; }
+      sums[0] = a; sums[1] = c;
+    }
+    __syncwarp();
+    gn_publish_and_finalize_warp(sums, partials, counters, meanrstd, b, blk, gridDim.x, 1, (float)D, kGnEps);
+  }
+}
+
+// ------------------------------------------------------------------ conv 1 -> 64 (first conv of downs.0)
+// x fp32 [B,H,W] --GN(1,1)+SiLU on load--> 3x3 conv -> raw bf16 NHWC [B,H,W,64] + bias, + GN(4,64) stats.
+// 8 threads per pixel (8 channels each) so each pixel's 128-byte NHWC row is one coalesced store.
+constexpr int kCinTH = 8, kCinTW = 32;
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ xstats,
+                                                      const float* __restrict__ gn_w, const float* __restrict__ gn_b,
+                                                      const float* __restrict__ w /*[64][9]*/, BiasRef bias,
+                                                      __nv_bfloat16* __restrict__ out, float* partials, int* counters,
+                                                      float* meanrstd, int H, int W) {
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
+  const int tid = threadIdx.x;
+  __shared__ float tile[kCinTH + 2][kCinTW + 2];
+  const float mean = xstats[b * 2], rstd = xstats[b * 2 + 1];
+  const float ga = rstd * gn_w[0], gb = gn_b[0] - mean * rstd * gn_w[0];
+  for (int i = tid; i < (kCinTH + 2) * (kCinTW + 2); i += 256) {
+    int r = i / (kCinTW + 2), c = i % (kCinTW + 2);
+    int h = h0 + r - 1, ww = w0 + c - 1;
+    float v = 0.f;
+    if (h >= 0 && h < H && ww >= 0 && ww < W) v = silu_f(fmaf(x[((size_t)b * H + h) * W + ww], ga, gb));
+    tile[r][c] = v;
+  }
+  const int cg = tid & 7;
+  float wr[9][8], br[8];
+  const float* bp = bias_ptr(bias, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    br[j] = bp[cg * 8 + j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][j] = w[(cg * 8 + j) * 9 + t];
+  }
+  __syncthreads();
+  float s = 0.f, ss = 0.f;
+#pragma unroll 1
+  for (int pass = 0; pass < 8; ++pass) {
+    const int p = pass * 32 + (tid >> 3);
+    const int r = p / kCinTW, c = p % kCinTW;
+    const int h = h0 + r, ww = w0 + c;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = br[j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const float v = tile[r + ky][c + kx];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[ky * 3 + kx][j], acc[j]);
+      }
+    if (h < H && ww < W) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s += acc[j]; ss = fmaf(acc[j], acc[j], ss); }
+      uint4 pk;
+      pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
+      pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
+      *reinterpret_cast<uint4*>(out + (((size_t)b * H + h) * W + ww) * 64 + cg * 8) = pk;
+    }
+  }
+  // group of this thread = cg / 2; reduce over lane bits 0, 3, 4 then across the 8 warps
+  s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+  __shared__ float red[8][4][2];
+  __shared__ float sums[8];
+  const int lane = tid & 31, warp = tid >> 5;
+  if (lane < 8 && (lane & 1) == 0) { red[warp][lane >> 1][0] = s; red[warp][lane >> 1][1] = ss; }
+  __syncthreads();
+  if (tid < 32) {
+    if (tid < 8) {
+      float a = 0.f;
+      for (int wq = 0; wq < 8; ++wq) a += red[wq][tid >> 1][tid & 1];
+      sums[tid] = a;
+    }
+    __syncwarp();
+    const int part = blockIdx.y * gridDim.x + blockIdx.x;
+    gn_publish_and_finalize_warp(sums, partials, counters, meanrstd, b, part, gridDim.x * gridDim.y, 4,
+                                 (float)H * (float)W * 16.0f, kGnEps);
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm(4,C)+SiLU apply, in place
+// act bf16 NHWC [B,H,W,C]; each thread handles 8 consecutive channels (16 bytes).
+__global__ void __launch_bounds__(256) gn_silu_apply_kernel(__nv_bfloat16* act, const float* __restrict__ meanrstd,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, int HW, int C) {
+  const int b = blockIdx.y;
+  __shared__ float sa[128], sb[128];
+  for (int c = threadIdx.x; c < C; c += 256) {
+    int g = c / (C / 4);
+    float mean = meanrstd[(b * 4 + g) * 2], rstd = meanrstd[(b * 4 + g) * 2 + 1];
+    float a = rstd * gamma[c];
+    sa[c] = a;
+    sb[c] = beta[c] - mean * a;
+  }
+  __syncthreads();
+  const size_t nvec = (size_t)HW * C / 8;
+  uint4* p = reinterpret_cast<uint4*>(act + (size_t)b * HW * C);
+  const int cvec = C / 8;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+    uint4 v = p[i];
+    const int c0 = (int)(i % cvec) * 8;
+    uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u[j]);
+      float lo = __low2float(h), hi = __high2float(h);
+      lo = silu_f(fmaf(lo, sa[c0 + 2 * j], sb[c0 + 2 * j]));
+      hi = silu_f(fmaf(hi, sa[c0 + 2 * j + 1], sb[c0 + 2 * j + 1]));
+      u[j] = pack_bf16x2(lo, hi);
+    }
+    p[i] = make_uint4(u[0], u[1], u[2], u[3]);
+  }
+}
+
+// ------------------------------------------------------------------ conv 64 -> 1 (first conv of ups.1)
+// act bf16 NHWC [B,H,W,64] (already GN+SiLU'd) -> raw fp32 [B,H,W] + bias, + GN(1,1) stats.
+__global__ void __launch_bounds__(256) conv_out1_kernel(const __nv_bfloat16* __restrict__ act,
+                                                        const float* __restrict__ w /*[1][64][3][3]*/,
+                                                        const float* __restrict__ bias, float* __restrict__ out,
+                                                        float* partials, int* counters, float* meanrstd, int H,
+                                                        int W) {
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
+  const int tid = threadIdx.x, cg = tid & 7;
+  float wr[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wr[t][j] = w[(cg * 8 + j) * 9 + t];
+  const float bv = bias[0];
+  float s = 0.f, ss = 0.f;
+#pragma unroll 1
+  for (int pass = 0; pass < 8; ++pass) {
+    const int p = pass * 32 + (tid >> 3);
+    const int h = h0 + p / kCinTW, ww = w0 + p % kCinTW;
+    float acc = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int hh = h + ky - 1, wx = ww + kx - 1;
+        if (hh >= 0 && hh < H && wx >= 0 && wx < W && h < H && ww < W) {
+          uint4 v = __ldg(reinterpret_cast<const uint4*>(act + (((size_t)b * H + hh) * W + wx) * 64 + cg * 8));
+          uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[j]);
+            acc = fmaf(__low2float(hv), wr[ky * 3 + kx][2 * j], acc);
+            acc = fmaf(__high2float(hv), wr[ky * 3 + kx][2 * j + 1], acc);
+          }
+        }
+      }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    acc += bv;
+    if (cg == 0 && h < H && ww < W) {
+      out[((size_t)b * H + h) * W + ww] = acc;
+      s += acc;
+      ss = fmaf(acc, acc, ss);
+    }
+  }
+  __shared__ float red[8][2];
+  __shared__ float sums[2];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+  if ((tid & 31) == 0) { red[tid >> 5][0] = s; red[tid >> 5][1] = ss; }
+  __syncthreads();
+  if (tid < 32) {
+    if (tid == 0) {
+      float a = 0.f, c = 0.f;
+      for (int wq = 0; wq < 8; ++wq) { a += red[wq][0]; c += red[wq][1]; }
+      sums[0] = a; sums[1] = c;
+    }
+    __syncwarp();
+    const int part = blockIdx.y * gridDim.x + blockIdx.x;
+    gn_publish_and_finalize_warp(sums, partials, counters, meanrstd, b, part, gridDim.x * gridDim.y, 1,
+                                 (float)H * (float)W, kGnEps);
+  }
+}
+
+// ------------------------------------------------------------------ conv 1 -> 1 (last conv) + time bias
+// e fp32 [B,H,W] raw --GN(1,1)+SiLU on load--> 3x3 conv + (conv bias + time_emb)[b] -> eps fp32 [B,H,W].
+__global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict__ e, const float* __restrict__ stats,
+                                                        const float* __restrict__ gn_w, const float* __restrict__ gn_b,
+                                                        const float* __restrict__ w /*[9]*/, BiasRef bias,
+                                                        float* __restrict__ out, int H, int W) {
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
+  const int tid = threadIdx.x;
+  __shared__ float tile[kCinTH + 2][kCinTW + 2];
+  const float mean = stats[b * 2], rstd = stats[b * 2 + 1];
+  const float ga = rstd * gn_w[0], gb = gn_b[0] - mean * rstd * gn_w[0];
+  for (int i = tid; i < (kCinTH + 2) * (kCinTW + 2); i += 256) {
+    int r = i / (kCinTW + 2), c = i % (kCinTW + 2);
+    int h = h0 + r - 1, ww = w0 + c - 1;
+    float v = 0.f;
+    if (h >= 0 && h < H && ww >= 0 && ww < W) v = silu_f(fmaf(e[((size_t)b * H + h) * W + ww], ga, gb));
+    tile[r][c] = v;
+  }
+  __syncthreads();
+  const int r = tid / kCinTW, c = tid % kCinTW;
+  const int h = h0 + r, ww = w0 + c;
+  if (h < H && ww < W) {
+    float acc = bias_ptr(bias, b)[0];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) acc = fmaf(tile[r + ky][c + kx], w[ky * 3 + kx], acc);
+    out[((size_t)b * H + h) * W + ww] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ bring-up cross-check conv (CUDA cores)
+// Same contract as the tcgen05 kernel minus the statistics: act bf16 NHWC, w bf16 [kx][ky][Cout][Cin].
+__global__ void conv3x3_simt_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ w,
+                                    BiasRef bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cin,
+                                    int Cout) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)B * H * W * Cout;
+  if (idx >= total) return;
+  int co = idx % Cout;
+  size_t p = idx / Cout;
+  int ww = p % W;
+  int h = (p / W) % H;
+  int b = p / ((size_t)W * H);
+  float acc = bias_ptr(bias, b)[co];
+  for (int kx = 0; kx < 3; ++kx)
+    for (int ky = 0; ky < 3; ++ky) {
+      int hh = h + ky - 1, wx = ww + kx - 1;
+      if (hh < 0 || hh >= H || wx < 0 || wx >= W) continue;
+      const __nv_bfloat16* a = act + (((size_t)b * H + hh) * W + wx) * Cin;
+      const __nv_bfloat16* wr = w + ((size_t)(kx * 3 + ky) * Cout + co) * Cin;
+      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(__bfloat162float(a[ci]), __bfloat162float(wr[ci]), acc);
+    }
+  out[idx] = __float2bfloat16_rn(acc);
+}
+
+// GroupNorm(4,C) statistics straight from a bf16 NHWC tensor (cross-check path only).
+__global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const __nv_bfloat16* __restrict__ act, float* meanrstd,
+                                                            int HW, int C) {
+  const int b = blockIdx.x / 4, g = blockIdx.x % 4;
+  const int cpg = C / 4;
+  double s = 0.0, ss = 0.0;
+  for (size_t i = threadIdx.x; i < (size_t)HW * cpg; i += 256) {
+    size_t p = i / cpg;
+    int c = g * cpg + (int)(i % cpg);
+    float v = __bfloat162float(act[((size_t)b * HW + p) * C + c]);
+    s += v;
+    ss += (double)v * v;
+  }
+  __shared__ double rs[256], rss[256];
+  rs[threadIdx.x] = s; rss[threadIdx.x] = ss;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) { rs[threadIdx.x] += rs[threadIdx.x + o]; rss[threadIdx.x] += rss[threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double n = (double)HW * cpg, mean = rs[0] / n, var = rss[0] / n - mean * mean;
+    if (var < 0) var = 0;
+    meanrstd[(b * 4 + g) * 2] = (float)mean;
+    meanrstd[(b * 4 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+  }
+}
+
+}  // namespace sdd

@@ -1,0 +1,252 @@
+// Fused superposition update: one coalesced, vectorised HBM pass per step.
+//   reads  x[B,D], eps[M,B,D], (noise[B,D] | Philox)      writes x'[B,D]
+//   per-sample reductions <eps_m,dx>, <x,eps_m>, |eps_m|^2, sum x', sum x'^2 via warp shuffles,
+//   fixed-order cross-CTA reduce by the last CTA of each sample -> logq', kappa, GN(1,1) stats of x'.
+// Algorithmic bytes / element: 4 + 4M + (4 if noise tensor) + 4.
+#pragma once
+#include "common.cuh"
+
+namespace sdd {
+
+constexpr int kMaxModels = 4;
+constexpr int kUpdThreads = 256;
+constexpr int kUpdMaxBlocksPerSample = 64;
+
+// Per-timestep scalars, either passed by value (operator API) or read from a device table
+// indexed by the device-side step counter (captured step graph).
+struct StepScalars {
+  float alpha, alpha_bar, beta;
+  int draw_index;  // Philox draw index / noise-stack slice for this step; < 0 => z = 0 (t == 0)
+};
+
+struct UpdateArgs {
+  const float* x_in;
+  float* x_out;
+  const float* eps;          // [M,B,D]
+  const float* noise;        // [B,D] slice base or nullptr
+  int64_t noise_step_stride; // elements between consecutive draw indices in a noise stack (0 = single slice)
+  const float* logq;         // [B,M]
+  float* logq_out;           // [B,M]
+  float* kappa_out;          // [B,M] or nullptr
+  float* xstats_out;         // [B,2] (mean, rstd) or nullptr
+  float* kappa_traj;         // [T,B,M] or nullptr (row = step)
+  float* logq_traj;          // [T+1,B,M] or nullptr (row = step+1)
+  const StepScalars* table;  // device table or nullptr
+  const int* step_ptr;       // device step counter or nullptr
+  StepScalars sc;            // used when table == nullptr
+  float temperature;
+  const float* bias;         // [M] or nullptr
+  uint64_t seed;
+  int64_t sample_offset;
+  float* partials;           // [B][nblk][kPartialsPerBlock]
+  int* counters;             // [B]
+  int B, D, M, nblk;
+};
+
+constexpr int kPartialsPerBlock = 3 * kMaxModels + 2;
+
+// ------------------------------------------------------------------------------------- Philox
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ float u01(uint32_t r) { return (float)r * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
+// 4 standard normals for elements 4q..4q+3 of (global sample, draw); definition in oracle.philox_normal.
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t q, uint32_t gsample, uint32_t draw) {
+  uint4 r = philox4x32_10(make_uint4(q, gsample, draw, 0x5D1FFu), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  float4 o;
+  float rad0 = sqrtf(-2.0f * logf(u01(r.x)));
+  float rad1 = sqrtf(-2.0f * logf(u01(r.z)));
+  float s0, c0, s1, c1;
+  sincospif(2.0f * u01(r.y) - 1.0f, &s0, &c0);
+  sincospif(2.0f * u01(r.w) - 1.0f, &s1, &c1);
+  o.x = rad0 * s0; o.y = rad0 * c0; o.z = rad1 * s1; o.w = rad1 * c1;
+  return o;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// x' for one element, with the reference's expression tree and no FMA contraction (ddpm.py:42-44):
+//   (1/sqrt(alpha)) * (x - ((1-alpha)/sqrt(1-alpha_bar)) * eps_bar) + sqrt(beta) * z
+__device__ __forceinline__ float ddpm_x_update(float x, float eb, float z, float c1, float c2, float c3) {
+  return __fadd_rn(__fmul_rn(c1, __fsub_rn(x, __fmul_rn(c2, eb))), __fmul_rn(c3, z));
+}
+
+template <int M>
+__global__ void __launch_bounds__(kUpdThreads) superpose_update_kernel(const UpdateArgs a) {
+  const int b = blockIdx.y;
+  const int blk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int step = a.step_ptr ? *a.step_ptr : 0;
+  const StepScalars sc = a.table ? a.table[step] : a.sc;
+
+  // kappa = softmax(temperature * logq + bias), recomputed by every CTA (M values)
+  float kap[M];
+  {
+    float lg[M], mx = -INFINITY;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      lg[m] = a.temperature * a.logq[b * M + m] + (a.bias ? a.bias[m] : 0.0f);
+      mx = fmaxf(mx, lg[m]);
+    }
+    float den = 0.0f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) { kap[m] = expf(lg[m] - mx); den += kap[m]; }
+#pragma unroll
+    for (int m = 0; m < M; ++m) kap[m] = kap[m] / den;
+  }
+  const float c1 = 1.0f / sqrtf(sc.alpha);
+  const float c2 = (1.0f - sc.alpha) / sqrtf(1.0f - sc.alpha_bar);
+  const float c3 = sqrtf(sc.beta);
+
+  const int nq = a.D >> 2;  // float4 per sample
+  const int q_per_blk = (nq + a.nblk - 1) / a.nblk;
+  const int q0 = blk * q_per_blk;
+  const int q1 = min(nq, q0 + q_per_blk);
+
+  const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
+  float4* xo4 = reinterpret_cast<float4*>(a.x_out + (size_t)b * a.D);
+  const float4* e4[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) e4[m] = reinterpret_cast<const float4*>(a.eps + ((size_t)m * a.B + b) * a.D);
+  const float4* n4 = nullptr;
+  const bool have_noise = sc.draw_index >= 0;
+  if (a.noise && have_noise)
+    n4 = reinterpret_cast<const float4*>(a.noise + (size_t)sc.draw_index * a.noise_step_stride + (size_t)b * a.D);
+  const uint32_t gsample = (uint32_t)(a.sample_offset + b);
+
+  float accA[M], accB[M], accC[M], sx = 0.0f, sxx = 0.0f;
+#pragma unroll
+  for (int m = 0; m < M; ++m) accA[m] = accB[m] = accC[m] = 0.0f;
+
+  for (int q = q0 + tid; q < q1; q += kUpdThreads) {
+    const float4 xv = __ldcs(x4 + q);
+    float4 ev[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) ev[m] = __ldcs(e4[m] + q);
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (have_noise) zv = n4 ? __ldcs(n4 + q) : philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
+
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float zs[4] = {zv.x, zv.y, zv.z, zv.w};
+    float xn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float es[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) es[m] = (j == 0 ? ev[m].x : j == 1 ? ev[m].y : j == 2 ? ev[m].z : ev[m].w);
+      float eb = __fmul_rn(kap[0], es[0]);
+#pragma unroll
+      for (int m = 1; m < M; ++m) eb = __fadd_rn(eb, __fmul_rn(kap[m], es[m]));
+      xn[j] = ddpm_x_update(xs[j], eb, zs[j], c1, c2, c3);
+      const float dx = xn[j] - xs[j];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        accA[m] = fmaf(es[m], dx, accA[m]);
+        accB[m] = fmaf(xs[j], es[m], accB[m]);
+        accC[m] = fmaf(es[m], es[m], accC[m]);
+      }
+      sx += xn[j];
+      sxx = fmaf(xn[j], xn[j], sxx);
+    }
+    xo4[q] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+  }
+
+  // block reduce: shuffle within warps, fixed-order sum across the 8 warps
+  __shared__ float red[kUpdThreads / 32][3 * M + 2];
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    accA[m] = warp_sum(accA[m]); accB[m] = warp_sum(accB[m]); accC[m] = warp_sum(accC[m]);
+  }
+  sx = warp_sum(sx); sxx = warp_sum(sxx);
+  if (lane == 0) {
+#pragma unroll
+    for (int m = 0; m < M; ++m) { red[warp][3 * m] = accA[m]; red[warp][3 * m + 1] = accB[m]; red[warp][3 * m + 2] = accC[m]; }
+    red[warp][3 * M] = sx; red[warp][3 * M + 1] = sxx;
+  }
+  __syncthreads();
+  __shared__ int s_last;
+  float* part = a.partials + ((size_t)b * a.nblk + blk) * kPartialsPerBlock;
+  if (tid < 3 * M + 2) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kUpdThreads / 32; ++w) v += red[w][tid];
+    __stcg(part + tid, v);
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    int prev = atomicAdd(&a.counters[b], 1);
+    s_last = (prev == a.nblk - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+
+  // last CTA of sample b: fixed-order reduce over blocks, then the Ito increment (in double)
+  __shared__ double tot[3 * M + 2];
+  if (tid < 3 * M + 2) {
+    double v = 0.0;
+    const float* src = a.partials + (size_t)b * a.nblk * kPartialsPerBlock + tid;
+    for (int p = 0; p < a.nblk; ++p) v += (double)__ldcg(src + (size_t)p * kPartialsPerBlock);
+    tot[tid] = v;
+  }
+  __syncthreads();
+  if (tid < M) {
+    const double beta = (double)sc.beta;
+    const double inv_sig = 1.0 / sqrt(1.0 - (double)sc.alpha_bar);
+    const double A = tot[3 * tid], Bx = tot[3 * tid + 1], C = tot[3 * tid + 2];
+    // s = -eps * inv_sig:  <s,dx> - beta D/2 - beta/2 <x,s> - beta/2 |s|^2
+    const double inc = -inv_sig * A - 0.5 * beta * (double)a.D + 0.5 * beta * inv_sig * Bx - 0.5 * beta * inv_sig * inv_sig * C;
+    const float lq_new = (float)((double)a.logq[b * M + tid] + inc);
+    a.logq_out[b * M + tid] = lq_new;
+    if (a.kappa_out) a.kappa_out[b * M + tid] = kap[tid];
+    if (a.kappa_traj) a.kappa_traj[((size_t)step * a.B + b) * M + tid] = kap[tid];
+    if (a.logq_traj) a.logq_traj[((size_t)(step + 1) * a.B + b) * M + tid] = lq_new;
+  }
+  if (tid == 0) {
+    if (a.xstats_out) {
+      const double mean = tot[3 * M] / (double)a.D;
+      double var = tot[3 * M + 1] / (double)a.D - mean * mean;
+      if (var < 0.0) var = 0.0;
+      a.xstats_out[b * 2 + 0] = (float)mean;
+      a.xstats_out[b * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    }
+    a.counters[b] = 0;
+  }
+}
+
+// Blocks per sample depend on D only, so the reduction tree (hence every bit of logq / x stats)
+// is identical however the batch is sharded across GPUs.
+inline int update_blocks_per_sample(int D) {
+  int nq = D / 4;
+  int nb = (nq + kUpdThreads * 4 - 1) / (kUpdThreads * 4);
+  if (nb < 1) nb = 1;
+  if (nb > kUpdMaxBlocksPerSample) nb = kUpdMaxBlocksPerSample;
+  return nb;
+}
+
+inline size_t update_workspace_bytes(int B, int D, int /*M*/) {
+  size_t part = (size_t)B * update_blocks_per_sample(D) * kPartialsPerBlock * sizeof(float);
+  part = (part + 255) & ~(size_t)255;
+  return part + (((size_t)B * sizeof(int) + 255) & ~(size_t)255);
+}
+
+int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream);
+
+__global__ void philox_normal_kernel(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw);
+__global__ void copy_f32_kernel(float* dst, const float* src, size_t n);
+
+}  // namespace sdd

@@ -1,0 +1,114 @@
+"""Drop-in ``UNet`` for /root/reference/src/models/unet.py:37-65.
+
+Same constructor, same module tree (hence the same 54 ``state_dict`` keys, so reference checkpoints
+``load_state_dict(strict=True)`` unchanged), same ``forward(x, t)`` contract.  The modules below
+only HOLD parameters; ``forward`` hands raw device pointers to the C ABI (sdd_unet_forward), which
+runs the hand-written sm_100a kernels.  Inference only (sampling runs under ``torch.no_grad()``,
+src/train/training_logic.py:54).
+"""
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from super_diff_disease_b200 import _lib
+
+
+class SinusoidalPosEmb(nn.Module):
+    """Parameter-free placeholder at index 0 of ``time_mlp`` (unet.py:6-16); evaluated on device by
+    sinusoid_kernel with the reference's (half-1) divisor and sin-then-cos order."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+    def forward(self, t):  # pragma: no cover - never used on the product path
+        raise _lib.SddError("SinusoidalPosEmb is evaluated inside sdd_unet_forward; call UNet.forward")
+
+
+class ResidualBlock(nn.Module):
+    """Parameter container for unet.py:18-34: block = [GN, SiLU, Conv3x3, GN, SiLU, Conv3x3], time_emb."""
+
+    def __init__(self, in_ch, out_ch, time_emb_dim):
+        super().__init__()
+        layers = [nn.GroupNorm(min(4, in_ch), in_ch), nn.SiLU(), nn.Conv2d(in_ch, out_ch, 3, padding=1),
+                  nn.GroupNorm(min(4, out_ch), out_ch), nn.SiLU(), nn.Conv2d(out_ch, out_ch, 3, padding=1)]
+        self.block = nn.Sequential(*layers)
+        self.time_emb = nn.Linear(time_emb_dim, out_ch)
+
+    def forward(self, x, t):  # pragma: no cover
+        raise _lib.SddError("ResidualBlock runs fused inside sdd_unet_forward; call UNet.forward")
+
+
+class UNet(nn.Module):
+    def __init__(self, in_channels=1, out_channels=1, time_emb_dim=256, base_channels=64):
+        super().__init__()
+        if (in_channels, out_channels, time_emb_dim, base_channels) != (1, 1, 256, 64):
+            # train.py:88 always default-constructs the UNet; the kernels are specialised to that.
+            raise _lib.SddError("the B200 kernels implement the reference's default UNet() only "
+                                "(in=1, out=1, time_emb_dim=256, base_channels=64)")
+        self.time_mlp = nn.Sequential(SinusoidalPosEmb(time_emb_dim), nn.Linear(time_emb_dim, time_emb_dim * 4),
+                                      nn.SiLU(), nn.Linear(time_emb_dim * 4, time_emb_dim))
+        c = base_channels
+        self.downs = nn.ModuleList([ResidualBlock(in_channels, c, time_emb_dim),
+                                    ResidualBlock(c, 2 * c, time_emb_dim)])
+        self.mid = ResidualBlock(2 * c, 2 * c, time_emb_dim)
+        self.ups = nn.ModuleList([ResidualBlock(2 * c, c, time_emb_dim),
+                                  ResidualBlock(c, out_channels, time_emb_dim)])
+        self._handle = None
+        self._handle_key = None
+
+    # ---- C-ABI handle management -------------------------------------------------------------
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.state_dict(keep_vars=True).values())
+
+    def handle(self):
+        """The sdd_unet_t* for the current parameters (rebuilt if they were reloaded or moved)."""
+        sd = self.state_dict(keep_vars=True)
+        tensors = list(sd.values())
+        for k, v in sd.items():
+            _lib.require_cuda(v, f"UNet parameter {k}")
+        key = self._param_key()
+        if self._handle is not None and key == self._handle_key:
+            return self._handle
+        self._free()
+        L = _lib.lib()
+        dev = tensors[0].device
+        with torch.cuda.device(dev):
+            flat = [v.detach().to(torch.float32).contiguous() for v in tensors]
+            arr = (ctypes.c_void_p * len(flat))(*[v.data_ptr() for v in flat])
+            h = ctypes.c_void_p()
+            _lib.check(L.sdd_unet_create(ctypes.byref(h), arr, len(flat), _lib.stream_ptr(dev)))
+        self._handle, self._handle_key = h, key
+        return h
+
+    def _free(self):
+        if getattr(self, "_handle", None) is not None:
+            try:
+                _lib.lib().sdd_unet_destroy(self._handle)
+            except Exception:  # pragma: no cover - interpreter shutdown
+                pass
+            self._handle = None
+            self._handle_key = None
+
+    def __del__(self):
+        self._free()
+
+    # ---- forward -----------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, t):
+        """x fp32 [B,1,H,W] (CUDA), t int64 [B] -> predicted noise fp32 [B,1,H,W] (unet.py:57-65)."""
+        _lib.require_cuda(x, "x")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise _lib.SddError(f"x must be [B,1,H,W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        xc = x.detach().to(torch.float32).contiguous()
+        tc = t.to(device=x.device, dtype=torch.int64).contiguous()
+        if tc.numel() != B:
+            raise _lib.SddError("t must have one entry per sample")
+        out = torch.empty_like(xc)
+        h = self.handle()
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().sdd_unet_forward(h, xc.data_ptr(), tc.data_ptr(), out.data_ptr(), B, H, W,
+                                                   _lib.stream_ptr(x.device)))
+        return out

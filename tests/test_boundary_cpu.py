@@ -1,0 +1,130 @@
+"""CPU: host logic, C-ABI surface, fail-loudly behaviour, shard partition and 2-rank gloo gather."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__ as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    G.build()
+
+
+def test_header_symbols_exported():
+    import super_diff_disease_b200 as S
+    hdr = open(os.path.join(ROOT, "include", "sdd_b200.h")).read()
+    declared = set(re.findall(r"\b(sdd_[a-z0-9_]+)\s*\(", hdr))
+    L = ctypes.CDLL(S.lib_path())
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in sdd_b200.h but not exported"
+    assert declared == set(S._lib.SYMBOLS), (declared ^ set(S._lib.SYMBOLS))
+    assert S.lib().sdd_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    import super_diff_disease_b200 as S
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert S.lib().sdd_device_check() != 0
+    m = S.UNet()
+    with pytest.raises(S.SddError):
+        m(torch.zeros(1, 1, 16, 16), torch.zeros(1, dtype=torch.long))
+    with pytest.raises(S.SddError):
+        S.DDPM(4).sample(m, (1, 1, 16, 16), "cpu")
+    with pytest.raises(S.SddError):
+        S.superposed_sample([m, m], S.DDPM(4), (1, 1, 16, 16), "cpu", seed=0)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "super-diff-disease_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_state_dict_contract():
+    """Same 54 keys / shapes as the reference UNet (enumerated in SURVEY section 5)."""
+    import super_diff_disease_b200 as S
+    from oracle.superdiff_oracle import init_unet_params
+    p = init_unet_params(0)
+    m = S.UNet()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(p.keys())
+    for k in sd:
+        assert sd[k].shape == p[k].shape, k
+    m.load_state_dict(p, strict=True)
+    with pytest.raises(S.SddError):
+        S.UNet(base_channels=32)
+
+
+def test_ddpm_schedule_matches_golden(golden_dir):
+    import super_diff_disease_b200 as S
+    g = np.load(os.path.join(golden_dir, "ddpm_sample.npz"))
+    d = S.DDPM(1000)
+    assert d.T == 1000
+    assert np.array_equal(d.betas.numpy(), g["sched1000_betas"])
+    assert np.array_equal(d.alpha_bars.numpy(), g["sched1000_alpha_bars"])
+    assert torch.equal(d.alphas, 1.0 - d.betas)
+
+
+def test_shard_range():
+    from super_diff_disease_b200 import shard_range
+    for gb in (1, 7, 8, 64, 33):
+        for ws in (1, 2, 4, 8):
+            spans = [shard_range(gb, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == gb
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, gb, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from oracle.superdiff_oracle import philox_normal
+    from super_diff_disease_b200 import sharded_sample
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    def local_fn(lo, hi):  # stand-in sampler with the product's global-sample-id noise keying
+        return torch.from_numpy(philox_normal(99, np.arange(lo, hi), 0, 64)).reshape(hi - lo, 1, 8, 8)
+
+    full = sharded_sample(local_fn, gb, (1, 8, 8), "cpu")
+    q.put((rank, full.numpy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("gb", [4, 5])
+def test_two_rank_gloo_gather_is_shard_invariant(gb):
+    import torch.multiprocessing as mp
+    from oracle.superdiff_oracle import philox_normal
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, gb, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(60)
+    single = philox_normal(99, np.arange(gb), 0, 64).reshape(gb, 1, 8, 8)
+    assert np.array_equal(res[0], single) and np.array_equal(res[1], single)
