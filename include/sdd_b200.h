@@ -125,6 +125,16 @@ int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t
 int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta,
                       int B, int H, int W, int C, void* stream);
 
+/* Kernel-only timing for the roofline numbers (bench.py): `iters` launches, each bracketed by CUDA events
+ * on the launching stream; `flush` (may be NULL) is rewritten before every launch to evict L2.
+ * *ms_host receives the mean kernel duration in milliseconds. */
+int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W,
+                        int Cin, int Cout, int iters, void* flush, size_t flush_bytes, float* ms_host,
+                        void* stream);
+int sdd_superpose_update_profile(float* x, const float* eps, const float* noise, float* logq, int B, int D,
+                                 int M, int iters, void* flush, size_t flush_bytes, float* ms_host,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -520,6 +520,8 @@ struct sdd_sampler {
   float *x = nullptr, *eps = nullptr, *logq = nullptr, *xstats = nullptr;
   void* upd_ws = nullptr;
   float* stat_partials = nullptr; int* stat_counters = nullptr;
+  cudaStream_t work = nullptr;   // private stream: graph capture is illegal on the legacy default stream
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t exec = nullptr;
   sdd_sample_args captured;  // arguments baked into `exec`
   int64_t captured_gen[kMaxModels] = {0, 0, 0, 0};
@@ -573,6 +575,9 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
   auto fail = [&](int code) { sdd_sampler_destroy(s); return code; };
 #define S_CUDA(expr) do { if ((expr) != cudaSuccess) { set_error(#expr " failed"); return fail(SDD_ECUDA); } } while (0)
   const size_t BD = (size_t)B * s->D;
+  S_CUDA(cudaStreamCreateWithFlags(&s->work, cudaStreamNonBlocking));
+  S_CUDA(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
+  S_CUDA(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
   S_CUDA(cudaMalloc(&s->x, BD * sizeof(float)));
   S_CUDA(cudaMalloc(&s->eps, (size_t)M * BD * sizeof(float)));
   S_CUDA(cudaMalloc(&s->logq, (size_t)B * M * sizeof(float)));
@@ -622,7 +627,10 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
 
 int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream) {
   SDD_CHECK(s && args && args->x_out, "null argument");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t st = s->work;  // everything runs here, ordered after / before the caller's stream by events
+  SDD_CUDA(cudaEventRecord(s->ev_in, user));
+  SDD_CUDA(cudaStreamWaitEvent(st, s->ev_in, 0));
   const size_t BD = (size_t)s->B * s->D;
   const int64_t l0 = g_launches;
   // --- x_T, logq = 0, step = 0, GN(1,1) stats of x_T
@@ -655,8 +663,8 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
       cudaGraph_t graph = nullptr;
       SDD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
       int rc = enqueue_step(s, *args, st);
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      if (rc != SDD_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);  // always leave capture mode, even on error
+      if (rc != SDD_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
       SDD_CUDA(ce);
       ce = cudaGraphInstantiate(&s->exec, graph, 0);
       cudaGraphDestroy(graph);
@@ -672,6 +680,8 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
   int blocks = (int)std::min<size_t>((BD + 255) / 256, 2048);
   copy_f32_kernel<<<blocks, 256, 0, st>>>(args->x_out, s->x, BD);
   SDD_LAUNCH_CHECK();
+  SDD_CUDA(cudaEventRecord(s->ev_out, st));
+  SDD_CUDA(cudaStreamWaitEvent(user, s->ev_out, 0));
   return SDD_OK;
 }
 
@@ -681,7 +691,11 @@ int64_t sdd_sampler_launches_per_run(const sdd_sampler_t* s) {
 
 int sdd_sampler_destroy(sdd_sampler_t* s) {
   if (!s) return SDD_OK;
+  if (s->work) cudaStreamSynchronize(s->work);
   if (s->exec) cudaGraphExecDestroy(s->exec);
+  if (s->ev_in) cudaEventDestroy(s->ev_in);
+  if (s->ev_out) cudaEventDestroy(s->ev_out);
+  if (s->work) cudaStreamDestroy(s->work);
   for (int m = 0; m < kMaxModels; ++m) cudaFree(s->tables[m]);
   cudaFree(s->sched); cudaFree(s->step); cudaFree(s->x); cudaFree(s->eps); cudaFree(s->logq); cudaFree(s->xstats);
   cudaFree(s->upd_ws); cudaFree(s->stat_partials); cudaFree(s->stat_counters);
@@ -736,6 +750,85 @@ int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t
   e = cudaGetLastError();
   if (e != cudaSuccess) { set_error(std::string("conv3x3 launch: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
   return SDD_OK;
+}
+
+// Kernel-only timing for the roofline: `iters` launches of the tcgen05 conv at one shape, each bracketed by
+// CUDA events on the launching stream, with `flush_bytes` of `flush` rewritten before every launch (L2 flush).
+int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
+                        int Cout, int iters, void* flush, size_t flush_bytes, float* ms_host, void* stream) {
+  SDD_CHECK(act && w && bias && out && ms_host && iters > 0, "bad argument");
+  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "Cin, Cout must be 64 or 128");
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* wt = nullptr; float* partials = nullptr; int* counters = nullptr; float* mr = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const int total_w = 9 * Cout * Cin, tiles_ps = (H / kTileH) * (W / kTileW);
+  int rc = SDD_OK;
+  CUtensorMap tmA, tmB;
+  if (cudaMalloc(&wt, (size_t)total_w * 2) != cudaSuccess || cudaMalloc(&partials, (size_t)B * tiles_ps * 32) != cudaSuccess ||
+      cudaMalloc(&counters, (size_t)B * 4) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 32) != cudaSuccess) rc = SDD_ENOMEM;
+  if (rc == SDD_OK) {
+    cudaMemsetAsync(counters, 0, (size_t)B * 4, st);
+    conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
+    rc = make_act_map(&tmA, act, B, H, W, Cin);
+  }
+  if (rc == SDD_OK) rc = make_wt_map(&tmB, wt, Cout, Cin);
+  if (rc == SDD_OK && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) rc = SDD_ECUDA;
+  BiasRef br{bias, nullptr, 0, 0};
+  double total = 0.0;
+  for (int i = 0; rc == SDD_OK && i < iters + 2; ++i) {
+    if (flush && flush_bytes) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
+    cudaEventRecord(e0, st);
+    rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("conv profile: kernel failed"); rc = SDD_ECUDA; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (i >= 2) total += ms;
+  }
+  cudaStreamSynchronize(st);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr);
+  if (rc == SDD_OK) *ms_host = (float)(total / iters);
+  return rc;
+}
+
+// Same for the fused update kernel (M models, fp32 eps; noise == NULL => in-kernel Philox).
+int sdd_superpose_update_profile(float* x, const float* eps, const float* noise, float* logq, int B, int D, int M,
+                                 int iters, void* flush, size_t flush_bytes, float* ms_host, void* stream) {
+  SDD_CHECK(x && eps && logq && ms_host && iters > 0, "bad argument");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  void* ws = nullptr;
+  size_t wb = update_workspace_bytes(B, D, M);
+  SDD_CUDA(cudaMalloc(&ws, wb));
+  cudaMemsetAsync(ws, 0, wb, st);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  UpdateArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_in = x; a.x_out = x; a.eps = eps; a.noise = noise; a.logq = logq; a.logq_out = logq;
+  a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f; a.temperature = 1.0f; a.seed = 1234;
+  a.B = B; a.D = D; a.M = M;
+  int rc = SDD_OK;
+  double total = 0.0;
+  for (int i = 0; rc == SDD_OK && i < iters + 2; ++i) {
+    if (flush && flush_bytes) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
+    a.sc.draw_index = noise ? 0 : i;
+    cudaEventRecord(e0, st);
+    rc = launch_superpose_update(a, ws, st);
+    cudaEventRecord(e1, st);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("update profile: kernel failed"); rc = SDD_ECUDA; break; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (i >= 2) total += ms;
+  }
+  cudaStreamSynchronize(st);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws);
+  if (rc == SDD_OK) *ms_host = (float)(total / iters);
+  return rc;
 }
 
 int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta, int B, int H, int W,

@@ -1,0 +1,314 @@
+"""GPU (-m gpu): parity of the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (stated per quantity):
+  * fused update kernel (fp32 in/out): x' max-abs <= 2e-6 * max|x'|, logq rel <= 2e-5, kappa abs <= 2e-6
+    (differences only from reduction order / expf ulps);
+  * tcgen05 conv vs fp32 conv of the SAME bf16-rounded operands: <= 1 bf16 ulp of the output (rtol 8e-3);
+  * UNet forward, bf16 operands / fp32 accumulate vs fp32 oracle: rel-L2 <= 2e-2, max-abs <= 5e-2 * max|ref|;
+  * sampling loops: final x rel-L2 <= 5e-2, kappa max-abs <= 5e-2, logq rel-to-max <= 2e-2.
+Measured values are printed and appended to gpurun_out/parity_report.jsonl.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import superdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _report(**kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps(kw) + "\n")
+    print("PARITY", kw)
+
+
+@pytest.fixture(scope="module")
+def S():
+    import __graft_entry__ as G
+    G.build()
+    import super_diff_disease_b200 as S
+    assert torch.cuda.is_available()
+    assert S.lib().sdd_device_check() == 0, S.lib().sdd_last_error()
+    return S
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def _models(S, dev, seeds):
+    params, models = [], []
+    for s in seeds:
+        p = O.init_unet_params(s)
+        m = S.UNet()
+        m.load_state_dict(p, strict=True)
+        params.append(p)
+        models.append(m.to(dev))
+    return params, models
+
+
+def _rel(a, b):
+    return ((a - b).norm() / b.norm()).item()
+
+
+# ------------------------------------------------------------------ fused update kernel
+@pytest.mark.parametrize("B,D,M", [(1, 64, 1), (3, 256, 2), (2, 16384, 2), (5, 65536, 2), (2, 4096, 3), (1, 262144, 4)])
+@pytest.mark.parametrize("mode", ["noise", "zero"])
+def test_update_kernel_matches_oracle(S, dev, B, D, M, mode):
+    g = torch.Generator().manual_seed(B * 1000 + D + M)
+    x = torch.randn(B, D, generator=g) * 2
+    eps = torch.randn(M, B, D, generator=g)
+    z = torch.randn(B, D, generator=g) if mode == "noise" else None
+    logq = torch.randn(B, M, generator=g) * 3
+    s = O.Schedule(100)
+    t = 37
+    a, ab, b = s.alphas[t], s.alpha_bars[t], s.betas[t]
+    xr, lr, kr = O.superpose_step(x, [eps[i] for i in range(M)], z if z is not None else torch.zeros_like(x), logq, a, ab, b,
+                                  temperature=0.7, bias=torch.linspace(-0.2, 0.3, M))
+    xn, ln, kn, st = S.superpose_update(x.to(dev), eps.to(dev), logq.to(dev), a.item(), ab.item(), b.item(),
+                                        noise=None if z is None else z.to(dev), temperature=0.7,
+                                        bias=torch.linspace(-0.2, 0.3, M))
+    xn, ln, kn, st = xn.cpu(), ln.cpu(), kn.cpu(), st.cpu()
+    ex = (xn - xr).abs().max().item() / xr.abs().max().item()
+    el = ((ln - lr).abs() / lr.abs().clamp_min(1.0)).max().item()
+    ek = (kn - kr).abs().max().item()
+    _report(test="update", B=B, D=D, M=M, mode=mode, x_relmax=ex, logq_rel=el, kappa_abs=ek)
+    assert ex <= 2e-6 and el <= 2e-5 and ek <= 2e-6
+    mean, var = xr.mean(1), xr.var(1, unbiased=False)
+    assert torch.allclose(st[:, 0], mean, atol=1e-5)
+    assert torch.allclose(st[:, 1], 1 / torch.sqrt(var + 1e-5), rtol=1e-4)
+
+
+def test_update_kernel_identity_and_inplace(S, dev):
+    """M=2 with identical eps and equal logq == M=1, bit for bit (kappa = 1/2 exactly); in place works."""
+    g = torch.Generator().manual_seed(3)
+    B, D = 3, 4096
+    x = torch.randn(B, D, generator=g).to(dev)
+    e = torch.randn(1, B, D, generator=g).to(dev)
+    z = torch.randn(B, D, generator=g).to(dev)
+    s = O.Schedule(50)
+    args = (s.alphas[9].item(), s.alpha_bars[9].item(), s.betas[9].item())
+    x1, l1, k1, _ = S.superpose_update(x, e, torch.zeros(B, 1, device=dev), *args, noise=z)
+    x2, l2, k2, _ = S.superpose_update(x, torch.cat([e, e]), torch.zeros(B, 2, device=dev), *args, noise=z)
+    assert torch.equal(x1, x2) and torch.equal(k2, torch.full_like(k2, 0.5))
+    assert torch.equal(l2[:, 0], l2[:, 1])
+    xin = x.clone()
+    x3, _, _, _ = S.superpose_update(xin, e, torch.zeros(B, 1, device=dev), *args, noise=z, out=xin)
+    assert torch.equal(x3, x1)
+
+
+def test_philox_normals_match_oracle(S, dev):
+    import ctypes
+    B, D, seed, off, draw = 3, 1024, 0x1234ABCD5678, 5, 7
+    out = torch.empty(B, D, device=dev)
+    rc = S.lib().sdd_philox_normal(out.data_ptr(), B, D, seed, off, draw, None)
+    assert rc == 0
+    ref = O.philox_normal(seed, np.arange(off, off + B), draw, D)
+    err = np.abs(out.cpu().numpy() - ref).max()
+    _report(test="philox", max_abs=float(err))
+    assert err < 2e-6
+    # in-kernel noise == the same stream
+    x = torch.zeros(B, D, device=dev)
+    eps = torch.zeros(1, B, D, device=dev)
+    s = O.Schedule(10)
+    xn, _, _, _ = S.superpose_update(x, eps, torch.zeros(B, 1, device=dev), s.alphas[3].item(), s.alpha_bars[3].item(),
+                                     s.betas[3].item(), seed=seed, sample_offset=off, draw_index=draw)
+    exp = torch.sqrt(s.betas[3]) * torch.from_numpy(ref)
+    assert torch.allclose(xn.cpu(), exp, atol=1e-6)
+
+
+# ------------------------------------------------------------------ tcgen05 conv
+def _conv_ref(act_bf16, w, bias):
+    a = act_bf16.float().permute(0, 3, 1, 2)
+    wr = w.to(torch.bfloat16).float()
+    y = F.conv2d(a, wr, None, padding=1) + bias[:, :, None, None]
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("Cin,Cout", [(64, 64), (64, 128), (128, 128), (128, 64)])
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 32, 24), (3, 48, 64)])
+def test_conv3x3_matches_fp32_conv_of_same_operands(S, dev, impl, Cin, Cout, B, H, W):
+    g = torch.Generator().manual_seed(Cin * 7 + Cout + H)
+    act = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    bias = torch.randn(B, Cout, generator=g)
+    ref = _conv_ref(act, w, bias)
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    mr = torch.zeros(B, 4, 2, device=dev)
+    a_d, w_d, b_d = act.to(dev), w.to(dev), bias.to(dev)
+    rc = S.lib().sdd_conv3x3_nhwc(a_d.data_ptr(), w_d.data_ptr(), b_d.data_ptr(), Cout, out.data_ptr(),
+                                  mr.data_ptr(), B, H, W, Cin, Cout, impl, None)
+    assert rc == 0, S.lib().sdd_last_error()
+    torch.cuda.synchronize()
+    o = out.float().cpu()
+    err = (o - ref).abs().max().item()
+    _report(test="conv", impl=impl, Cin=Cin, Cout=Cout, B=B, H=H, W=W, max_abs=err, ref_max=ref.abs().max().item())
+    assert torch.allclose(o, ref, rtol=8e-3, atol=8e-3), err
+    # GroupNorm(4, Cout) statistics of the conv output
+    rg = ref.reshape(B, H * W, 4, Cout // 4).permute(0, 2, 1, 3).reshape(B, 4, -1)
+    mean, var = rg.mean(2), rg.var(2, unbiased=False)
+    m = mr.cpu()
+    assert torch.allclose(m[..., 0], mean, atol=3e-3), (m[..., 0] - mean).abs().max()
+    assert torch.allclose(m[..., 1], 1 / torch.sqrt(var + 1e-5), rtol=5e-3)
+
+
+def test_gn_silu_apply(S, dev):
+    g = torch.Generator().manual_seed(11)
+    B, H, W, C = 2, 16, 8, 128
+    act = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    mr = torch.stack([torch.randn(B, 4, generator=g) * 0.1, torch.rand(B, 4, generator=g) + 0.5], -1)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    a = act.float().reshape(B, H * W, 4, C // 4)
+    ref = (a - mr[:, None, :, 0:1]) * mr[:, None, :, 1:2]
+    ref = ref.reshape(B, H, W, C) * gamma + beta
+    ref = F.silu(ref)
+    d, mr_d, g_d, b_d = act.to(dev), mr.contiguous().to(dev), gamma.to(dev), beta.to(dev)
+    rc = S.lib().sdd_gn_silu_apply(d.data_ptr(), mr_d.data_ptr(), g_d.data_ptr(), b_d.data_ptr(), B, H, W, C, None)
+    torch.cuda.synchronize()
+    assert rc == 0, S.lib().sdd_last_error()
+    assert torch.allclose(d.float().cpu(), ref, rtol=1e-2, atol=1e-2)
+
+
+# ------------------------------------------------------------------ UNet forward (K1)
+@pytest.mark.parametrize("wseed,xseed,B,R,t", [(0, 101, 2, 16, 0), (0, 101, 2, 16, 49), (1, 102, 2, 64, 1),
+                                               (1, 102, 2, 64, 999), (0, 103, 1, 128, 250)])
+def test_unet_forward_matches_oracle_and_golden(S, dev, golden_dir, wseed, xseed, B, R, t):
+    params, models = _models(S, dev, [wseed])
+    g = torch.Generator().manual_seed(xseed)
+    x = torch.randn((B, 1, R, R), generator=g)
+    tt = torch.full((B,), t, dtype=torch.long)
+    y = models[0](x.to(dev), tt.to(dev)).cpu()
+    with torch.no_grad():
+        ref = O.unet_forward(params[0], x, tt)
+    gold = torch.from_numpy(np.load(os.path.join(golden_dir, "unet_forward.npz"))[f"fwd_w{wseed}_x{xseed}_B{B}_R{R}_t{t}"])
+    assert torch.allclose(ref, gold, atol=2e-5)  # the oracle is the reference
+    rel, mx = _rel(y, gold), (y - gold).abs().max().item() / gold.abs().max().item()
+    _report(test="unet_forward", R=R, t=t, rel_l2=rel, relmax=mx)
+    assert rel <= 2e-2 and mx <= 5e-2
+
+
+def test_unet_forward_per_sample_timesteps_and_chunking(S, dev, monkeypatch):
+    """t may differ per sample (ddpm.py:28 draws random t); chunked execution must not change results."""
+    params, models = _models(S, dev, [1])
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn((5, 1, 32, 32), generator=g)
+    tt = torch.tensor([0, 3, 500, 998, 17])
+    with torch.no_grad():
+        ref = O.unet_forward(params[0], x, tt)
+    y = models[0](x.to(dev), tt.to(dev)).cpu()
+    assert _rel(y, ref) <= 2e-2
+    monkeypatch.setenv("SDD_CHUNK", "2")
+    p2, m2 = _models(S, dev, [1])
+    y2 = m2[0](x.to(dev), tt.to(dev)).cpu()
+    assert torch.equal(y, y2)
+
+
+def test_unet_rejects_bad_shapes(S, dev):
+    _, models = _models(S, dev, [0])
+    with pytest.raises(S.SddError):
+        models[0](torch.zeros(1, 1, 20, 20, device=dev), torch.zeros(1, dtype=torch.long, device=dev))
+
+
+# ------------------------------------------------------------------ DDPM.sample (K2) and superposition (K3, K5)
+def _draw_noise_stack(seed, shape, T):
+    torch.manual_seed(seed)
+    st = [torch.randn(shape)]
+    for _ in range(T - 1):
+        st.append(torch.randn_like(st[0]))
+    return torch.stack(st, 0)
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_ddpm_sample_matches_reference_golden(S, dev, golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "ddpm_sample.npz"))
+    wseed, nseed, T, *shape = [int(v) for v in g[f"sample_{name}_meta"]]
+    params, models = _models(S, dev, [wseed])
+    stack = _draw_noise_stack(nseed, tuple(shape), T)
+    y = S.DDPM(T).sample(models[0], tuple(shape), dev, noise=stack.to(dev)).cpu()
+    ref = torch.from_numpy(g[f"sample_{name}"])
+    rel, mx = _rel(y, ref), (y - ref).abs().max().item()
+    _report(test="ddpm_sample", name=name, T=T, rel_l2=rel, max_abs=mx)
+    assert rel <= 5e-2
+
+
+def test_ddpm_sample_default_rng_contract(S, dev):
+    """Default call consumes torch's generators like ddpm.py:33,36: same seed -> same sample."""
+    _, models = _models(S, dev, [0])
+    d = S.DDPM(5)
+    torch.manual_seed(3); torch.cuda.manual_seed_all(3)
+    a = d.sample(models[0], (2, 1, 16, 16), dev)
+    torch.manual_seed(3); torch.cuda.manual_seed_all(3)
+    b = d.sample(models[0], (2, 1, 16, 16), dev)
+    assert a.shape == (2, 1, 16, 16) and a.device.type == "cuda" and torch.equal(a, b)
+    torch.manual_seed(3); torch.cuda.manual_seed_all(3)
+    st = d.draw_noise_stack((2, 1, 16, 16), dev)
+    assert torch.equal(d.sample(models[0], (2, 1, 16, 16), dev, noise=st), a)
+
+
+def test_k3_self_superposition_equals_ddpm_sample_on_gpu(S, dev):
+    params, models = _models(S, dev, [0])
+    T, shape = 12, (2, 1, 16, 16)
+    stack = _draw_noise_stack(7, shape, T).to(dev)
+    d = S.DDPM(T)
+    y1 = d.sample(models[0], shape, dev, noise=stack)
+    y2, kap, lq = S.superposed_sample([models[0], models[0]], d, shape, dev, noise=stack, return_trajectory=True)
+    assert torch.equal(y1, y2)
+    assert torch.equal(kap, torch.full_like(kap, 0.5))
+    assert torch.equal(lq[..., 0], lq[..., 1]) and torch.equal(lq[0], torch.zeros_like(lq[0]))
+
+
+@pytest.mark.parametrize("T,shape", [(12, (2, 1, 16, 16)), (30, (3, 1, 32, 32)), (20, (2, 1, 64, 64))])
+def test_k5_superposed_two_models_matches_oracle(S, dev, T, shape):
+    params, models = _models(S, dev, [0, 1])
+    g = torch.Generator().manual_seed(T)
+    stack = torch.randn((T,) + shape, generator=g)
+    xr, kr, lr = O.superposed_sample(params, O.Schedule(T), stack)
+    x, kap, lq = S.superposed_sample(models, S.DDPM(T), shape, dev, noise=stack.to(dev), return_trajectory=True)
+    rel = _rel(x.cpu(), xr)
+    ek = (kap.cpu() - kr).abs().max().item()
+    el = ((lq.cpu() - lr).abs().max() / lr.abs().max()).item()
+    _report(test="superposed", T=T, shape=list(shape), x_rel_l2=rel, kappa_abs=ek, logq_rel=el,
+            kappa_min=kr.min().item(), kappa_max=kr.max().item())
+    assert rel <= 5e-2 and ek <= 5e-2 and el <= 2e-2
+
+
+def test_graph_equals_eager_and_philox_shard_invariance(S, dev):
+    _, models = _models(S, dev, [0, 1])
+    d = S.DDPM(8)
+    shape = (4, 1, 32, 32)
+    a = S.superposed_sample(models, d, shape, dev, seed=42, use_graph=True)
+    b = S.superposed_sample(models, d, shape, dev, seed=42, use_graph=False)
+    assert torch.equal(a, b)
+    lo = S.superposed_sample(models, d, (2, 1, 32, 32), dev, seed=42, sample_offset=0)
+    hi = S.superposed_sample(models, d, (2, 1, 32, 32), dev, seed=42, sample_offset=2)
+    assert torch.equal(torch.cat([lo, hi]), a)  # batch sharding changes no bit
+    c = S.superposed_sample(models, d, shape, dev, seed=43)
+    assert not torch.equal(a, c)
+    # Philox mode == oracle fed the same (numpy-restated) noise stack
+    st = O.philox_noise_stack(42, range(4), 8, (1, 32, 32))
+    params = [O.init_unet_params(0), O.init_unet_params(1)]
+    xr, _, _ = O.superposed_sample(params, O.Schedule(8), st)
+    assert _rel(a.cpu(), xr) <= 5e-2
+
+
+def test_size_independent_properties_at_full_size(S, dev):
+    """At BASELINE config-2 size (128x128, batch 16): kappa rows sum to 1, logq[0] = 0, finite output,
+    determinism across calls."""
+    _, models = _models(S, dev, [0, 1])
+    d = S.DDPM(6)
+    shape = (16, 1, 128, 128)
+    x, kap, lq = S.superposed_sample(models, d, shape, dev, seed=1, return_trajectory=True)
+    assert torch.isfinite(x).all() and torch.isfinite(lq).all()
+    assert torch.allclose(kap.sum(-1), torch.ones_like(kap[..., 0]), atol=1e-6)
+    assert torch.equal(lq[0], torch.zeros_like(lq[0]))
+    x2 = S.superposed_sample(models, d, shape, dev, seed=1)
+    assert torch.equal(x, x2)
