@@ -203,11 +203,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B; 8-row
 // swizzle atoms 1024 B apart).  Field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);  // start address, 16-byte units
   d |= (uint64_t)1 << 16;                      // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset: next 8-row group
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;       // stride byte offset: next 8-row group
   d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
   return d;

@@ -24,11 +24,19 @@ constexpr int kHaloRows = (kTileH + 2) * kTileW;  // 144 smem rows per kx load
 constexpr int kABytes = kHaloRows * 128;          // 18432
 constexpr int kConvThreads = 256;
 
-template <int COUT>
+// HALO experiment: one (64 ci, 10 w, 18 h) box per stage; the 9 taps are descriptor views starting at
+// row (ky*10 + kx) with a 1280-byte stride between 8-row groups (start not 1024-aligned, SBO not a multiple
+// of 1024) -- tests whether UMMA applies the 128B swizzle on absolute smem address bits.
+constexpr int kHaloW = kTileW + 2;
+constexpr int kHaloBytes = ((kTileH + 2) * kHaloW * 128 + 1023) / 1024 * 1024;  // 23552
+
+template <int COUT, bool HALO = false>
 struct ConvCfg {
   static constexpr int kBBytes = 3 * COUT * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (COUT == 64) ? 5 : 3;
+  static constexpr int kAStage = HALO ? kHaloBytes : kABytes;
+  static constexpr int kStageBytes = kAStage + kBBytes;
+  static constexpr int kTxBytes = (HALO ? (kTileH + 2) * kHaloW * 128 : kABytes) + kBBytes;
+  static constexpr int kStages = (COUT == 64) ? (HALO ? 4 : 5) : 3;
   static constexpr int kTmemCols = 2 * COUT;  // 128 or 256: power of two >= 32
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -43,11 +51,11 @@ struct ConvTcArgs {
   int tiles_w, tiles_per_sample, num_tiles;
 };
 
-template <int COUT>
+template <int COUT, bool HALO = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const ConvTcArgs a) {
-  using Cfg = ConvCfg<COUT>;
+  using Cfg = ConvCfg<COUT, HALO>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::kStages * Cfg::kStageBytes;
@@ -90,10 +98,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int kx = 0; kx < 3; ++kx)
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(empty_bar(stage), phase ^ 1u);
-            mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+            mbar_arrive_expect_tx(full_bar(stage), Cfg::kTxBytes);
             const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-            tma_load_4d(sa, &tmA, full_bar(stage), kc * 64, w0 + kx - 1, h0 - 1, n);
-            tma_load_3d(sa + kABytes, &tmB, full_bar(stage), kc * 64, 0, kx * 3);
+            tma_load_4d(sa, &tmA, full_bar(stage), kc * 64, HALO ? w0 - 1 : w0 + kx - 1, h0 - 1, n);
+            tma_load_3d(sa + Cfg::kAStage, &tmB, full_bar(stage), kc * 64, 0, kx * 3);
             if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
           }
       }
@@ -112,10 +120,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sb = sa + Cfg::kAStage;
+          const int kx = it / kchunks;
 #pragma unroll
           for (int ky = 0; ky < 3; ++ky) {
-            const uint64_t adesc = umma_desc_sw128(sa + ky * (kTileW * 128));
+            const uint64_t adesc = HALO ? umma_desc_sw128(sa + (ky * kHaloW + kx) * 128, kHaloW * 128)
+                                        : umma_desc_sw128(sa + ky * (kTileW * 128));
             const uint64_t bdesc = umma_desc_sw128(sb + ky * (COUT * 128));
 #pragma unroll
             for (int k = 0; k < 4; ++k)  // 4 x UMMA_K(16 bf16 = 32 B) inside the 128-byte swizzle row

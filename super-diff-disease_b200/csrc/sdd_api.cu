@@ -73,12 +73,12 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 // act bf16 [N][H][W][C]  ->  box (64 c, 8 w, 18 h, 1 n), 128-byte swizzle, zero fill out of bounds
-static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C) {
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, bool halo = false) {
   EncodeTiledFn enc = get_encode();
   SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)kTileW, (cuuint32_t)(kTileH + 2), 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)(halo ? kHaloW : kTileW), (cuuint32_t)(kTileH + 2), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -121,12 +121,16 @@ static int conv_tc_init() {
                                 ConvCfg<64>::kSmemBytes));
   SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 ConvCfg<128>::kSmemBytes));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<64, true>::kSmemBytes));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ConvCfg<128, true>::kSmemBytes));
   done = true;
   return SDD_OK;
 }
 
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, __nv_bfloat16* out, BiasRef bias,
-                          GnScratch gn, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+                          GnScratch gn, int B, int H, int W, int Cin, int Cout, cudaStream_t st, bool halo = false) {
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
   SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
   ConvTcArgs a;
@@ -138,7 +142,12 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, __nv_b
   a.num_tiles = B * a.tiles_per_sample;
   int grid = std::min(a.num_tiles, num_sms());
   SDD_TRY(conv_tc_init());
-  if (Cout == 64)
+  if (halo) {
+    if (Cout == 64)
+      conv3x3_tc_kernel<64, true><<<grid, kConvThreads, ConvCfg<64, true>::kSmemBytes, st>>>(tmA, tmB, a);
+    else
+      conv3x3_tc_kernel<128, true><<<grid, kConvThreads, ConvCfg<128, true>::kSmemBytes, st>>>(tmA, tmB, a);
+  } else if (Cout == 64)
     conv3x3_tc_kernel<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(tmA, tmB, a);
   else
     conv3x3_tc_kernel<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(tmA, tmB, a);
@@ -718,7 +727,7 @@ int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t
   ++g_launches;
   BiasRef br{bias, nullptr, 0, bias_batch_stride};
   int rc = SDD_OK;
-  if (impl == 0) {
+  if (impl == 0 || impl == 2) {
     const int tiles_ps = (H / kTileH) * (W / kTileW);
     CUtensorMap tmA, tmB;
     rc = (H % kTileH == 0 && W % kTileW == 0) ? SDD_OK : SDD_EINVAL;
@@ -727,10 +736,11 @@ int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t
     if (rc == SDD_OK && cudaMalloc(&counters, (size_t)B * sizeof(int)) != cudaSuccess) rc = SDD_ENOMEM;
     if (rc == SDD_OK && cudaMalloc(&mr, (size_t)B * 8 * sizeof(float)) != cudaSuccess) rc = SDD_ENOMEM;
     if (rc == SDD_OK) cudaMemsetAsync(counters, 0, (size_t)B * sizeof(int), st);
-    if (rc == SDD_OK) rc = make_act_map(&tmA, act, B, H, W, Cin);
+    if (rc == SDD_OK) rc = make_act_map(&tmA, act, B, H, W, Cin, impl == 2);
     if (rc == SDD_OK) rc = make_wt_map(&tmB, wt, Cout, Cin);
     if (rc == SDD_OK)
-      rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
+      rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st,
+                          impl == 2);
     if (rc == SDD_OK && gn_meanrstd)
       cudaMemcpyAsync(gn_meanrstd, mr, (size_t)B * 8 * sizeof(float), cudaMemcpyDeviceToDevice, st);
   } else {
