@@ -136,23 +136,23 @@ def workload_config(args, world):
 
 
 # ----------------------------------------------------------------------------- dominant-kernel roofline leg
-def conv_roofline(S, dev, R, chunk, iters=20):
+def conv_roofline(S, dev, R, chunk, iters=20, cin=128, cout=128, impl=2, flush_l2=True):
     """Mean duration of the dominant kernel (tcgen05 128->128 3x3 conv) at the shape the sampler launches it
     with (chunk samples of RxR): CUDA events around each launch on the launching stream (sdd_conv3x3_profile),
     256 MiB rewritten before every launch to flush L2."""
     import ctypes
     lib = S.lib()
-    act = torch.randn(chunk, R, R, 128, device=dev).to(torch.bfloat16)
-    w = torch.randn(128, 128, 3, 3, device=dev) * 0.03
-    bias = torch.zeros(128, device=dev)
-    out = torch.empty_like(act)
+    act = torch.randn(chunk, R, R, cin, device=dev).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, device=dev) * 0.03
+    bias = torch.zeros(cout, device=dev)
+    out = torch.empty(chunk, R, R, cout, device=dev, dtype=torch.bfloat16)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ms = ctypes.c_float()
-    rc = lib.sdd_conv3x3_profile(act.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), chunk, R, R, 128, 128,
-                                 iters, flush.data_ptr(), flush.numel(), ctypes.byref(ms),
+    rc = lib.sdd_conv3x3_profile(act.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), chunk, R, R, cin, cout,
+                                 impl, iters, flush.data_ptr(), flush.numel() if flush_l2 else 0, ctypes.byref(ms),
                                  torch.cuda.current_stream().cuda_stream)
     assert rc == 0, lib.sdd_last_error()
-    flops = 2.0 * MAC_128x128 * chunk * R * R
+    flops = 2.0 * 9 * cin * cout * chunk * R * R
     return flops / (ms.value * 1e-3) / 1e12, ms.value
 
 
@@ -290,7 +290,7 @@ def main():
 
     if rank == 0:
         hbm, tf_burst, tf_sust, src = peaks()
-        chunk = int(os.environ.get("SDD_CHUNK", "0")) or max(1, min(B, (96 << 20) // (R * R * 128 * 2 * 2)))
+        chunk = int(os.environ.get("SDD_CHUNK", "0")) or max(1, min(B, (1536 << 20) // (R * R * 128 * 2)))
         conv_tf, conv_ms = conv_roofline(S, dev, R, chunk)
         upd_gbs, upd_ms = update_roofline(S, dev, B, D)
         step_flops = 2.0 * CONV_MAC_PER_PIXEL * D * M * T  # per sample
@@ -300,7 +300,7 @@ def main():
                 "config": workload_config(args, world), "clocks": clk,
                 "gpu_launches": int(launches) * args.steps * world,
                 "whole_path_tensor_frac_of_sustained": value / world * step_flops / (tf_sust * 1e12),
-                "roofline": {"kernel": "conv3x3_tc_kernel<128> (128->128, 66.6% of conv FLOPs)", "bound": "tensor",
+                "roofline": {"kernel": "conv3x3_tc2_kernel<128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)", "bound": "tensor",
                              "achieved": conv_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_tf / tf_burst,
                              "traffic": None, "peak_source": f"{src} bf16 burst", "launch_ms": conv_ms,
                              "how": f"kernel alone at the sampler's launch shape ({chunk}x{R}x{R}x128), CUDA events "

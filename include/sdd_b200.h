@@ -121,6 +121,13 @@ int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t
                      void* out, float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, int impl,
                      void* stream);
 
+/* The product kernel: GroupNorm(4,Cin)+SiLU of the RAW input (statistics in_meanrstd[B,4,2], affine in_gamma/in_beta[Cin])
+ * fused with the 3x3 conv, bias add and the OUTPUT's GroupNorm(4,Cout) statistics (unet.py:21-28 in one launch).
+ * in_meanrstd == NULL: the input is used as is.  2-CTA tcgen05 kernel with resident weights. */
+int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const float* in_gamma, const float* in_beta,
+                           const float* w, const float* bias, int64_t bias_batch_stride, void* out,
+                           float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, void* stream);
+
 /* In place on bf16 NHWC act[B,H,W,C]: silu((v - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]), G = 4. */
 int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta,
                       int B, int H, int W, int C, void* stream);
@@ -128,8 +135,10 @@ int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, cons
 /* Kernel-only timing for the roofline numbers (bench.py): `iters` launches, each bracketed by CUDA events
  * on the launching stream; `flush` (may be NULL) is rewritten before every launch to evict L2.
  * *ms_host receives the mean kernel duration in milliseconds. */
+/* impl: 0 = v1 kernel (streamed weights, pre-activated input), 1 = product kernel without the fused GroupNorm,
+ * 2 = product kernel with the fused GroupNorm+SiLU (identity statistics). */
 int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W,
-                        int Cin, int Cout, int iters, void* flush, size_t flush_bytes, float* ms_host,
+                        int Cin, int Cout, int impl, int iters, void* flush, size_t flush_bytes, float* ms_host,
                         void* stream);
 int sdd_superpose_update_profile(float* x, const float* eps, const float* noise, float* logq, int B, int D,
                                  int M, int iters, void* flush, size_t flush_bytes, float* ms_host,

@@ -39,8 +39,9 @@ SYMBOLS = {
     "sdd_sampler_destroy": (_i, [_vp]),
     "sdd_sampler_launches_per_run": (_i64, [_vp]),
     "sdd_conv3x3_nhwc": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sdd_conv3x3_fused_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sdd_gn_silu_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "sdd_conv3x3_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, ctypes.POINTER(_f), _vp]),
+    "sdd_conv3x3_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, ctypes.POINTER(_f), _vp]),
     "sdd_superpose_update_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, ctypes.POINTER(_f), _vp]),
 }
 

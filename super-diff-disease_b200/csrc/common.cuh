@@ -74,18 +74,57 @@ __device__ __forceinline__ void gn_publish_and_finalize_warp(
   if (!is_last) return;
   __threadfence();
   const float* src = partials + (size_t)b * nparts * G * 2;
-  for (int g = 0; g < G; ++g) {
-    double s = 0.0, ss = 0.0;
-    for (int p = lane; p < nparts; p += 32) {
-      s += (double)__ldcg(src + ((size_t)p * G + g) * 2 + 0);
-      ss += (double)__ldcg(src + ((size_t)p * G + g) * 2 + 1);
-    }
+  // fixed-order reduction: lane l owns parts l, l+32, ...; all loads of a batch are issued before any add
+  double acc[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+  const int GG = G * 2;  // floats per part (2 or 8)
+  if (GG == 8) {
+    for (int base = 0; base < nparts; base += 32 * 8) {
+      float4 va[8], vb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int p = base + lane + 32 * u;
+        if (p < nparts) {
+          va[u] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)p * 8));
+          vb[u] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)p * 8 + 4));
+        } else {
+          va[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          vb[u] = va[u];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        acc[0] += (double)va[u].x; acc[1] += (double)va[u].y; acc[2] += (double)va[u].z; acc[3] += (double)va[u].w;
+        acc[4] += (double)vb[u].x; acc[5] += (double)vb[u].y; acc[6] += (double)vb[u].z; acc[7] += (double)vb[u].w;
+      }
     }
-    if (lane == 0) {
+  } else {
+    for (int base = 0; base < nparts; base += 32 * 8) {
+      float v[8][2];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int p = base + lane + 32 * u;
+        v[u][0] = p < nparts ? __ldcg(src + (size_t)p * GG) : 0.f;
+        v[u][1] = p < nparts ? __ldcg(src + (size_t)p * GG + 1) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc[0] += (double)v[u][0]; acc[1] += (double)v[u][1]; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  }
+  if (lane == 0) {
+    for (int g = 0; g < G; ++g) {
+      double s = 0.0, ss = 0.0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {  // static indexing keeps acc[] in registers
+        if (i == 2 * g) s = acc[i];
+        if (i == 2 * g + 1) ss = acc[i];
+      }
       double mean = s / (double)count_per_group;
       double var = ss / (double)count_per_group - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -199,6 +238,21 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+// 32-byte (one full sector) global store per thread
+__device__ __forceinline__ void st_global_v8(void* p, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (rows of 64 bf16 = 128 B; 8-row
@@ -215,6 +269,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
 // kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, M x N.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// One lane of a converged warp; ptxas then knows the guarded region runs single-threaded and feeds
+// tcgen05 / TMA descriptors through uniform registers without a per-instruction waterfall loop.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {

@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "unet_kernels.cuh"
 #include "update.cuh"
 
@@ -107,6 +108,24 @@ static int make_wt_map(CUtensorMap* m, const void* base, int Cout, int Cin) {
   return SDD_OK;
 }
 
+// v2: wt bf16 [9][Cout][Cin] -> box (64 ci, Cout/2 rows, 1 tap): each CTA of a pair keeps its N half resident
+static int make_wt_map2(CUtensorMap* m, const void* base, int Cout, int Cin) {
+  EncodeTiledFn enc = get_encode();
+  SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)(Cout / 2), 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(wt2) failed: " + std::to_string((int)r));
+    return SDD_ECUDA;
+  }
+  return SDD_OK;
+}
+
 // ------------------------------------------------------------------------------- conv launchers
 struct GnScratch {
   float* partials;
@@ -155,6 +174,47 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, __nv_b
   return SDD_OK;
 }
 
+struct GnInput {  // GroupNorm(4, Cin) + SiLU applied to the conv's input inside the kernel (nullptr: none)
+  const float* meanrstd;
+  const float* gamma;
+  const float* beta;
+};
+
+static int launch_conv_tc2(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2, __nv_bfloat16* out, BiasRef bias,
+                           GnInput in, GnScratch gn, int B, int H, int W, int Cin, int Cout, cudaStream_t st,
+                           int dbg = 0, long long* trace = nullptr) {
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
+  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
+  static bool attr = false;
+  if (!attr) {
+    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  conv_tc2_smem_bytes(64, 128, conv_tc2_stages(64, 128))));
+    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  conv_tc2_smem_bytes(128, 128, conv_tc2_stages(128, 128))));
+    attr = true;
+  }
+  ConvTc2Args a;
+  a.in = nullptr; a.out = out; a.bias = bias;
+  a.in_meanrstd = in.meanrstd; a.in_gamma = in.gamma; a.in_beta = in.beta;
+  a.partials = gn.partials; a.counters = gn.counters; a.meanrstd = gn.meanrstd;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+  a.tiles_w = W / kTileW;
+  a.tiles_per_sample = (H / kTileH) * a.tiles_w;
+  a.num_tiles = B * a.tiles_per_sample;
+  a.num_pairs = (a.num_tiles + 1) / 2;
+  a.stages = conv_tc2_stages(Cout, Cin);
+  a.dbg = dbg;
+  a.trace = trace;
+  const int smem = conv_tc2_smem_bytes(Cout, Cin, a.stages);
+  const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
+  if (Cout == 64)
+    conv3x3_tc2_kernel<64><<<grid, kC2Threads, smem, st>>>(tmA_halo, tmB2, a);
+  else
+    conv3x3_tc2_kernel<128><<<grid, kC2Threads, smem, st>>>(tmA_halo, tmB2, a);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
 static int launch_apply(__nv_bfloat16* act, const float* meanrstd, const float* gamma, const float* beta, int B,
                         int H, int W, int C, cudaStream_t st) {
   size_t nvec = (size_t)H * W * C / 8;
@@ -176,10 +236,11 @@ struct BlockParams {
   int cin, cout;
   const float *gn1_w, *gn1_b, *conv1_w, *conv1_b, *gn2_w, *gn2_b, *conv2_w, *conv2_b, *temb_w, *temb_b;
   __nv_bfloat16 *conv1_wt, *conv2_wt;  // bf16 [kx][ky][Cout][Cin] (tensor-core convs only)
-  CUtensorMap tm_w1, tm_w2;
+  CUtensorMap tm_w1, tm_w2;      // v1 kernel: box (64, Cout, 3 taps)
+  CUtensorMap tm_w1h, tm_w2h;    // v2 kernel: box (64, Cout/2, 1 tap)
 };
 
-constexpr int kBiasRow = 64 + 128 + 128 + 64 + 1;  // 385: per-block (conv2 bias + time_emb) rows
+constexpr int kBiasRow = 388;  // 64+128+128+64+1 = 385 per-block (conv2 bias + time_emb) values, padded to 16 B
 constexpr int kBiasOff[5] = {0, 64, 192, 320, 384};
 constexpr int kBlkCin[5] = {1, 64, 128, 128, 64};
 constexpr int kBlkCout[5] = {64, 128, 128, 64, 1};
@@ -194,7 +255,8 @@ struct Workspace {
   int* counters = nullptr;
   float* meanrstd = nullptr;  // 10 x [cap_b][4][2]
   float* xstats = nullptr;    // [cap_b][2] (used when the caller has no stats of x)
-  CUtensorMap tm_act[2][2];   // [buffer][Cin == 128]
+  CUtensorMap tm_act[2][2];   // [buffer][Cin == 128], v1 box (64, 8, 18)
+  CUtensorMap tm_halo[2][2];  // v2 halo box (64, 10, 18)
   void release() {
     cudaFree(act[0]); cudaFree(act[1]); cudaFree(e1); cudaFree(partials); cudaFree(counters);
     cudaFree(meanrstd); cudaFree(xstats);
@@ -225,9 +287,11 @@ int chunk_for(int B, int H, int W) {
     int c = atoi(e);
     if (c > 0) return std::min(c, B);
   }
-  // keep the two ping-pong activation tensors of a chunk inside L2 (~126 MB): 2 * c * H*W*128*2 B <= 96 MB
-  size_t per_sample = (size_t)H * W * 128 * 2 * 2;
-  int c = (int)std::max<size_t>(1, (96u << 20) / per_sample);
+  // Measured (tools/conv_chunk.py): the conv kernels are far from HBM-bound (<= 1.5 TB/s of traffic), while every
+  // launch pays a fixed prologue (resident-weight load, TMEM alloc) and a partially filled last wave, so large
+  // chunks win: 128->128 goes from 0.53 of peak at 3 samples to 0.65 at >= 16.  Cap a ping-pong buffer at 1.5 GB.
+  size_t per_sample = (size_t)H * W * 128 * 2;
+  int c = (int)std::max<size_t>(1, ((size_t)1536 << 20) / per_sample);
   return std::min(c, B);
 }
 
@@ -250,6 +314,8 @@ int ensure_workspace(sdd_unet* u, int B, int H, int W) {
   for (int bi = 0; bi < 2; ++bi) {
     SDD_TRY(make_act_map(&ws.tm_act[bi][0], ws.act[bi], need, H, W, 64));
     SDD_TRY(make_act_map(&ws.tm_act[bi][1], ws.act[bi], need, H, W, 128));
+    SDD_TRY(make_act_map(&ws.tm_halo[bi][0], ws.act[bi], need, H, W, 64, true));
+    SDD_TRY(make_act_map(&ws.tm_halo[bi][1], ws.act[bi], need, H, W, 128, true));
   }
   ws.cap_b = need; ws.H = H; ws.W = W;
   ++ws.generation;
@@ -290,8 +356,7 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
   const int HW = H * W;
   const int chunk = ws.cap_b;
   const dim3 egrid((W + kCinTW - 1) / kCinTW, (H + kCinTH - 1) / kCinTH, 1);
-  const int tiles_ps = (H / kTileH) * (W / kTileW);
-  (void)tiles_ps;
+  static const bool use_v1 = getenv("SDD_CONV_V1") != nullptr;  // A/B switch: v1 = streamed weights + apply passes
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = std::min(chunk, B - b0);
     const float* xc = x + (size_t)b0 * HW;
@@ -314,20 +379,36 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     conv_in_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
                                        ws.partials, ws.counters, mr(0), H, W);
     SDD_LAUNCH_CHECK();
-    SDD_TRY(launch_apply(ws.act[0], mr(0), d0.gn2_w, d0.gn2_b, nb, H, W, 64, st));
-    SDD_TRY(launch_conv_tc(ws.tm_act[0][0], d0.tm_w2, ws.act[1], bias_time(0), gn(1), nb, H, W, 64, 64, st));
-    // downs.1, mid, ups.0: two tensor-core convs each, ping-ponging act[1] -> act[0] -> act[1]
-    int cur = 1, gi = 1;
-    for (int bi = 1; bi <= 3; ++bi) {
-      const BlockParams& p = u->blk[bi];
-      SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn1_w, p.gn1_b, nb, H, W, p.cin, st));
-      SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cin == 128], p.tm_w1, ws.act[cur ^ 1], bias_const(p.conv1_b),
-                             gn(gi + 1), nb, H, W, p.cin, p.cout, st));
-      cur ^= 1; ++gi;
-      SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn2_w, p.gn2_b, nb, H, W, p.cout, st));
-      SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cout == 128], p.tm_w2, ws.act[cur ^ 1], bias_time(bi), gn(gi + 1), nb,
-                             H, W, p.cout, p.cout, st));
-      cur ^= 1; ++gi;
+    int cur, gi;
+    if (use_v1) {
+      SDD_TRY(launch_apply(ws.act[0], mr(0), d0.gn2_w, d0.gn2_b, nb, H, W, 64, st));
+      SDD_TRY(launch_conv_tc(ws.tm_act[0][0], d0.tm_w2, ws.act[1], bias_time(0), gn(1), nb, H, W, 64, 64, st));
+      cur = 1; gi = 1;
+      for (int bi = 1; bi <= 3; ++bi) {
+        const BlockParams& p = u->blk[bi];
+        SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn1_w, p.gn1_b, nb, H, W, p.cin, st));
+        SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cin == 128], p.tm_w1, ws.act[cur ^ 1], bias_const(p.conv1_b),
+                               gn(gi + 1), nb, H, W, p.cin, p.cout, st));
+        cur ^= 1; ++gi;
+        SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn2_w, p.gn2_b, nb, H, W, p.cout, st));
+        SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cout == 128], p.tm_w2, ws.act[cur ^ 1], bias_time(bi), gn(gi + 1),
+                               nb, H, W, p.cout, p.cout, st));
+        cur ^= 1; ++gi;
+      }
+    } else {
+      // v2: every tensor-core conv normalises + activates its own input (GroupNorm+SiLU fused on the operand path)
+      SDD_TRY(launch_conv_tc2(ws.tm_halo[0][0], d0.tm_w2h, ws.act[1], bias_time(0), GnInput{mr(0), d0.gn2_w, d0.gn2_b},
+                              gn(1), nb, H, W, 64, 64, st));
+      cur = 1; gi = 1;
+      for (int bi = 1; bi <= 3; ++bi) {
+        const BlockParams& p = u->blk[bi];
+        SDD_TRY(launch_conv_tc2(ws.tm_halo[cur][p.cin == 128], p.tm_w1h, ws.act[cur ^ 1], bias_const(p.conv1_b),
+                                GnInput{mr(gi), p.gn1_w, p.gn1_b}, gn(gi + 1), nb, H, W, p.cin, p.cout, st));
+        cur ^= 1; ++gi;
+        SDD_TRY(launch_conv_tc2(ws.tm_halo[cur][p.cout == 128], p.tm_w2h, ws.act[cur ^ 1], bias_time(bi),
+                                GnInput{mr(gi), p.gn2_w, p.gn2_b}, gn(gi + 1), nb, H, W, p.cout, p.cout, st));
+        cur ^= 1; ++gi;
+      }
     }
     // ups.1: GN(4,64)+SiLU apply, 64->1 conv, then GN(1,1)+SiLU fused into the 1->1 conv (+ time bias)
     const BlockParams& u1 = u->blk[4];
@@ -393,17 +474,18 @@ int sdd_unet_create(sdd_unet_t** out, const float* const* tensors, int num_tenso
   __nv_bfloat16* wp = u->wt;
   for (int i = 0; i < 5; ++i) {
     BlockParams& b = u->blk[i];
-    auto conv = [&](const float* w, int cout, int cin, __nv_bfloat16** dst, CUtensorMap* tm) -> int {
+    auto conv = [&](const float* w, int cout, int cin, __nv_bfloat16** dst, CUtensorMap* tm, CUtensorMap* tmh) -> int {
       int total_w = 9 * cout * cin;
       conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wp, cout, cin);
       SDD_LAUNCH_CHECK();
       *dst = wp;
       SDD_TRY(make_wt_map(tm, wp, cout, cin));
+      SDD_TRY(make_wt_map2(tmh, wp, cout, cin));
       wp += total_w;
       return SDD_OK;
     };
-    if (b.cin >= 64 && b.cout >= 64) { int r = conv(b.conv1_w, b.cout, b.cin, &b.conv1_wt, &b.tm_w1); if (r) return fail(r); }
-    if (b.cout >= 64) { int r = conv(b.conv2_w, b.cout, b.cout, &b.conv2_wt, &b.tm_w2); if (r) return fail(r); }
+    if (b.cin >= 64 && b.cout >= 64) { int r = conv(b.conv1_w, b.cout, b.cin, &b.conv1_wt, &b.tm_w1, &b.tm_w1h); if (r) return fail(r); }
+    if (b.cout >= 64) { int r = conv(b.conv2_w, b.cout, b.cout, &b.conv2_wt, &b.tm_w2, &b.tm_w2h); if (r) return fail(r); }
   }
   // sinusoid frequencies exactly as unet.py:14 evaluates them in fp32
   float hf[kTimeDim / 2];
@@ -765,32 +847,53 @@ int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t
 // Kernel-only timing for the roofline: `iters` launches of the tcgen05 conv at one shape, each bracketed by
 // CUDA events on the launching stream, with `flush_bytes` of `flush` rewritten before every launch (L2 flush).
 int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
-                        int Cout, int iters, void* flush, size_t flush_bytes, float* ms_host, void* stream) {
+                        int Cout, int impl, int iters, void* flush, size_t flush_bytes, float* ms_host, void* stream) {
   SDD_CHECK(act && w && bias && out && ms_host && iters > 0, "bad argument");
   SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "Cin, Cout must be 64 or 128");
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
   SDD_TRY(device_check());
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* wt = nullptr; float* partials = nullptr; int* counters = nullptr; float* mr = nullptr;
+  float* gin = nullptr;  // identity GroupNorm input: mean 0, rstd 1 | gamma 1 | beta 0
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   const int total_w = 9 * Cout * Cin, tiles_ps = (H / kTileH) * (W / kTileW);
   int rc = SDD_OK;
   CUtensorMap tmA, tmB;
   if (cudaMalloc(&wt, (size_t)total_w * 2) != cudaSuccess || cudaMalloc(&partials, (size_t)B * tiles_ps * 32) != cudaSuccess ||
-      cudaMalloc(&counters, (size_t)B * 4) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 32) != cudaSuccess) rc = SDD_ENOMEM;
+      cudaMalloc(&counters, (size_t)B * 4) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 32) != cudaSuccess ||
+      cudaMalloc(&gin, ((size_t)B * 8 + 256) * 4) != cudaSuccess) rc = SDD_ENOMEM;
   if (rc == SDD_OK) {
+    std::vector<float> h((size_t)B * 8 + 256, 0.f);
+    for (int i = 0; i < B * 4; ++i) h[2 * i + 1] = 1.f;
+    for (int i = 0; i < 128; ++i) h[(size_t)B * 8 + i] = 1.f;
+    cudaMemcpyAsync(gin, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
     cudaMemsetAsync(counters, 0, (size_t)B * 4, st);
     conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
-    rc = make_act_map(&tmA, act, B, H, W, Cin);
+    rc = make_act_map(&tmA, act, B, H, W, Cin, (impl & 15) != 0);
   }
-  if (rc == SDD_OK) rc = make_wt_map(&tmB, wt, Cout, Cin);
+  if (rc == SDD_OK) rc = (impl & 15) == 0 ? make_wt_map(&tmB, wt, Cout, Cin) : make_wt_map2(&tmB, wt, Cout, Cin);
+  GnInput gi{nullptr, nullptr, nullptr};
+  const int dbg = impl >> 4;
+  impl &= 15;
+  long long* trace = nullptr;
+  const char* trace_path = getenv("SDD_CONV_TRACE");
+  if (trace_path && impl != 0) { cudaMalloc(&trace, 2 * 6 * 64 * 4 * sizeof(long long)); }
+  if (impl == 2) gi = GnInput{gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128};
   if (rc == SDD_OK && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) rc = SDD_ECUDA;
   BiasRef br{bias, nullptr, 0, 0};
   double total = 0.0;
   for (int i = 0; rc == SDD_OK && i < iters + 2; ++i) {
     if (flush && flush_bytes) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
     cudaEventRecord(e0, st);
-    rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
+    if (impl == 0)
+      rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
+    else
+    {
+      if (trace) cudaMemsetAsync(trace, 0, 2 * 6 * 64 * 4 * sizeof(long long), st);
+      rc = launch_conv_tc2(tmA, tmB, (__nv_bfloat16*)out, br, gi, GnScratch{partials, counters, mr}, B,
+                           H, W, Cin, Cout, st, dbg, trace);
+    }
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("conv profile: kernel failed"); rc = SDD_ECUDA; break; }
     float ms = 0.f;
@@ -800,7 +903,21 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
   cudaStreamSynchronize(st);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr);
+  if (trace) {
+    std::vector<long long> h(2 * 6 * 64 * 4);
+    cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "w")) {
+      for (int c = 0; c < 2; ++c)
+        for (int r = 0; r < 6; ++r)
+          for (int i = 0; i < 64; ++i) {
+            const long long* p = &h[(((size_t)c * 6 + r) * 64 + i) * 4];
+            if (p[0] | p[1] | p[2] | p[3]) fprintf(f, "%d %d %d %lld %lld %lld %lld\n", c, r, i, p[0], p[1], p[2], p[3]);
+          }
+      fclose(f);
+    }
+    cudaFree(trace);
+  }
+  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr); cudaFree(gin);
   if (rc == SDD_OK) *ms_host = (float)(total / iters);
   return rc;
 }
@@ -839,6 +956,42 @@ int sdd_superpose_update_profile(float* x, const float* eps, const float* noise,
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws);
   if (rc == SDD_OK) *ms_host = (float)(total / iters);
   return rc;
+}
+
+int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const float* in_gamma, const float* in_beta,
+                           const float* w, const float* bias, int64_t bias_batch_stride, void* out,
+                           float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, void* stream) {
+  SDD_CHECK(act_raw && w && bias && out, "null argument");
+  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "Cin, Cout must be 64 or 128");
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
+  SDD_CHECK(!in_meanrstd || (in_gamma && in_beta), "in_gamma / in_beta required with in_meanrstd");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* wt = nullptr; float* partials = nullptr; int* counters = nullptr; float* mr = nullptr;
+  const int total_w = 9 * Cout * Cin, tiles_ps = (H / kTileH) * (W / kTileW);
+  int rc = SDD_OK;
+  CUtensorMap tmA, tmB;
+  if (cudaMalloc(&wt, (size_t)total_w * 2) != cudaSuccess || cudaMalloc(&partials, (size_t)B * tiles_ps * 32) != cudaSuccess ||
+      cudaMalloc(&counters, (size_t)B * 4) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 32) != cudaSuccess) {
+    set_error("cudaMalloc failed"); rc = SDD_ENOMEM;
+  }
+  if (rc == SDD_OK) {
+    cudaMemsetAsync(counters, 0, (size_t)B * 4, st);
+    conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
+    ++g_launches;
+    rc = make_act_map(&tmA, act_raw, B, H, W, Cin, true);
+  }
+  if (rc == SDD_OK) rc = make_wt_map2(&tmB, wt, Cout, Cin);
+  if (rc == SDD_OK)
+    rc = launch_conv_tc2(tmA, tmB, (__nv_bfloat16*)out, BiasRef{bias, nullptr, 0, bias_batch_stride},
+                         GnInput{in_meanrstd, in_gamma, in_beta}, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
+  if (rc == SDD_OK && gn_meanrstd)
+    cudaMemcpyAsync(gn_meanrstd, mr, (size_t)B * 32, cudaMemcpyDeviceToDevice, st);
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr);
+  if (rc != SDD_OK) return rc;
+  if (e != cudaSuccess) { set_error(std::string("conv3x3_fused: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
+  return SDD_OK;
 }
 
 int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta, int B, int H, int W,

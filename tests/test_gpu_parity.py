@@ -161,6 +161,46 @@ def test_conv3x3_matches_fp32_conv_of_same_operands(S, dev, impl, Cin, Cout, B, 
     assert torch.allclose(m[..., 1], 1 / torch.sqrt(var + 1e-5), rtol=5e-3)
 
 
+@pytest.mark.parametrize("fuse", [False, True])
+@pytest.mark.parametrize("Cin,Cout", [(64, 64), (64, 128), (128, 128), (128, 64)])
+@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (3, 16, 8), (2, 32, 24), (3, 48, 64), (2, 128, 128)])
+def test_conv3x3_fused_2cta_kernel(S, dev, fuse, Cin, Cout, B, H, W):
+    """The product conv kernel (2-CTA tcgen05, resident weights, halo views, fused GroupNorm+SiLU on the input)
+    vs an fp32 computation on the same bf16 operands.  Odd tile counts exercise the dummy-tile path."""
+    g = torch.Generator().manual_seed(Cin * 3 + Cout + H + B)
+    raw = (torch.randn(B, H, W, Cin, generator=g) * 1.7 + 0.3).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
+    bias = torch.randn(B, Cout, generator=g)
+    if fuse:
+        mr = torch.stack([torch.randn(B, 4, generator=g) * 0.3, torch.rand(B, 4, generator=g) + 0.4], -1).contiguous()
+        gamma, beta = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.2
+        a = raw.float().reshape(B, H * W, 4, Cin // 4)
+        a = (a - mr[:, None, :, 0:1]) * mr[:, None, :, 1:2]
+        act = F.silu(a.reshape(B, H, W, Cin) * gamma + beta).to(torch.bfloat16)
+        mr_d, g_d, b_d = mr.to(dev), gamma.to(dev), beta.to(dev)
+        ptrs = (mr_d.data_ptr(), g_d.data_ptr(), b_d.data_ptr())
+    else:
+        act, ptrs = raw, (None, None, None)
+    ref = _conv_ref(act, w, bias)
+    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    omr = torch.zeros(B, 4, 2, device=dev)
+    r_d, w_d, bias_d = raw.to(dev), w.to(dev), bias.to(dev)
+    rc = S.lib().sdd_conv3x3_fused_nhwc(r_d.data_ptr(), *ptrs, w_d.data_ptr(), bias_d.data_ptr(), Cout, out.data_ptr(),
+                                        omr.data_ptr(), B, H, W, Cin, Cout, None)
+    assert rc == 0, S.lib().sdd_last_error()
+    torch.cuda.synchronize()
+    o = out.float().cpu()
+    err = (o - ref).abs().max().item()
+    _report(test="conv_fused", fuse=fuse, Cin=Cin, Cout=Cout, B=B, H=H, W=W, max_abs=err, ref_max=ref.abs().max().item())
+    tol = 3e-2 if fuse else 8e-3  # fused: tanh.approx SiLU may move an activation by one bf16 ulp
+    assert torch.allclose(o, ref, rtol=tol, atol=tol), err
+    rg = ref.reshape(B, H * W, 4, Cout // 4).permute(0, 2, 1, 3).reshape(B, 4, -1)
+    mean, var = rg.mean(2), rg.var(2, unbiased=False)
+    m = omr.cpu()
+    assert torch.allclose(m[..., 0], mean, atol=5e-3), (m[..., 0] - mean).abs().max()
+    assert torch.allclose(m[..., 1], 1 / torch.sqrt(var + 1e-5), rtol=1e-2)
+
+
 def test_gn_silu_apply(S, dev):
     g = torch.Generator().manual_seed(11)
     B, H, W, C = 2, 16, 8, 128
