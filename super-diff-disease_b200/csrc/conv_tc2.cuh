@@ -27,11 +27,14 @@
 
 namespace sdd {
 
-constexpr int kC2Threads = 512;  // warps: 0 weights TMA, 1 MMA, 2 TMEM alloc, 3 stats publisher, 4-11 epilogue, 12-15 loaders
+constexpr int kC2XformWarps = 8;  // transform warps (2 per SM sub-partition: one warp alone is latency-bound)
+constexpr int kC2XformThreads = kC2XformWarps * 32;
+// warps: 0 TMA producer, 1 MMA, 2 TMEM alloc, 3 stats publisher, 4-11 epilogue, 12.. transform
+constexpr int kC2Threads = 384 + kC2XformThreads;
 constexpr int kC2MaxStages = 6;
 constexpr int kHaloRowsV2 = (kTileH + 2) * kHaloW;  // 180
 constexpr int kHaloVecs = kHaloRowsV2 * 8;          // 1440 16-byte vectors per stage
-constexpr int kVecsPerLoader = (kHaloVecs + 127) / 128;  // 12
+constexpr int kVecsPerLoader = (kHaloVecs + kC2XformThreads - 1) / kC2XformThreads;  // 6 with 8 warps
 constexpr int kC2SmemLimit = 232448;                // 227 KB
 
 struct ConvTc2Args {
@@ -175,7 +178,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(ready_bar(s), 8); mbar_init(empty_bar(s), 1); mbar_init(full_bar(s), 1); }
+    for (int s = 0; s < a.stages; ++s) { mbar_init(ready_bar(s), 2 * kC2XformWarps); mbar_init(empty_bar(s), 1); mbar_init(full_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
     mbar_init(w_bar, 1);
     for (int s = 0; s < 2; ++s) { mbar_init(sfull_bar(s), 8); mbar_init(sempty_bar(s), 1); }
@@ -361,7 +364,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp >= 12) {
     // ===================== transform warps: GroupNorm + SiLU on the landed halo box, in place ==========
-    const int tt = threadIdx.x - 384;  // 0..127
+    const int tt = threadIdx.x - 384;  // 0..kC2XformThreads-1
     __shared__ __align__(16) float s_ga[128], s_gb[128];
     const bool fuse = a.in_meanrstd != nullptr;
     // vector v = tt + 128*i sits at smem row v>>3, physical 16-byte chunk v&7; (v & 7) and (row & 7) are the
@@ -378,7 +381,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int n = tile / a.tiles_per_sample, tr = tile % a.tiles_per_sample;
       const int h0 = (tr / a.tiles_w) * kTileH, w0 = (tr % a.tiles_w) * kTileW;
       if (fuse && n != cur_n) {
-        named_bar_sync(2, 128);  // previous readers of s_ga/s_gb are done
+        named_bar_sync(2, kC2XformThreads);  // previous readers of s_ga/s_gb are done
         if (tt < a.Cin) {
           const int g = tt / (a.Cin / 4);
           const float mean = a.in_meanrstd[(n * 4 + g) * 2], rstd = a.in_meanrstd[(n * 4 + g) * 2 + 1];
@@ -386,7 +389,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           s_ga[tt] = sc;
           s_gb[tt] = a.in_beta[tt] - mean * sc;
         }
-        named_bar_sync(2, 128);
+        named_bar_sync(2, kC2XformThreads);
         cur_n = n;
       }
       for (int kc = 0; kc < kchunks; ++kc) {
@@ -403,7 +406,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
 #pragma unroll
           for (int i = 0; i < kVecsPerLoader; ++i) {
-            const int row = (tt >> 3) + 16 * i;
+            const int row = (tt >> 3) + (kC2XformThreads / 8) * i;
             const int hr = row / kHaloW, wr = row - hr * kHaloW;
             const int hh = h0 - 1 + hr, ww = w0 - 1 + wr;
             if (row < kHaloRowsV2 && hh >= 0 && hh < a.H && ww >= 0 && ww < a.W) okmask |= 1u << i;
@@ -416,24 +419,21 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint4 r[kVecsPerLoader];
 #pragma unroll
           for (int i = 0; i < kVecsPerLoader; ++i)
-            if ((okmask >> i) & 1u) r[i] = (a.dbg & 16) ? make_uint4(i, tt, i, tt) : *reinterpret_cast<const uint4*>(sp + (size_t)(tt + 128 * i) * 16);
+            if ((okmask >> i) & 1u) r[i] = *reinterpret_cast<const uint4*>(sp + (size_t)(tt + kC2XformThreads * i) * 16);
 #pragma unroll
           for (int i = 0; i < kVecsPerLoader; ++i) {
             if (!((okmask >> i) & 1u)) continue;  // padding stays the exact zeros TMA wrote
             uint32_t u[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (a.dbg & 128) continue;
               __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[j]);
-              float lo = fmaf(__low2float(hv), ga[2 * j], gb[2 * j]);
-              float hi = fmaf(__high2float(hv), ga[2 * j + 1], gb[2 * j + 1]);
-              if (a.dbg & 8) { lo = fmaf(lo, lo, lo); hi = fmaf(hi, hi, hi); }  // timing experiment: no MUFU
-              else { lo = silu_tanh(lo); hi = silu_tanh(hi); }
+              const float lo = silu_tanh(fmaf(__low2float(hv), ga[2 * j], gb[2 * j]));
+              const float hi = silu_tanh(fmaf(__high2float(hv), ga[2 * j + 1], gb[2 * j + 1]));
               u[j] = pack_bf16x2(lo, hi);
             }
-            if (!(a.dbg & 16)) *reinterpret_cast<uint4*>(sp + (size_t)(tt + 128 * i) * 16) = make_uint4(u[0], u[1], u[2], u[3]);
+            *reinterpret_cast<uint4*>(sp + (size_t)(tt + kC2XformThreads * i) * 16) = make_uint4(u[0], u[1], u[2], u[3]);
           }
-          if (!(a.dbg & 32)) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         }
         if (!w_ready) { mbar_wait(w_bar, 0); w_ready = true; }  // this CTA's weights have landed too
         __syncwarp();
