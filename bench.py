@@ -107,7 +107,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     R, T, M = args.res, args.diffusion_steps, 2
-    sB, sN = 2, 2
+    sB, sN = 4, 4
     for _ in range(args.warmup):
         cpu_reference_run(R, T, M, sB, 1, warm_steps=0)
     vals, t0 = [], time.perf_counter()
@@ -313,9 +313,9 @@ def main():
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
             t0 = time.perf_counter()
-            v, secs = cpu_reference_run(R, T, M, 2, 3)
+            v, secs = cpu_reference_run(R, T, M, 4, 8)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                                    "sample": f"B=2, 3 of {T} diffusion steps after 1 warm-up step "
+                                    "sample": f"B=4, 8 of {T} diffusion steps after 1 warm-up step "
                                               f"({secs:.1f} s of CPU work), extrapolated linearly in T"}
         print(json.dumps(line), flush=True)
     if world > 1:

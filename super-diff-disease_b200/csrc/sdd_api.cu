@@ -538,16 +538,20 @@ int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st) {
   SDD_CHECK(a.M >= 1 && a.M <= kMaxModels, "1 <= M <= 4");
   SDD_CHECK(a.D % 4 == 0 && a.D > 0 && a.B > 0, "D must be a positive multiple of 4");
   a.nblk = update_blocks_per_sample(a.D);
-  size_t part = (size_t)a.B * a.nblk * kPartialsPerBlock * sizeof(float);
-  part = (part + 255) & ~(size_t)255;
   a.partials = reinterpret_cast<float*>(workspace);
-  a.counters = reinterpret_cast<int*>(reinterpret_cast<char*>(workspace) + part);
   dim3 grid(a.nblk, a.B);
   switch (a.M) {
     case 1: superpose_update_kernel<1><<<grid, kUpdThreads, 0, st>>>(a); break;
     case 2: superpose_update_kernel<2><<<grid, kUpdThreads, 0, st>>>(a); break;
     case 3: superpose_update_kernel<3><<<grid, kUpdThreads, 0, st>>>(a); break;
     default: superpose_update_kernel<4><<<grid, kUpdThreads, 0, st>>>(a); break;
+  }
+  SDD_LAUNCH_CHECK();
+  switch (a.M) {
+    case 1: superpose_finalize_kernel<1><<<a.B, 256, 0, st>>>(a); break;
+    case 2: superpose_finalize_kernel<2><<<a.B, 256, 0, st>>>(a); break;
+    case 3: superpose_finalize_kernel<3><<<a.B, 256, 0, st>>>(a); break;
+    default: superpose_finalize_kernel<4><<<a.B, 256, 0, st>>>(a); break;
   }
   SDD_LAUNCH_CHECK();
   return SDD_OK;

@@ -10,7 +10,6 @@ namespace sdd {
 
 constexpr int kMaxModels = 4;
 constexpr int kUpdThreads = 256;
-constexpr int kUpdMaxBlocksPerSample = 64;
 
 // Per-timestep scalars, either passed by value (operator API) or read from a device table
 // indexed by the device-side step counter (captured step graph).
@@ -39,7 +38,6 @@ struct UpdateArgs {
   uint64_t seed;
   int64_t sample_offset;
   float* partials;           // [B][nblk][kPartialsPerBlock]
-  int* counters;             // [B]
   int B, D, M, nblk;
 };
 
@@ -62,11 +60,13 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)r * 2.328306436
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t q, uint32_t gsample, uint32_t draw) {
   uint4 r = philox4x32_10(make_uint4(q, gsample, draw, 0x5D1FFu), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   float4 o;
-  float rad0 = sqrtf(-2.0f * logf(u01(r.x)));
-  float rad1 = sqrtf(-2.0f * logf(u01(r.z)));
+  // accurate logf (the radius is ill-conditioned near u = 1); fast sqrt and sin/cos (angle in (-pi, pi], where the
+  // MUFU approximations are good to ~4e-7 absolute).  Normals agree with the float64 oracle to < 5e-6.
+  float rad0 = __fsqrt_rn(-2.0f * logf(u01(r.x)));
+  float rad1 = __fsqrt_rn(-2.0f * logf(u01(r.z)));
   float s0, c0, s1, c1;
-  sincospif(2.0f * u01(r.y) - 1.0f, &s0, &c0);
-  sincospif(2.0f * u01(r.w) - 1.0f, &s1, &c1);
+  __sincosf(3.14159265358979f * (2.0f * u01(r.y) - 1.0f), &s0, &c0);
+  __sincosf(3.14159265358979f * (2.0f * u01(r.w) - 1.0f), &s1, &c1);
   o.x = rad0 * s0; o.y = rad0 * c0; o.z = rad1 * s1; o.w = rad1 * c1;
   return o;
 }
@@ -83,69 +83,78 @@ __device__ __forceinline__ float ddpm_x_update(float x, float eb, float z, float
   return __fadd_rn(__fmul_rn(c1, __fsub_rn(x, __fmul_rn(c2, eb))), __fmul_rn(c3, z));
 }
 
+// One CTA = one segment of one sample: kSegVecPerThread float4 per thread and array (2048 elements), all loads
+// issued before any use.  Segment boundaries and every reduction order are fixed functions of D alone, so
+// logq / statistics are bit-identical for any batch sharding.  No atomics, no fences: per-segment partial sums go
+// to a small buffer and superpose_finalize_kernel (one CTA per sample) reduces them in a fixed order.
+constexpr int kSegVecPerThread = 2;
+constexpr int kSegVec = kUpdThreads * kSegVecPerThread;  // float4 per segment
+
 template <int M>
-__global__ void __launch_bounds__(kUpdThreads) superpose_update_kernel(const UpdateArgs a) {
-  const int b = blockIdx.y;
-  const int blk = blockIdx.x;
-  const int tid = threadIdx.x;
+__device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, int b, float (&kap)[M]) {
+  float lg[M], mx = -INFINITY;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    lg[m] = a.temperature * a.logq[b * M + m] + (a.bias ? a.bias[m] : 0.0f);
+    mx = fmaxf(mx, lg[m]);
+  }
+  float den = 0.0f;
+#pragma unroll
+  for (int m = 0; m < M; ++m) { kap[m] = expf(lg[m] - mx); den += kap[m]; }
+#pragma unroll
+  for (int m = 0; m < M; ++m) kap[m] = kap[m] / den;
+}
+
+template <int M>
+__global__ void __launch_bounds__(kUpdThreads, 4) superpose_update_kernel(const UpdateArgs a) {
+  const int b = blockIdx.y, seg = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const int step = a.step_ptr ? *a.step_ptr : 0;
   const StepScalars sc = a.table ? a.table[step] : a.sc;
+  const int nq = a.D >> 2;
+  const bool have_noise = sc.draw_index >= 0;
+  const bool noise_tensor = a.noise != nullptr && have_noise;
 
-  // kappa = softmax(temperature * logq + bias), recomputed by every CTA (M values)
-  float kap[M];
-  {
-    float lg[M], mx = -INFINITY;
+  // ---- all global loads first (up to 4 * (2 + M) float4 in flight per thread)
+  const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
+  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(a.noise + (size_t)sc.draw_index * a.noise_step_stride + (size_t)b * a.D) : nullptr;
+  float4 xv[kSegVecPerThread], ev[M][kSegVecPerThread], zv[kSegVecPerThread];
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      lg[m] = a.temperature * a.logq[b * M + m] + (a.bias ? a.bias[m] : 0.0f);
-      mx = fmaxf(mx, lg[m]);
-    }
-    float den = 0.0f;
+  for (int i = 0; i < kSegVecPerThread; ++i) {
+    const int q = seg * kSegVec + i * kUpdThreads + tid;
+    const bool ok = q < nq;
+    xv[i] = ok ? __ldcs(x4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int m = 0; m < M; ++m) { kap[m] = expf(lg[m] - mx); den += kap[m]; }
-#pragma unroll
-    for (int m = 0; m < M; ++m) kap[m] = kap[m] / den;
+    for (int m = 0; m < M; ++m)
+      ev[m][i] = ok ? __ldcs(reinterpret_cast<const float4*>(a.eps + ((size_t)m * a.B + b) * a.D) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    zv[i] = (ok && noise_tensor) ? __ldcs(n4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  float kap[M];
+  softmax_kappa<M>(a, b, kap);
   const float c1 = 1.0f / sqrtf(sc.alpha);
   const float c2 = (1.0f - sc.alpha) / sqrtf(1.0f - sc.alpha_bar);
   const float c3 = sqrtf(sc.beta);
-
-  const int nq = a.D >> 2;  // float4 per sample
-  const int q_per_blk = (nq + a.nblk - 1) / a.nblk;
-  const int q0 = blk * q_per_blk;
-  const int q1 = min(nq, q0 + q_per_blk);
-
-  const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
   float4* xo4 = reinterpret_cast<float4*>(a.x_out + (size_t)b * a.D);
-  const float4* e4[M];
-#pragma unroll
-  for (int m = 0; m < M; ++m) e4[m] = reinterpret_cast<const float4*>(a.eps + ((size_t)m * a.B + b) * a.D);
-  const float4* n4 = nullptr;
-  const bool have_noise = sc.draw_index >= 0;
-  if (a.noise && have_noise)
-    n4 = reinterpret_cast<const float4*>(a.noise + (size_t)sc.draw_index * a.noise_step_stride + (size_t)b * a.D);
   const uint32_t gsample = (uint32_t)(a.sample_offset + b);
 
   float accA[M], accB[M], accC[M], sx = 0.0f, sxx = 0.0f;
 #pragma unroll
   for (int m = 0; m < M; ++m) accA[m] = accB[m] = accC[m] = 0.0f;
-
-  for (int q = q0 + tid; q < q1; q += kUpdThreads) {
-    const float4 xv = __ldcs(x4 + q);
-    float4 ev[M];
 #pragma unroll
-    for (int m = 0; m < M; ++m) ev[m] = __ldcs(e4[m] + q);
-    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (have_noise) zv = n4 ? __ldcs(n4 + q) : philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
-
-    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
-    const float zs[4] = {zv.x, zv.y, zv.z, zv.w};
+  for (int i = 0; i < kSegVecPerThread; ++i) {
+    const int q = seg * kSegVec + i * kUpdThreads + tid;
+    if (q >= nq) continue;
+    float4 z = zv[i];
+    if (have_noise && !noise_tensor) z = philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
+    const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+    const float zs[4] = {z.x, z.y, z.z, z.w};
     float xn[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float es[M];
 #pragma unroll
-      for (int m = 0; m < M; ++m) es[m] = (j == 0 ? ev[m].x : j == 1 ? ev[m].y : j == 2 ? ev[m].z : ev[m].w);
+      for (int m = 0; m < M; ++m)
+        es[m] = (j == 0 ? ev[m][i].x : j == 1 ? ev[m][i].y : j == 2 ? ev[m][i].z : ev[m][i].w);
       float eb = __fmul_rn(kap[0], es[0]);
 #pragma unroll
       for (int m = 1; m < M; ++m) eb = __fadd_rn(eb, __fmul_rn(kap[m], es[m]));
@@ -160,12 +169,11 @@ __global__ void __launch_bounds__(kUpdThreads) superpose_update_kernel(const Upd
       sx += xn[j];
       sxx = fmaf(xn[j], xn[j], sxx);
     }
-    xo4[q] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    __stcs(xo4 + q, make_float4(xn[0], xn[1], xn[2], xn[3]));
   }
 
-  // block reduce: shuffle within warps, fixed-order sum across the 8 warps
+  // segment reduce: shuffle within warps, fixed-order sum across the 8 warps
   __shared__ float red[kUpdThreads / 32][3 * M + 2];
-  const int warp = tid >> 5, lane = tid & 31;
 #pragma unroll
   for (int m = 0; m < M; ++m) {
     accA[m] = warp_sum(accA[m]); accB[m] = warp_sum(accB[m]); accC[m] = warp_sum(accC[m]);
@@ -177,71 +185,77 @@ __global__ void __launch_bounds__(kUpdThreads) superpose_update_kernel(const Upd
     red[warp][3 * M] = sx; red[warp][3 * M + 1] = sxx;
   }
   __syncthreads();
-  __shared__ int s_last;
-  float* part = a.partials + ((size_t)b * a.nblk + blk) * kPartialsPerBlock;
   if (tid < 3 * M + 2) {
     float v = 0.0f;
 #pragma unroll
     for (int w = 0; w < kUpdThreads / 32; ++w) v += red[w][tid];
-    __stcg(part + tid, v);
+    a.partials[((size_t)b * a.nblk + seg) * kPartialsPerBlock + tid] = v;
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    int prev = atomicAdd(&a.counters[b], 1);
-    s_last = (prev == a.nblk - 1);
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
+}
 
-  // last CTA of sample b: fixed-order reduce over blocks, then the Ito increment (in double)
+// One CTA (256 threads) per sample: fixed-order reduce of the segment partials (16 strided lanes per value, then the
+// 16 lanes in order), Ito log-density increment in double, kappa, GroupNorm(1,1) statistics of x'.
+template <int M>
+__global__ void __launch_bounds__(256) superpose_finalize_kernel(const UpdateArgs a) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int step = a.step_ptr ? *a.step_ptr : 0;
+  const StepScalars sc = a.table ? a.table[step] : a.sc;
+  __shared__ float fin[16][16];
   __shared__ double tot[3 * M + 2];
+  {
+    const int j = tid & 15, g = tid >> 4;
+    float v = 0.0f;
+    if (j < 3 * M + 2) {
+      const float* src = a.partials + (size_t)b * a.nblk * kPartialsPerBlock + j;
+      for (int p = g; p < a.nblk; p += 16) v += src[(size_t)p * kPartialsPerBlock];
+    }
+    fin[g][j] = v;
+  }
+  __syncthreads();
   if (tid < 3 * M + 2) {
     double v = 0.0;
-    const float* src = a.partials + (size_t)b * a.nblk * kPartialsPerBlock + tid;
-    for (int p = 0; p < a.nblk; ++p) v += (double)__ldcg(src + (size_t)p * kPartialsPerBlock);
+#pragma unroll
+    for (int g = 0; g < 16; ++g) v += (double)fin[g][tid];
     tot[tid] = v;
   }
   __syncthreads();
   if (tid < M) {
+    float kap[M];
+    softmax_kappa<M>(a, b, kap);
     const double beta = (double)sc.beta;
     const double inv_sig = 1.0 / sqrt(1.0 - (double)sc.alpha_bar);
     const double A = tot[3 * tid], Bx = tot[3 * tid + 1], C = tot[3 * tid + 2];
     // s = -eps * inv_sig:  <s,dx> - beta D/2 - beta/2 <x,s> - beta/2 |s|^2
     const double inc = -inv_sig * A - 0.5 * beta * (double)a.D + 0.5 * beta * inv_sig * Bx - 0.5 * beta * inv_sig * inv_sig * C;
     const float lq_new = (float)((double)a.logq[b * M + tid] + inc);
+    float kv = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) if (m == tid) kv = kap[m];
+    __syncwarp((1u << M) - 1u);  // every lane has read logq[b,:] (for kappa) before any lane overwrites it in place
     a.logq_out[b * M + tid] = lq_new;
-    if (a.kappa_out) a.kappa_out[b * M + tid] = kap[tid];
-    if (a.kappa_traj) a.kappa_traj[((size_t)step * a.B + b) * M + tid] = kap[tid];
+    if (a.kappa_out) a.kappa_out[b * M + tid] = kv;
+    if (a.kappa_traj) a.kappa_traj[((size_t)step * a.B + b) * M + tid] = kv;
     if (a.logq_traj) a.logq_traj[((size_t)(step + 1) * a.B + b) * M + tid] = lq_new;
   }
-  if (tid == 0) {
-    if (a.xstats_out) {
-      const double mean = tot[3 * M] / (double)a.D;
-      double var = tot[3 * M + 1] / (double)a.D - mean * mean;
-      if (var < 0.0) var = 0.0;
-      a.xstats_out[b * 2 + 0] = (float)mean;
-      a.xstats_out[b * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
-    }
-    a.counters[b] = 0;
+  if (tid == 32 && a.xstats_out) {
+    const double mean = tot[3 * M] / (double)a.D;
+    double var = tot[3 * M + 1] / (double)a.D - mean * mean;
+    if (var < 0.0) var = 0.0;
+    a.xstats_out[b * 2 + 0] = (float)mean;
+    a.xstats_out[b * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
   }
 }
 
-// Blocks per sample depend on D only, so the reduction tree (hence every bit of logq / x stats)
-// is identical however the batch is sharded across GPUs.
+// Segments per sample depend on D only (2048 elements each).
 inline int update_blocks_per_sample(int D) {
   int nq = D / 4;
-  int nb = (nq + kUpdThreads * 4 - 1) / (kUpdThreads * 4);
-  if (nb < 1) nb = 1;
-  if (nb > kUpdMaxBlocksPerSample) nb = kUpdMaxBlocksPerSample;
-  return nb;
+  int nb = (nq + kSegVec - 1) / kSegVec;
+  return nb < 1 ? 1 : nb;
 }
 
 inline size_t update_workspace_bytes(int B, int D, int /*M*/) {
   size_t part = (size_t)B * update_blocks_per_sample(D) * kPartialsPerBlock * sizeof(float);
-  part = (part + 255) & ~(size_t)255;
-  return part + (((size_t)B * sizeof(int) + 255) & ~(size_t)255);
+  return (part + 255) & ~(size_t)255;
 }
 
 int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream);
