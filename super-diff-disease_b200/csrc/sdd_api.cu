@@ -410,11 +410,16 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
         cur ^= 1; ++gi;
       }
     }
-    // ups.1: GN(4,64)+SiLU apply, 64->1 conv, then GN(1,1)+SiLU fused into the 1->1 conv (+ time bias)
+    // ups.1: GroupNorm(4,64)+SiLU fused into the 64->1 conv (mma.sync), then GN(1,1)+SiLU fused into the 1->1 conv
     const BlockParams& u1 = u->blk[4];
-    SDD_TRY(launch_apply(ws.act[cur], mr(gi), u1.gn1_w, u1.gn1_b, nb, H, W, 64, st));
-    conv_out1_kernel<<<eg, 256, 0, st>>>(ws.act[cur], u1.conv1_w, u1.conv1_b, ws.e1, ws.partials, ws.counters,
-                                         mr(gi + 1), H, W);
+    if (use_v1) {
+      SDD_TRY(launch_apply(ws.act[cur], mr(gi), u1.gn1_w, u1.gn1_b, nb, H, W, 64, st));
+      conv_out1_kernel<<<eg, 256, 0, st>>>(ws.act[cur], u1.conv1_w, u1.conv1_b, ws.e1, ws.partials, ws.counters,
+                                           mr(gi + 1), H, W);
+    } else {
+      conv_out1_mma_kernel<<<eg, 256, 0, st>>>(ws.act[cur], mr(gi), u1.gn1_w, u1.gn1_b, u1.conv1_w, u1.conv1_b, ws.e1,
+                                               ws.partials, ws.counters, mr(gi + 1), H, W);
+    }
     SDD_LAUNCH_CHECK();
     conv_out2_kernel<<<eg, 256, 0, st>>>(ws.e1, mr(gi + 1), u1.gn2_w, u1.gn2_b, u1.conv2_w, bias_time(4),
                                          eps_out + (size_t)b0 * HW, H, W);

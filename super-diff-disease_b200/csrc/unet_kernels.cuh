@@ -270,6 +270,132 @@ __global__ void __launch_bounds__(256) conv_out1_kernel(const __nv_bfloat16* __r
   }
 }
 
+// ------------------------------------------------------------------ GN(4,64)+SiLU + conv 64 -> 1, tensor cores
+// raw bf16 NHWC [B,H,W,64] --GroupNorm(4,64)+SiLU in registers--> 3x3 conv to ONE channel -> raw fp32 [B,H,W] + bias,
+// + GN(1,1) statistics.  Written as out[p] = sum_tap T[p + off_tap][tap] with T[q][tap] = <act'[q,:], w[tap,:]>:
+// T is a [halo pixels x 64] x [64 x 16] GEMM (9 taps padded to 16) done with mma.sync m16n8k16 (bf16, fp32 accumulate;
+// a 576-MAC/pixel layer is far too small to justify a tcgen05 pipeline), then a 9-tap gather from shared memory.
+// The K order is permuted so that each lane's 16 channels are 32 contiguous bytes of the pixel row (coalesced 16-byte
+// loads, no shuffles): lane t = lane%4 owns channels [16t, 16t+16), register ks*2+h holds channels 16t + 4ks + 2h + {0,1}.
+constexpr int kO1TH = 8, kO1TW = 32;
+constexpr int kO1HW = kO1TW + 2, kO1HH = kO1TH + 2;        // 34 x 10 halo
+constexpr int kO1Pix = kO1HW * kO1HH;                      // 340
+constexpr int kO1MT = (kO1Pix + 15) / 16;                  // 22 m-tiles
+constexpr int kO1Taps = 9;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) conv_out1_mma_kernel(const __nv_bfloat16* __restrict__ raw,
+                                                            const float* __restrict__ in_meanrstd,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ w /*[1][64][3][3]*/,
+                                                            const float* __restrict__ bias, float* __restrict__ out,
+                                                            float* partials, int* counters, float* meanrstd, int H, int W) {
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.y * kO1TH, w0 = blockIdx.x * kO1TW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = lane & 3, j = lane >> 2;
+  __shared__ float tb[kO1MT * 16][kO1Taps + 1];  // T[halo pixel][tap], padded against bank conflicts
+
+  // per-lane GroupNorm scale/shift of its 16 channels, and the weight fragments in the permuted K order
+  float ga[16], gb[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = t * 16 + i, g = c >> 4;
+    const float mean = in_meanrstd[(b * 4 + g) * 2], rstd = in_meanrstd[(b * 4 + g) * 2 + 1];
+    ga[i] = rstd * gamma[c];
+    gb[i] = beta[c] - mean * ga[i];
+  }
+  uint32_t bw[2][4][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int tap = nt * 8 + j, c = t * 16 + ks * 4 + h * 2;
+        const float w0v = tap < kO1Taps ? w[c * 9 + tap] : 0.f, w1v = tap < kO1Taps ? w[(c + 1) * 9 + tap] : 0.f;
+        bw[nt][ks][h] = pack_bf16x2(w0v, w1v);
+      }
+
+  const __nv_bfloat16* img = raw + (size_t)b * H * W * 64 + t * 16;
+  for (int mt = warp; mt < kO1MT; mt += 8) {
+    uint32_t a[2][8];  // [row half][ks*2+h]
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int p = mt * 16 + j + 8 * rh;
+      const int hr = p / kO1HW, wr = p - hr * kO1HW;
+      const int hh = h0 - 1 + hr, ww = w0 - 1 + wr;
+      const bool ok = p < kO1Pix && hh >= 0 && hh < H && ww >= 0 && ww < W;
+      uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
+      if (ok) {
+        const uint4* src = reinterpret_cast<const uint4*>(img + ((size_t)hh * W + ww) * 64);
+        v0 = __ldg(src);
+        v1 = __ldg(src + 1);
+      }
+      uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (ok) {
+          __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[i]);
+          const float lo = silu_f(fmaf(__low2float(hv), ga[2 * i], gb[2 * i]));
+          const float hi = silu_f(fmaf(__high2float(hv), ga[2 * i + 1], gb[2 * i + 1]));
+          u[i] = pack_bf16x2(lo, hi);
+        }
+        a[rh][i] = u[i];
+      }
+    }
+    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t af[4] = {a[0][ks * 2], a[1][ks * 2], a[0][ks * 2 + 1], a[1][ks * 2 + 1]};
+      mma_bf16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
+      mma_bf16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
+    }
+    // d0: taps 2t, 2t+1 of rows j and j+8; d1: taps 8+2t, 9+2t (only tap 8 exists)
+    const int r0 = mt * 16 + j;
+    tb[r0][2 * t] = d0[0]; tb[r0][2 * t + 1] = d0[1];
+    tb[r0 + 8][2 * t] = d0[2]; tb[r0 + 8][2 * t + 1] = d0[3];
+    if (t == 0) { tb[r0][8] = d1[0]; tb[r0 + 8][8] = d1[2]; }
+  }
+  __syncthreads();
+
+  const int r = tid / kO1TW, c = tid % kO1TW;
+  const int h = h0 + r, ww = w0 + c;
+  float s = 0.f, ss = 0.f;
+  if (h < H && ww < W) {
+    float acc = bias[0];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) acc += tb[(r + ky) * kO1HW + (c + kx)][ky * 3 + kx];
+    out[((size_t)b * H + h) * W + ww] = acc;
+    s = acc; ss = acc * acc;
+  }
+  __shared__ float red[8][2];
+  __shared__ float sums[2];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+  if (lane == 0) { red[warp][0] = s; red[warp][1] = ss; }
+  __syncthreads();
+  if (tid < 32) {
+    if (tid == 0) {
+      float x0 = 0.f, x1 = 0.f;
+      for (int wq = 0; wq < 8; ++wq) { x0 += red[wq][0]; x1 += red[wq][1]; }
+      sums[0] = x0; sums[1] = x1;
+    }
+    __syncwarp();
+    const int part = blockIdx.y * gridDim.x + blockIdx.x;
+    gn_publish_and_finalize_warp(sums, partials, counters, meanrstd, b, part, gridDim.x * gridDim.y, 1,
+                                 (float)H * (float)W, kGnEps);
+  }
+}
+
 // ------------------------------------------------------------------ conv 1 -> 1 (last conv) + time bias
 // e fp32 [B,H,W] raw --GN(1,1)+SiLU on load--> 3x3 conv + (conv bias + time_emb)[b] -> eps fp32 [B,H,W].
 __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict__ e, const float* __restrict__ stats,
