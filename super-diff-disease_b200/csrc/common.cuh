@@ -135,7 +135,37 @@ __device__ __forceinline__ void gn_publish_and_finalize_warp(
   if (lane == 0) counters[b] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Order-independent GroupNorm statistics: producers add their fp32 partial (sum, sum of squares) as 64-bit
+// fixed-point integers in units of 2^-20 with fire-and-forget RED.ADDs.  Integer addition is associative, so the
+// totals are bit-reproducible whatever the arrival order or batch sharding, and no fence / counter / last-CTA
+// protocol is needed; consumers (the next kernel) derive (mean, rstd) themselves.  Range: |sum| < 8.8e12.
+constexpr float kGnFixScale = 1048576.0f;
+constexpr double kGnFixInv = 1.0 / 1048576.0;
+__device__ __forceinline__ void gn_red_add(long long* dst, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)__float2ll_rn(v * kGnFixScale));
+}
+__device__ __forceinline__ void gn_mean_rstd_from_sums(const long long* sums2, double count, float eps, float& mean,
+                                                       float& rstd) {
+  const double m = (double)sums2[0] * kGnFixInv / count;
+  double var = (double)sums2[1] * kGnFixInv / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)eps));
+}
+
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// silu(v) = v * sigmoid(v) = 0.5 v (1 + tanh(v/2)): ONE MUFU op per element (8 cycles per warp instruction on B200,
+// measured by tools/micro/mufu.cu) instead of ex2 + rcp; absolute error ~5e-4 * |v|, below bf16 output rounding
+__device__ __forceinline__ float silu_tanh(float v) {
+  const float h = 0.5f * v;
+  return fmaf(h, tanh_approx(h), h);
+}
 
 // ----------------------------------------------------------------------------------------- PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -167,7 +197,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (error returned to the host) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 24); ++i) {
+  for (uint32_t i = 0; i < (1u << 22); ++i) {
     if (mbar_try_wait(bar, parity)) return;
   }
   printf("sdd: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
@@ -184,6 +214,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// bring a box into L2 only (no shared memory, no barrier): hides DRAM latency for tiles a few iterations ahead
+__device__ __forceinline__ void tma_prefetch_l2_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1,
                                             int c2) {

@@ -51,7 +51,8 @@ struct ConvTc2Args {
   int tiles_w, tiles_per_sample, num_tiles, num_pairs;
   int stages;
   long long* trace;  // optional [2 ctas][6 roles][64 iters][4 events] stamps of CTA pair 0 (debug)
-  int dbg;           // timing experiments only (results invalid): 2 = no stores/stats, 4 = no MMA
+  int dbg;           // timing experiments only (results invalid): 2 = no stores/stats, 4 = no MMA, 8 = no stats publish
+  int prefetch;      // halo boxes pulled into L2 this many pipeline items ahead of their shared-memory load (0 = off)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -94,7 +95,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  for (uint32_t i = 0; i < (1u << 24); ++i)
+  for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait_cluster(bar, parity)) return;
   printf("sdd: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,
          (int)threadIdx.x, bar, parity);
@@ -119,17 +120,6 @@ __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ float tanh_approx(float x) {
-  float y;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-// silu(v) = v * sigmoid(v) = 0.5 v (1 + tanh(v/2)): one MUFU op per element
-__device__ __forceinline__ float silu_tanh(float v) {
-  const float h = 0.5f * v;
-  return fmaf(h, tanh_approx(h), h);
-}
-
 // debug stamps go to shared memory (a global store would be dragged into the release of the next mbarrier
 // arrive and perturb exactly what is being measured) and are dumped once at kernel exit
 constexpr int kTraceIters = 12;
@@ -211,19 +201,35 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int kc = 0; kc < kchunks; ++kc)
           tma_load_3d(smem_base + (uint32_t)(tap * kchunks + kc) * kWSlot, &tmB, w_bar, kc * 64,
                       (int)rank * (COUT / 2), tap);
-      // then one (64 ci x 10 w x 18 h) halo box per (tile, chunk); out-of-image pixels are zero-filled by TMA
-      int stage = 0; uint32_t phase = 0;
-      for (int pair = pair0; pair < a.num_pairs; pair += pair_stride) {
+      // then one (64 ci x 10 w x 18 h) halo box per (tile, chunk); out-of-image pixels are zero-filled by TMA.
+      // Shared memory only holds a few stages (3 for 128->128), too few to cover DRAM latency, so the boxes of the
+      // items kPrefetch ahead are pulled into L2 first (cp.async.bulk.prefetch.tensor): the real load then hits L2.
+      const int kPrefetch = a.prefetch;
+      const int total_items = ((a.num_pairs - pair0 + pair_stride - 1) / pair_stride) * kchunks;
+      auto coords = [&](int j, int& n, int& h0, int& w0, int& kc) {
         bool valid;
-        const int tile = tile_of(pair, valid);
-        const int n = tile / a.tiles_per_sample, tr = tile % a.tiles_per_sample;
-        const int h0 = (tr / a.tiles_w) * kTileH, w0 = (tr % a.tiles_w) * kTileW;
-        for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), kHaloVecs * 16);
-          tma_load_4d(a_base + stage * kHaloBytes, &tmA, full_bar(stage), kc * 64, w0 - 1, h0 - 1, n);
-          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        const int tile = tile_of(pair0 + (j / kchunks) * pair_stride, valid);
+        n = tile / a.tiles_per_sample;
+        const int tr = tile % a.tiles_per_sample;
+        h0 = (tr / a.tiles_w) * kTileH; w0 = (tr % a.tiles_w) * kTileW; kc = j % kchunks;
+      };
+      for (int j = 0; j < kPrefetch && j < total_items; ++j) {
+        int n, h0, w0, kc;
+        coords(j, n, h0, w0, kc);
+        tma_prefetch_l2_4d(&tmA, kc * 64, w0 - 1, h0 - 1, n);
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int j = 0; j < total_items; ++j) {
+        int n, h0, w0, kc;
+        if (j + kPrefetch < total_items) {
+          coords(j + kPrefetch, n, h0, w0, kc);
+          tma_prefetch_l2_4d(&tmA, kc * 64, w0 - 1, h0 - 1, n);
         }
+        coords(j, n, h0, w0, kc);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), kHaloVecs * 16);
+        tma_load_4d(a_base + stage * kHaloBytes, &tmA, full_bar(stage), kc * 64, w0 - 1, h0 - 1, n);
+        if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -277,7 +283,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const int slot = it & 1;
       mbar_wait(sfull_bar(slot), (uint32_t)((it >> 1) & 1));
       if (lane == 0) SDD_TRACE(4, it, 0);
-      if (valid && !(a.dbg & 2)) {
+      if (valid && !(a.dbg & (2 | 8))) {
         if (lane < 8) {  // lane = group*2 + {sum, sumsq}; fixed order over the four lane quadrants
           const int g = lane >> 1, hc = g >> 1, k = (g & 1) * 2 + (lane & 1);
           s_sums[lane] = (s_red[slot][hc * 4 + 0][k] + s_red[slot][hc * 4 + 1][k]) +

@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
+#include "conv_tc3.cuh"
 #include "unet_kernels.cuh"
 #include "update.cuh"
 
@@ -205,12 +206,59 @@ static int launch_conv_tc2(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   a.stages = conv_tc2_stages(Cout, Cin);
   a.dbg = dbg;
   a.trace = trace;
+  static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 8;
+  a.prefetch = prefetch;
   const int smem = conv_tc2_smem_bytes(Cout, Cin, a.stages);
   const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
   if (Cout == 64)
     conv3x3_tc2_kernel<64><<<grid, kC2Threads, smem, st>>>(tmA_halo, tmB2, a);
   else
     conv3x3_tc2_kernel<128><<<grid, kC2Threads, smem, st>>>(tmA_halo, tmB2, a);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+struct GnInput3 {  // GroupNorm(4, Cin) + SiLU of the conv's input: fixed-point sums (product path) or mean/rstd floats
+  const long long* sums;
+  const float* meanrstd;
+  const float* gamma;
+  const float* beta;
+};
+
+static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2, const __nv_bfloat16* in,
+                           __nv_bfloat16* out, BiasRef bias, GnInput3 gi, long long* out_sums, int B, int H, int W,
+                           int Cin, int Cout, cudaStream_t st, int dbg = 0, long long* trace = nullptr) {
+  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
+  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
+  SDD_CHECK((size_t)B * H * W * Cin * 2 < ((size_t)1 << 40), "tensor too large");
+  static bool attr = false;
+  if (!attr) {
+    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
+    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
+    attr = true;
+  }
+  ConvTc3Args a;
+  a.in = in; a.out = out; a.bias = bias;
+  a.in_sums = gi.sums; a.in_meanrstd = gi.meanrstd; a.in_gamma = gi.gamma; a.in_beta = gi.beta;
+  a.out_sums = out_sums;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+  a.tiles_w = W / kTileW;
+  a.tiles_per_sample = (H / kTileH) * a.tiles_w;
+  a.num_tiles = B * a.tiles_per_sample;
+  a.num_pairs = (a.num_tiles + 1) / 2;
+  a.stages = conv_tc3_stages(Cout, Cin);
+  static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 6;
+  a.prefetch = prefetch;
+  a.dbg = dbg;
+  a.trace = trace;
+  const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages);
+  const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
+  if (Cout == 64)
+    conv3x3_tc3_kernel<64><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+  else
+    conv3x3_tc3_kernel<128><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
   SDD_LAUNCH_CHECK();
   return SDD_OK;
 }
@@ -245,6 +293,7 @@ constexpr int kBiasOff[5] = {0, 64, 192, 320, 384};
 constexpr int kBlkCin[5] = {1, 64, 128, 128, 64};
 constexpr int kBlkCout[5] = {64, 128, 128, 64, 1};
 constexpr int kTimeDim = 256;
+constexpr int kGnLayers = 9;  // GroupNorms fed by a conv output: downs.0 gn2 ... ups.1 gn2 (the first one reads x)
 
 struct Workspace {
   int cap_b = 0, H = 0, W = 0;  // chunk capacity and image size the buffers were built for
@@ -253,13 +302,13 @@ struct Workspace {
   float* e1 = nullptr;
   float* partials = nullptr;
   int* counters = nullptr;
-  float* meanrstd = nullptr;  // 10 x [cap_b][4][2]
+  long long* gnsums = nullptr;  // 9 x [cap_b][4][2] fixed-point GroupNorm sums, one slab per GroupNorm layer (common.cuh)
   float* xstats = nullptr;    // [cap_b][2] (used when the caller has no stats of x)
   CUtensorMap tm_act[2][2];   // [buffer][Cin == 128], v1 box (64, 8, 18)
   CUtensorMap tm_halo[2][2];  // v2 halo box (64, 10, 18)
   void release() {
     cudaFree(act[0]); cudaFree(act[1]); cudaFree(e1); cudaFree(partials); cudaFree(counters);
-    cudaFree(meanrstd); cudaFree(xstats);
+    cudaFree(gnsums); cudaFree(xstats);
     int64_t g = generation;
     *this = Workspace();
     generation = g;
@@ -304,12 +353,10 @@ int ensure_workspace(sdd_unet* u, int B, int H, int W) {
   SDD_CUDA(cudaMalloc(&ws.act[0], act_bytes));
   SDD_CUDA(cudaMalloc(&ws.act[1], act_bytes));
   SDD_CUDA(cudaMalloc(&ws.e1, (size_t)need * H * W * sizeof(float)));
-  int parts = std::max({(H / kTileH) * (W / kTileW), ((H + kCinTH - 1) / kCinTH) * ((W + kCinTW - 1) / kCinTW),
-                        kStatsBlocks});
-  SDD_CUDA(cudaMalloc(&ws.partials, (size_t)need * parts * 8 * sizeof(float)));
+  SDD_CUDA(cudaMalloc(&ws.partials, (size_t)need * kStatsBlocks * 2 * sizeof(float)));  // stats_x_kernel only
   SDD_CUDA(cudaMalloc(&ws.counters, (size_t)need * sizeof(int)));
   SDD_CUDA(cudaMemset(ws.counters, 0, (size_t)need * sizeof(int)));
-  SDD_CUDA(cudaMalloc(&ws.meanrstd, (size_t)10 * need * 8 * sizeof(float)));
+  SDD_CUDA(cudaMalloc(&ws.gnsums, (size_t)kGnLayers * need * 8 * sizeof(long long)));
   SDD_CUDA(cudaMalloc(&ws.xstats, (size_t)need * 2 * sizeof(float)));
   for (int bi = 0; bi < 2; ++bi) {
     SDD_TRY(make_act_map(&ws.tm_act[bi][0], ws.act[bi], need, H, W, 64));
@@ -356,17 +403,17 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
   const int HW = H * W;
   const int chunk = ws.cap_b;
   const dim3 egrid((W + kCinTW - 1) / kCinTW, (H + kCinTH - 1) / kCinTH, 1);
-  static const bool use_v1 = getenv("SDD_CONV_V1") != nullptr;  // A/B switch: v1 = streamed weights + apply passes
   for (int b0 = 0; b0 < B; b0 += chunk) {
     const int nb = std::min(chunk, B - b0);
     const float* xc = x + (size_t)b0 * HW;
-    auto mr = [&](int i) { return ws.meanrstd + (size_t)i * ws.cap_b * 8; };
-    auto gn = [&](int i) { return GnScratch{ws.partials, ws.counters, mr(i)}; };
+    auto sums = [&](int i) { return ws.gnsums + (size_t)i * ws.cap_b * 8; };
     auto bias_const = [&](const float* p) { return BiasRef{p, nullptr, 0, 0}; };
     auto bias_time = [&](int blk) {
       return BiasRef{tb.base + kBiasOff[blk] + (int64_t)b0 * tb.batch_stride, tb.row_ptr, tb.row_stride,
                      tb.batch_stride};
     };
+    // every GroupNorm accumulator of this forward starts at zero (producers only ever RED.ADD into them)
+    SDD_CUDA(cudaMemsetAsync(ws.gnsums, 0, (size_t)kGnLayers * ws.cap_b * 8 * sizeof(long long), st));
     const float* xs = xstats ? xstats + (size_t)b0 * 2 : nullptr;
     if (!xs) {
       stats_x_kernel<<<dim3(kStatsBlocks, nb), 256, 0, st>>>(xc, HW, ws.partials, ws.counters, ws.xstats);
@@ -374,54 +421,30 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
       xs = ws.xstats;
     }
     dim3 eg = egrid; eg.z = nb;
-    // downs.0: GN(1,1)+SiLU fused into the 1->64 conv; result raw in act[0], stats -> mr(0)
+    // downs.0: GN(1,1)+SiLU fused into the 1->64 conv; raw result in act[0], its GroupNorm(4,64) sums -> sums(0)
     const BlockParams& d0 = u->blk[0];
     conv_in_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
-                                       ws.partials, ws.counters, mr(0), H, W);
+                                       sums(0), H, W);
     SDD_LAUNCH_CHECK();
-    int cur, gi;
-    if (use_v1) {
-      SDD_TRY(launch_apply(ws.act[0], mr(0), d0.gn2_w, d0.gn2_b, nb, H, W, 64, st));
-      SDD_TRY(launch_conv_tc(ws.tm_act[0][0], d0.tm_w2, ws.act[1], bias_time(0), gn(1), nb, H, W, 64, 64, st));
-      cur = 1; gi = 1;
-      for (int bi = 1; bi <= 3; ++bi) {
-        const BlockParams& p = u->blk[bi];
-        SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn1_w, p.gn1_b, nb, H, W, p.cin, st));
-        SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cin == 128], p.tm_w1, ws.act[cur ^ 1], bias_const(p.conv1_b),
-                               gn(gi + 1), nb, H, W, p.cin, p.cout, st));
-        cur ^= 1; ++gi;
-        SDD_TRY(launch_apply(ws.act[cur], mr(gi), p.gn2_w, p.gn2_b, nb, H, W, p.cout, st));
-        SDD_TRY(launch_conv_tc(ws.tm_act[cur][p.cout == 128], p.tm_w2, ws.act[cur ^ 1], bias_time(bi), gn(gi + 1),
-                               nb, H, W, p.cout, p.cout, st));
-        cur ^= 1; ++gi;
-      }
-    } else {
-      // v2: every tensor-core conv normalises + activates its own input (GroupNorm+SiLU fused on the operand path)
-      SDD_TRY(launch_conv_tc2(ws.tm_halo[0][0], d0.tm_w2h, ws.act[1], bias_time(0), GnInput{mr(0), d0.gn2_w, d0.gn2_b},
-                              gn(1), nb, H, W, 64, 64, st));
-      cur = 1; gi = 1;
-      for (int bi = 1; bi <= 3; ++bi) {
-        const BlockParams& p = u->blk[bi];
-        SDD_TRY(launch_conv_tc2(ws.tm_halo[cur][p.cin == 128], p.tm_w1h, ws.act[cur ^ 1], bias_const(p.conv1_b),
-                                GnInput{mr(gi), p.gn1_w, p.gn1_b}, gn(gi + 1), nb, H, W, p.cin, p.cout, st));
-        cur ^= 1; ++gi;
-        SDD_TRY(launch_conv_tc2(ws.tm_halo[cur][p.cout == 128], p.tm_w2h, ws.act[cur ^ 1], bias_time(bi),
-                                GnInput{mr(gi), p.gn2_w, p.gn2_b}, gn(gi + 1), nb, H, W, p.cout, p.cout, st));
-        cur ^= 1; ++gi;
-      }
+    // every tensor-core conv normalises + activates its own input (GroupNorm+SiLU fused on the operand path)
+    SDD_TRY(launch_conv_tc3(ws.tm_halo[0][0], d0.tm_w2h, ws.act[0], ws.act[1], bias_time(0),
+                            GnInput3{sums(0), nullptr, d0.gn2_w, d0.gn2_b}, sums(1), nb, H, W, 64, 64, st));
+    int cur = 1, gi = 1;
+    for (int bi = 1; bi <= 3; ++bi) {
+      const BlockParams& p = u->blk[bi];
+      SDD_TRY(launch_conv_tc3(ws.tm_halo[cur][p.cin == 128], p.tm_w1h, ws.act[cur], ws.act[cur ^ 1], bias_const(p.conv1_b),
+                              GnInput3{sums(gi), nullptr, p.gn1_w, p.gn1_b}, sums(gi + 1), nb, H, W, p.cin, p.cout, st));
+      cur ^= 1; ++gi;
+      SDD_TRY(launch_conv_tc3(ws.tm_halo[cur][p.cout == 128], p.tm_w2h, ws.act[cur], ws.act[cur ^ 1], bias_time(bi),
+                              GnInput3{sums(gi), nullptr, p.gn2_w, p.gn2_b}, sums(gi + 1), nb, H, W, p.cout, p.cout, st));
+      cur ^= 1; ++gi;
     }
     // ups.1: GroupNorm(4,64)+SiLU fused into the 64->1 conv (mma.sync), then GN(1,1)+SiLU fused into the 1->1 conv
     const BlockParams& u1 = u->blk[4];
-    if (use_v1) {
-      SDD_TRY(launch_apply(ws.act[cur], mr(gi), u1.gn1_w, u1.gn1_b, nb, H, W, 64, st));
-      conv_out1_kernel<<<eg, 256, 0, st>>>(ws.act[cur], u1.conv1_w, u1.conv1_b, ws.e1, ws.partials, ws.counters,
-                                           mr(gi + 1), H, W);
-    } else {
-      conv_out1_mma_kernel<<<eg, 256, 0, st>>>(ws.act[cur], mr(gi), u1.gn1_w, u1.gn1_b, u1.conv1_w, u1.conv1_b, ws.e1,
-                                               ws.partials, ws.counters, mr(gi + 1), H, W);
-    }
+    conv_out1_mma_kernel<<<eg, 256, 0, st>>>(ws.act[cur], sums(gi), u1.gn1_w, u1.gn1_b, u1.conv1_w, u1.conv1_b, ws.e1,
+                                             sums(gi + 1), H, W);
     SDD_LAUNCH_CHECK();
-    conv_out2_kernel<<<eg, 256, 0, st>>>(ws.e1, mr(gi + 1), u1.gn2_w, u1.gn2_b, u1.conv2_w, bias_time(4),
+    conv_out2_kernel<<<eg, 256, 0, st>>>(ws.e1, sums(gi + 1), u1.gn2_w, u1.gn2_b, u1.conv2_w, bias_time(4),
                                          eps_out + (size_t)b0 * HW, H, W);
     SDD_LAUNCH_CHECK();
   }
@@ -886,23 +909,27 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
   const int dbg = impl >> 4;
   impl &= 15;
   long long* trace = nullptr;
+  long long* osums = nullptr;
   const char* trace_path = getenv("SDD_CONV_TRACE");
   if (trace_path && impl != 0) { cudaMalloc(&trace, 2 * 6 * 64 * 4 * sizeof(long long)); }
-  if (impl == 2) gi = GnInput{gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128};
+  if (rc == SDD_OK && cudaMalloc(&osums, (size_t)B * 8 * sizeof(long long)) != cudaSuccess) rc = SDD_ENOMEM;
+  if (impl == 2 || impl == 4) gi = GnInput{gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128};
   if (rc == SDD_OK && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) rc = SDD_ECUDA;
   BiasRef br{bias, nullptr, 0, 0};
   double total = 0.0;
   for (int i = 0; rc == SDD_OK && i < iters + 2; ++i) {
     if (flush && flush_bytes) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
+    if (trace) cudaMemsetAsync(trace, 0, 2 * 6 * 64 * 4 * sizeof(long long), st);
+    cudaMemsetAsync(osums, 0, (size_t)B * 8 * sizeof(long long), st);
     cudaEventRecord(e0, st);
     if (impl == 0)
       rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
+    else if (impl <= 2)
+      rc = launch_conv_tc3(tmA, tmB, (const __nv_bfloat16*)act, (__nv_bfloat16*)out, br,
+                           GnInput3{nullptr, gi.meanrstd, gi.gamma, gi.beta}, osums, B, H, W, Cin, Cout, st, dbg, trace);
     else
-    {
-      if (trace) cudaMemsetAsync(trace, 0, 2 * 6 * 64 * 4 * sizeof(long long), st);
       rc = launch_conv_tc2(tmA, tmB, (__nv_bfloat16*)out, br, gi, GnScratch{partials, counters, mr}, B,
                            H, W, Cin, Cout, st, dbg, trace);
-    }
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("conv profile: kernel failed"); rc = SDD_ECUDA; break; }
     float ms = 0.f;
@@ -926,6 +953,7 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
     }
     cudaFree(trace);
   }
+  cudaFree(osums);
   cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr); cudaFree(gin);
   if (rc == SDD_OK) *ms_host = (float)(total / iters);
   return rc;
@@ -976,28 +1004,31 @@ int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const 
   SDD_CHECK(!in_meanrstd || (in_gamma && in_beta), "in_gamma / in_beta required with in_meanrstd");
   SDD_TRY(device_check());
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* wt = nullptr; float* partials = nullptr; int* counters = nullptr; float* mr = nullptr;
-  const int total_w = 9 * Cout * Cin, tiles_ps = (H / kTileH) * (W / kTileW);
+  __nv_bfloat16* wt = nullptr; long long* osums = nullptr;
+  const int total_w = 9 * Cout * Cin;
   int rc = SDD_OK;
   CUtensorMap tmA, tmB;
-  if (cudaMalloc(&wt, (size_t)total_w * 2) != cudaSuccess || cudaMalloc(&partials, (size_t)B * tiles_ps * 32) != cudaSuccess ||
-      cudaMalloc(&counters, (size_t)B * 4) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 32) != cudaSuccess) {
+  if (cudaMalloc(&wt, (size_t)total_w * 2) != cudaSuccess || cudaMalloc(&osums, (size_t)B * 8 * sizeof(long long)) != cudaSuccess) {
     set_error("cudaMalloc failed"); rc = SDD_ENOMEM;
   }
   if (rc == SDD_OK) {
-    cudaMemsetAsync(counters, 0, (size_t)B * 4, st);
+    cudaMemsetAsync(osums, 0, (size_t)B * 8 * sizeof(long long), st);
     conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
     ++g_launches;
     rc = make_act_map(&tmA, act_raw, B, H, W, Cin, true);
   }
   if (rc == SDD_OK) rc = make_wt_map2(&tmB, wt, Cout, Cin);
   if (rc == SDD_OK)
-    rc = launch_conv_tc2(tmA, tmB, (__nv_bfloat16*)out, BiasRef{bias, nullptr, 0, bias_batch_stride},
-                         GnInput{in_meanrstd, in_gamma, in_beta}, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
-  if (rc == SDD_OK && gn_meanrstd)
-    cudaMemcpyAsync(gn_meanrstd, mr, (size_t)B * 32, cudaMemcpyDeviceToDevice, st);
+    rc = launch_conv_tc3(tmA, tmB, (const __nv_bfloat16*)act_raw, (__nv_bfloat16*)out,
+                         BiasRef{bias, nullptr, 0, bias_batch_stride}, GnInput3{nullptr, in_meanrstd, in_gamma, in_beta},
+                         osums, B, H, W, Cin, Cout, st);
+  if (rc == SDD_OK && gn_meanrstd) {
+    gn_sums_to_meanrstd_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(osums, gn_meanrstd, B * 4,
+                                                                   (double)H * (double)W * (double)(Cout / 4), kGnEps);
+    ++g_launches;
+  }
   cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr);
+  cudaFree(wt); cudaFree(osums);
   if (rc != SDD_OK) return rc;
   if (e != cudaSuccess) { set_error(std::string("conv3x3_fused: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
   return SDD_OK;

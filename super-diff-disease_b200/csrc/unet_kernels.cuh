@@ -96,8 +96,8 @@ constexpr int kCinTH = 8, kCinTW = 32;
 __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ xstats,
                                                       const float* __restrict__ gn_w, const float* __restrict__ gn_b,
                                                       const float* __restrict__ w /*[64][9]*/, BiasRef bias,
-                                                      __nv_bfloat16* __restrict__ out, float* partials, int* counters,
-                                                      float* meanrstd, int H, int W) {
+                                                      __nv_bfloat16* __restrict__ out, long long* out_sums /*[B][4][2]*/,
+                                                      int H, int W) {
   const int b = blockIdx.z;
   const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
   const int tid = threadIdx.x;
@@ -152,20 +152,13 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
   s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
   __shared__ float red[8][4][2];
-  __shared__ float sums[8];
   const int lane = tid & 31, warp = tid >> 5;
   if (lane < 8 && (lane & 1) == 0) { red[warp][lane >> 1][0] = s; red[warp][lane >> 1][1] = ss; }
   __syncthreads();
-  if (tid < 32) {
-    if (tid < 8) {
-      float a = 0.f;
-      for (int wq = 0; wq < 8; ++wq) a += red[wq][tid >> 1][tid & 1];
-      sums[tid] = a;
-    }
-    __syncwarp();
-    const int part = blockIdx.y * gridDim.x + blockIdx.x;
-    gn_publish_and_finalize_warp(sums, partials, counters, meanrstd, b, part, gridDim.x * gridDim.y, 4,
-                                 (float)H * (float)W * 16.0f, kGnEps);
+  if (tid < 8) {  // tid = group*2 + {sum, sumsq}: fixed-order sum over the 8 warps, one fixed-point RED per value
+    float a = 0.f;
+    for (int wq = 0; wq < 8; ++wq) a += red[wq][tid >> 1][tid & 1];
+    gn_red_add(out_sums + (size_t)b * 8 + tid, a);
   }
 }
 
@@ -203,73 +196,6 @@ __global__ void __launch_bounds__(256) gn_silu_apply_kernel(__nv_bfloat16* act, 
   }
 }
 
-// ------------------------------------------------------------------ conv 64 -> 1 (first conv of ups.1)
-// act bf16 NHWC [B,H,W,64] (already GN+SiLU'd) -> raw fp32 [B,H,W] + bias, + GN(1,1) stats.
-__global__ void __launch_bounds__(256) conv_out1_kernel(const __nv_bfloat16* __restrict__ act,
-                                                        const float* __restrict__ w /*[1][64][3][3]*/,
-                                                        const float* __restrict__ bias, float* __restrict__ out,
-                                                        float* partials, int* counters, float* meanrstd, int H,
-                                                        int W) {
-  const int b = blockIdx.z;
-  const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
-  const int tid = threadIdx.x, cg = tid & 7;
-  float wr[9][8];
-#pragma unroll
-  for (int t = 0; t < 9; ++t)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wr[t][j] = w[(cg * 8 + j) * 9 + t];
-  const float bv = bias[0];
-  float s = 0.f, ss = 0.f;
-#pragma unroll 1
-  for (int pass = 0; pass < 8; ++pass) {
-    const int p = pass * 32 + (tid >> 3);
-    const int h = h0 + p / kCinTW, ww = w0 + p % kCinTW;
-    float acc = 0.f;
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int hh = h + ky - 1, wx = ww + kx - 1;
-        if (hh >= 0 && hh < H && wx >= 0 && wx < W && h < H && ww < W) {
-          uint4 v = __ldg(reinterpret_cast<const uint4*>(act + (((size_t)b * H + hh) * W + wx) * 64 + cg * 8));
-          uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[j]);
-            acc = fmaf(__low2float(hv), wr[ky * 3 + kx][2 * j], acc);
-            acc = fmaf(__high2float(hv), wr[ky * 3 + kx][2 * j + 1], acc);
-          }
-        }
-      }
-    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-    acc += bv;
-    if (cg == 0 && h < H && ww < W) {
-      out[((size_t)b * H + h) * W + ww] = acc;
-      s += acc;
-      ss = fmaf(acc, acc, ss);
-    }
-  }
-  __shared__ float red[8][2];
-  __shared__ float sums[2];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-  if ((tid & 31) == 0) { red[tid >> 5][0] = s; red[tid >> 5][1] = ss; }
-  __syncthreads();
-  if (tid < 32) {
-    if (tid == 0) {
-      float a = 0.f, c = 0.f;
-      for (int wq = 0; wq < 8; ++wq) { a += red[wq][0]; c += red[wq][1]; }
-      sums[0] = a; sums[1] = c;
-    }
-    __syncwarp();
-    const int part = blockIdx.y * gridDim.x + blockIdx.x;
-    gn_publish_and_finalize_warp(sums, partials, counters, meanrstd, b, part, gridDim.x * gridDim.y, 1,
-                                 (float)H * (float)W, kGnEps);
-  }
-}
-
 // ------------------------------------------------------------------ GN(4,64)+SiLU + conv 64 -> 1, tensor cores
 // raw bf16 NHWC [B,H,W,64] --GroupNorm(4,64)+SiLU in registers--> 3x3 conv to ONE channel -> raw fp32 [B,H,W] + bias,
 // + GN(1,1) statistics.  Written as out[p] = sum_tap T[p + off_tap][tap] with T[q][tap] = <act'[q,:], w[tap,:]>:
@@ -290,12 +216,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256) conv_out1_mma_kernel(const __nv_bfloat16* __restrict__ raw,
-                                                            const float* __restrict__ in_meanrstd,
+__global__ void __launch_bounds__(256, 3) conv_out1_mma_kernel(const __nv_bfloat16* __restrict__ raw,
+                                                            const long long* __restrict__ in_sums /*[B][4][2]*/,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ w /*[1][64][3][3]*/,
                                                             const float* __restrict__ bias, float* __restrict__ out,
-                                                            float* partials, int* counters, float* meanrstd, int H, int W) {
+                                                            long long* out_sums /*[B][8], first two used*/, int H, int W) {
   const int b = blockIdx.z;
   const int h0 = blockIdx.y * kO1TH, w0 = blockIdx.x * kO1TW;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -304,12 +230,15 @@ __global__ void __launch_bounds__(256) conv_out1_mma_kernel(const __nv_bfloat16*
 
   // per-lane GroupNorm scale/shift of its 16 channels, and the weight fragments in the permuted K order
   float ga[16], gb[16];
+  {
+    float mean, rstd;  // lane t owns channels [16t, 16t+16) = exactly GroupNorm group t
+    gn_mean_rstd_from_sums(in_sums + ((size_t)b * 4 + t) * 2, (double)H * (double)W * 16.0, kGnEps, mean, rstd);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = t * 16 + i, g = c >> 4;
-    const float mean = in_meanrstd[(b * 4 + g) * 2], rstd = in_meanrstd[(b * 4 + g) * 2 + 1];
-    ga[i] = rstd * gamma[c];
-    gb[i] = beta[c] - mean * ga[i];
+    for (int i = 0; i < 16; ++i) {
+      const int c = t * 16 + i;
+      ga[i] = rstd * gamma[c];
+      gb[i] = beta[c] - mean * ga[i];
+    }
   }
   uint32_t bw[2][4][2];
 #pragma unroll
@@ -343,8 +272,8 @@ __global__ void __launch_bounds__(256) conv_out1_mma_kernel(const __nv_bfloat16*
       for (int i = 0; i < 8; ++i) {
         if (ok) {
           __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[i]);
-          const float lo = silu_f(fmaf(__low2float(hv), ga[2 * i], gb[2 * i]));
-          const float hi = silu_f(fmaf(__high2float(hv), ga[2 * i + 1], gb[2 * i + 1]));
+          const float lo = silu_tanh(fmaf(__low2float(hv), ga[2 * i], gb[2 * i]));
+          const float hi = silu_tanh(fmaf(__high2float(hv), ga[2 * i + 1], gb[2 * i + 1]));
           u[i] = pack_bf16x2(lo, hi);
         }
         a[rh][i] = u[i];
@@ -378,27 +307,20 @@ __global__ void __launch_bounds__(256) conv_out1_mma_kernel(const __nv_bfloat16*
     s = acc; ss = acc * acc;
   }
   __shared__ float red[8][2];
-  __shared__ float sums[2];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
   if (lane == 0) { red[warp][0] = s; red[warp][1] = ss; }
   __syncthreads();
-  if (tid < 32) {
-    if (tid == 0) {
-      float x0 = 0.f, x1 = 0.f;
-      for (int wq = 0; wq < 8; ++wq) { x0 += red[wq][0]; x1 += red[wq][1]; }
-      sums[0] = x0; sums[1] = x1;
-    }
-    __syncwarp();
-    const int part = blockIdx.y * gridDim.x + blockIdx.x;
-    gn_publish_and_finalize_warp(sums, partials, counters, meanrstd, b, part, gridDim.x * gridDim.y, 1,
-                                 (float)H * (float)W, kGnEps);
+  if (tid < 2) {
+    float x0 = 0.f;
+    for (int wq = 0; wq < 8; ++wq) x0 += red[wq][tid];
+    gn_red_add(out_sums + (size_t)b * 8 + tid, x0);
   }
 }
 
 // ------------------------------------------------------------------ conv 1 -> 1 (last conv) + time bias
 // e fp32 [B,H,W] raw --GN(1,1)+SiLU on load--> 3x3 conv + (conv bias + time_emb)[b] -> eps fp32 [B,H,W].
-__global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict__ e, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict__ e, const long long* __restrict__ in_sums /*[B][8]*/,
                                                         const float* __restrict__ gn_w, const float* __restrict__ gn_b,
                                                         const float* __restrict__ w /*[9]*/, BiasRef bias,
                                                         float* __restrict__ out, int H, int W) {
@@ -406,7 +328,8 @@ __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict_
   const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
   const int tid = threadIdx.x;
   __shared__ float tile[kCinTH + 2][kCinTW + 2];
-  const float mean = stats[b * 2], rstd = stats[b * 2 + 1];
+  float mean, rstd;
+  gn_mean_rstd_from_sums(in_sums + (size_t)b * 8, (double)H * (double)W, kGnEps, mean, rstd);
   const float ga = rstd * gn_w[0], gb = gn_b[0] - mean * rstd * gn_w[0];
   for (int i = tid; i < (kCinTH + 2) * (kCinTW + 2); i += 256) {
     int r = i / (kCinTW + 2), c = i % (kCinTW + 2);
