@@ -197,6 +197,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (error returned to the host) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 22); ++i) {
     if (mbar_try_wait(bar, parity)) return;
   }

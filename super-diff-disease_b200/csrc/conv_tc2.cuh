@@ -95,6 +95,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 22); ++i)
     if (mbar_try_wait_cluster(bar, parity)) return;
   printf("sdd: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x,

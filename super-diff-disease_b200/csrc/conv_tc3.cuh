@@ -411,7 +411,10 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       if (!w_ready) { mbar_wait(w_bar, 0); w_ready = true; }  // this CTA's weights have landed too
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(ready_bar(stage), 0);
+      // relaxed: the proxy fence above has already completed this thread's shared-memory writes (MEMBAR.ALL.CTA) and
+      // made them visible to the async proxy of THIS CTA's tensor core, which is the only reader; a release at
+      // cluster scope would additionally wait ~900 cycles on the in-flight global loads of the next item
+      if (lane == 0) mbar_arrive_relaxed_remote(ready_bar(stage), 0);
       if (tt == 0) SDD_TRACE(2, it, 2 + kc);
       if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       ++item;

@@ -230,7 +230,7 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
                            int Cin, int Cout, cudaStream_t st, int dbg = 0, long long* trace = nullptr) {
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
   SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
-  SDD_CHECK((size_t)B * H * W * Cin * 2 < ((size_t)1 << 40), "tensor too large");
+  SDD_CHECK((size_t)B * H * W * Cin * 2 < ((size_t)1 << 32), "input tensor of one launch must be < 4 GB (32-bit offsets)");
   static bool attr = false;
   if (!attr) {
     SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
