@@ -191,7 +191,7 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int th = tr0 / a.tiles_w, tw = tr0 - th * a.tiles_w;
       int kc = 0, pair = pair0;
       for (int j = 0; j < my_items; ++j) {
-        while (j >= *s_progress + a.prefetch) __nanosleep(100);
+        while (j >= *s_progress + a.prefetch) __nanosleep(800);
         tma_prefetch_l2_4d(&tmA, kc * 64, tw * kTileW - 1, th * kTileH - 1, n);
         if (++kc == kchunks) {
           kc = 0; pair += pair_stride;
