@@ -300,7 +300,7 @@ def main():
                 "config": workload_config(args, world), "clocks": clk,
                 "gpu_launches": int(launches) * args.steps * world,
                 "whole_path_tensor_frac_of_sustained": value / world * step_flops / (tf_sust * 1e12),
-                "roofline": {"kernel": "conv3x3_tc2_kernel<128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)", "bound": "tensor",
+                "roofline": {"kernel": "conv3x3_tc3_kernel<128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)", "bound": "tensor",
                              "achieved": conv_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_tf / tf_burst,
                              "traffic": None, "peak_source": f"{src} bf16 burst", "launch_ms": conv_ms,
                              "how": f"kernel alone at the sampler's launch shape ({chunk}x{R}x{R}x128), CUDA events "

@@ -423,8 +423,13 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     dim3 eg = egrid; eg.z = nb;
     // downs.0: GN(1,1)+SiLU fused into the 1->64 conv; raw result in act[0], its GroupNorm(4,64) sums -> sums(0)
     const BlockParams& d0 = u->blk[0];
-    conv_in_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
-                                       sums(0), H, W);
+    static const bool conv_in_simt = getenv("SDD_CONV_IN_SIMT") != nullptr;  // A/B: fp32 CUDA-core version
+    if (conv_in_simt)
+      conv_in_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
+                                         sums(0), H, W);
+    else
+      conv_in_mma_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
+                                             sums(0), H, W);
     SDD_LAUNCH_CHECK();
     // every tensor-core conv normalises + activates its own input (GroupNorm+SiLU fused on the operand path)
     SDD_TRY(launch_conv_tc3(ws.tm_halo[0][0], d0.tm_w2h, ws.act[0], ws.act[1], bias_time(0),

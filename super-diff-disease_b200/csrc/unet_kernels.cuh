@@ -162,6 +162,109 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------ conv 1 -> 64 on tensor cores (product path)
+// Same contract as conv_in_kernel.  A 576-MAC/pixel layer is FMA-bound on the CUDA cores at about the rate HBM can
+// absorb its 128 B/pixel of output, so the multiply goes to mma.sync instead: per 16-pixel m-tile,
+//   D[16 px x 64 co] = A[16 px x 16 taps (9 used)] * B[16 taps x 64 co],  m16n8k8 TF32 (fp32 accumulate),
+// TF32 (10-bit mantissa, round-to-nearest) rather than bf16 keeps this first layer close to the fp32 reference.
+// The N order is permuted so that lane t = lane%4 ends up with the 16 CONTIGUOUS channels [16t, 16t+16) of its two
+// pixels (n-tile j, column 2t+{0,1}  <->  channel 16t + 2j + {0,1}): 32-byte NHWC stores with no shuffles, and a
+// lane's channels are exactly GroupNorm group t.
+__device__ __forceinline__ void mma_tf32_1688(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+constexpr int kCinTS = 40;  // tile row stride in floats: the four tap groups of a warp's gather hit disjoint banks
+
+__global__ void __launch_bounds__(256) conv_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ xstats,
+                                                          const float* __restrict__ gn_w, const float* __restrict__ gn_b,
+                                                          const float* __restrict__ w /*[64][9]*/, BiasRef bias,
+                                                          __nv_bfloat16* __restrict__ out, long long* out_sums /*[B][4][2]*/,
+                                                          int H, int W) {
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = lane & 3, g = lane >> 2;
+  __shared__ uint32_t tile[kCinTH + 2][kCinTS];  // silu(GroupNorm(1,1)(x)) as TF32 bit patterns, 1-pixel halo
+  const float mean = xstats[b * 2], rstd = xstats[b * 2 + 1];
+  const float ga = rstd * gn_w[0], gb = gn_b[0] - mean * rstd * gn_w[0];
+  for (int i = tid; i < (kCinTH + 2) * (kCinTW + 2); i += 256) {
+    const int r = i / (kCinTW + 2), c = i - r * (kCinTW + 2);
+    const int h = h0 + r - 1, ww = w0 + c - 1;
+    float v = 0.f;
+    if (h >= 0 && h < H && ww >= 0 && ww < W) v = silu_f(fmaf(x[((size_t)b * H + h) * W + ww], ga, gb));
+    tile[r][c] = to_tf32(v);
+  }
+  // B fragments: k-step 0 holds taps t and t+4, k-step 1 only tap 8 (lane t == 0); column n = g of n-tile j
+  uint32_t bw0[8], bw1[8], bw2[8];
+  float bv[16];
+  const float* bp = bias_ptr(bias, b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = (g >> 1) * 16 + j * 2 + (g & 1);
+    bw0[j] = to_tf32(w[ch * 9 + t]);
+    bw1[j] = to_tf32(w[ch * 9 + t + 4]);
+    bw2[j] = t == 0 ? to_tf32(w[ch * 9 + 8]) : 0u;
+    bv[2 * j] = bp[t * 16 + 2 * j];
+    bv[2 * j + 1] = bp[t * 16 + 2 * j + 1];
+  }
+  // tile-relative offsets of this lane's taps: tap k -> (ky, kx) = (k / 3, k % 3)
+  const int o0 = (t / 3) * kCinTS + (t % 3), o1 = ((t + 4) / 3) * kCinTS + ((t + 4) % 3), o2 = 2 * kCinTS + 2;
+  __syncthreads();
+
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int mt = warp * 2 + k;               // 16 m-tiles: image row mt/2 of the tile, columns (mt%2)*16 .. +15
+    const int r = mt >> 1, c = (mt & 1) * 16 + g;
+    const uint32_t* tp = &tile[r][c];
+    const uint32_t a0[4] = {tp[o0], tp[o0 + 8], tp[o1], tp[o1 + 8]};          // rows g / g+8, taps t / t+4
+    const uint32_t a1[4] = {t == 0 ? tp[o2] : 0u, t == 0 ? tp[o2 + 8] : 0u, 0u, 0u};  // tap 8
+    float d[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[j][0] = bv[2 * j]; d[j][1] = bv[2 * j + 1]; d[j][2] = bv[2 * j]; d[j][3] = bv[2 * j + 1];
+      mma_tf32_1688(d[j], a0, bw0[j], bw1[j]);
+      mma_tf32_1688(d[j], a1, bw2[j], 0u);
+    }
+    const int h = h0 + r;
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      const int ww = w0 + c + 8 * rh;
+      if (h < H && ww < W) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float v0 = d[j][2 * rh], v1 = d[j][2 * rh + 1];
+          s += v0 + v1;
+          ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss);
+          pk[j] = pack_bf16x2(v0, v1);
+        }
+        st_global_v8(out + (((size_t)b * H + h) * W + ww) * 64 + t * 16, pk);
+      }
+    }
+  }
+  // this lane's channels are GroupNorm group t: sum over the 8 lanes sharing t, then over the 8 warps (fixed order)
+  s += __shfl_xor_sync(0xffffffffu, s, 4);   ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 8);   ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);  ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+  __shared__ float red[8][4][2];
+  if (lane < 4) { red[warp][lane][0] = s; red[warp][lane][1] = ss; }
+  __syncthreads();
+  if (tid < 8) {
+    float acc = 0.f;
+    for (int wq = 0; wq < 8; ++wq) acc += red[wq][tid >> 1][tid & 1];
+    gn_red_add(out_sums + (size_t)b * 8 + tid, acc);
+  }
+}
+
 // ------------------------------------------------------------------ GroupNorm(4,C)+SiLU apply, in place
 // act bf16 NHWC [B,H,W,C]; each thread handles 8 consecutive channels (16 bytes).
 __global__ void __launch_bounds__(256) gn_silu_apply_kernel(__nv_bfloat16* act, const float* __restrict__ meanrstd,
@@ -253,24 +356,36 @@ __global__ void __launch_bounds__(256, 3) conv_out1_mma_kernel(const __nv_bfloat
       }
 
   const __nv_bfloat16* img = raw + (size_t)b * H * W * 64 + t * 16;
-  for (int mt = warp; mt < kO1MT; mt += 8) {
-    uint32_t a[2][8];  // [row half][ks*2+h]
+  // software pipeline over this warp's m-tiles (2 or 3 of them): the raw vectors of m-tile k+1 are in flight while
+  // m-tile k is normalised, activated and multiplied, so a warp pays the global-load latency once, not per m-tile
+  auto load_mt = [&](int mt, uint4 (&v)[2][2], bool (&ok)[2]) {
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
       const int p = mt * 16 + j + 8 * rh;
       const int hr = p / kO1HW, wr = p - hr * kO1HW;
       const int hh = h0 - 1 + hr, ww = w0 - 1 + wr;
-      const bool ok = p < kO1Pix && hh >= 0 && hh < H && ww >= 0 && ww < W;
-      uint4 v0 = make_uint4(0u, 0u, 0u, 0u), v1 = v0;
-      if (ok) {
+      ok[rh] = p < kO1Pix && hh >= 0 && hh < H && ww >= 0 && ww < W;
+      v[rh][0] = make_uint4(0u, 0u, 0u, 0u);
+      v[rh][1] = v[rh][0];
+      if (ok[rh]) {
         const uint4* src = reinterpret_cast<const uint4*>(img + ((size_t)hh * W + ww) * 64);
-        v0 = __ldg(src);
-        v1 = __ldg(src + 1);
+        v[rh][0] = __ldg(src);
+        v[rh][1] = __ldg(src + 1);
       }
-      uint32_t u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    }
+  };
+  uint4 vc[2][2], vn[2][2];
+  bool okc[2], okn[2] = {false, false};
+  load_mt(warp, vc, okc);
+  for (int mt = warp; mt < kO1MT; mt += 8) {
+    if (mt + 8 < kO1MT) load_mt(mt + 8, vn, okn);
+    uint32_t a[2][8];  // [row half][ks*2+h]
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) {
+      uint32_t u[8] = {vc[rh][0].x, vc[rh][0].y, vc[rh][0].z, vc[rh][0].w, vc[rh][1].x, vc[rh][1].y, vc[rh][1].z, vc[rh][1].w};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (ok) {
+        if (okc[rh]) {
           __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[i]);
           const float lo = silu_tanh(fmaf(__low2float(hv), ga[2 * i], gb[2 * i]));
           const float hi = silu_tanh(fmaf(__high2float(hv), ga[2 * i + 1], gb[2 * i + 1]));
@@ -291,6 +406,8 @@ __global__ void __launch_bounds__(256, 3) conv_out1_mma_kernel(const __nv_bfloat
     tb[r0][2 * t] = d0[0]; tb[r0][2 * t + 1] = d0[1];
     tb[r0 + 8][2 * t] = d0[2]; tb[r0 + 8][2 * t + 1] = d0[3];
     if (t == 0) { tb[r0][8] = d1[0]; tb[r0 + 8][8] = d1[2]; }
+#pragma unroll
+    for (int rh = 0; rh < 2; ++rh) { vc[rh][0] = vn[rh][0]; vc[rh][1] = vn[rh][1]; okc[rh] = okn[rh]; }
   }
   __syncthreads();
 
