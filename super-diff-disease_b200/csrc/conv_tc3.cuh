@@ -375,37 +375,49 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         named_bar_sync(2, kC3LoaderThreads);
         cur_n = c.n;
       }
-      float ga[8], gb[8];
+      // scale / shift of this thread's 8 channels as packed fp32 pairs for FFMA2 (fma.rn.f32x2)
+      uint64_t ga2[4], gb2[4];
       if (fuse) {
         const int coff = kc * 64 + piece * 8;
 #pragma unroll
-        for (int j = 0; j < 8; j += 4) {
-          const float4 x = *reinterpret_cast<const float4*>(&s_ga[coff + j]);
-          const float4 y = *reinterpret_cast<const float4*>(&s_gb[coff + j]);
-          ga[j] = x.x; ga[j + 1] = x.y; ga[j + 2] = x.z; ga[j + 3] = x.w;
-          gb[j] = y.x; gb[j + 1] = y.y; gb[j + 2] = y.z; gb[j + 3] = y.w;
+        for (int j = 0; j < 4; j += 2) {
+          const float4 x = *reinterpret_cast<const float4*>(&s_ga[coff + 2 * j]);
+          const float4 y = *reinterpret_cast<const float4*>(&s_gb[coff + 2 * j]);
+          ga2[j] = pack_f32x2(x.x, x.y); ga2[j + 1] = pack_f32x2(x.z, x.w);
+          gb2[j] = pack_f32x2(y.x, y.y); gb2[j + 1] = pack_f32x2(y.z, y.w);
         }
       }
+      // silu(gn(v)) of one bf16 pair: 2 unpack + FFMA2 + 2 MUFU.TANH + FFMA2 + 1 pack
+      auto xform_pair = [&](uint32_t u, int j) -> uint32_t {
+        const uint64_t h = fma_f32x2(pack_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)), ga2[j], gb2[j]);
+        float hl, hh;
+        unpack_f32x2(h, hl, hh);
+        const uint64_t r = fma_f32x2(h, pack_f32x2(tanh_approx(hl), tanh_approx(hh)), h);
+        float rl, rh;
+        unpack_f32x2(r, rl, rh);
+        return pack_bf16x2(rl, rh);
+      };
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (tt == 0) { *s_progress = item + 1; SDD_TRACE(2, it, kc); }
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes;
       if (active) {
+        if (fuse && ok_c == (1u << kC3Vecs) - 1u && !(a.dbg & 64)) {
+          // interior tile (the common case): straight-line code, the six vectors' chains interleave freely
 #pragma unroll
-        for (int i = 0; i < kC3Vecs; ++i) {
-          uint4 v = cur[i];
-          if (fuse && ((ok_c >> i) & 1u) && !(a.dbg & 64)) {
-            uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[j]);
-              const float hl = fmaf(__low2float(hv), ga[2 * j], gb[2 * j]);
-              const float hh = fmaf(__high2float(hv), ga[2 * j + 1], gb[2 * j + 1]);
-              u[j] = pack_bf16x2(fmaf(hl, tanh_approx(hl), hl), fmaf(hh, tanh_approx(hh), hh));
-            }
-            v = make_uint4(u[0], u[1], u[2], u[3]);
+          for (int i = 0; i < kC3Vecs; ++i) {
+            const int row = (hr0 + i) * kHaloW + wr;
+            sts_v4(dst + (uint32_t)row * 128u + (uint32_t)((piece ^ (row & 7)) << 4),
+                   make_uint4(xform_pair(cur[i].x, 0), xform_pair(cur[i].y, 1), xform_pair(cur[i].z, 2), xform_pair(cur[i].w, 3)));
           }
-          const int row = (hr0 + i) * kHaloW + wr;  // padding pixels hold the zeros they were "loaded" as
-          sts_v4(dst + (uint32_t)row * 128u + (uint32_t)((piece ^ (row & 7)) << 4), v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < kC3Vecs; ++i) {
+            uint4 v = cur[i];
+            if (fuse && ((ok_c >> i) & 1u) && !(a.dbg & 64))
+              v = make_uint4(xform_pair(v.x, 0), xform_pair(v.y, 1), xform_pair(v.z, 2), xform_pair(v.w, 3));
+            const int row = (hr0 + i) * kHaloW + wr;  // padding pixels hold the zeros they were "loaded" as
+            sts_v4(dst + (uint32_t)row * 128u + (uint32_t)((piece ^ (row & 7)) << 4), v);
+          }
         }
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
