@@ -140,6 +140,8 @@ int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, cons
 int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W,
                         int Cin, int Cout, int impl, int iters, void* flush, size_t flush_bytes, float* ms_host,
                         void* stream);
+/* Times the one-pass update kernel ALONE (the event pair brackets superpose_update_kernel; the tiny per-sample finalize
+ * kernel that follows it is launched after the second event). */
 int sdd_superpose_update_profile(float* x, const float* eps, const float* noise, float* logq, int B, int D,
                                  int M, int iters, void* flush, size_t flush_bytes, float* ms_host,
                                  void* stream);

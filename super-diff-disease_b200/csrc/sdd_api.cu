@@ -567,7 +567,7 @@ size_t sdd_superpose_update_workspace(int B, int D, int M) { return update_works
 }  // extern "C"
 
 namespace sdd {
-int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st) {
+int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st, cudaEvent_t after_update = nullptr) {
   SDD_CHECK(a.M >= 1 && a.M <= kMaxModels, "1 <= M <= 4");
   SDD_CHECK(a.D % 4 == 0 && a.D > 0 && a.B > 0, "D must be a positive multiple of 4");
   a.nblk = update_blocks_per_sample(a.D);
@@ -580,6 +580,7 @@ int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st) {
     default: superpose_update_kernel<4><<<grid, kUpdThreads, 0, st>>>(a); break;
   }
   SDD_LAUNCH_CHECK();
+  if (after_update) cudaEventRecord(after_update, st);  // roofline timing of the HBM pass alone
   switch (a.M) {
     case 1: superpose_finalize_kernel<1><<<a.B, 256, 0, st>>>(a); break;
     case 2: superpose_finalize_kernel<2><<<a.B, 256, 0, st>>>(a); break;
@@ -621,6 +622,7 @@ int sdd_superpose_update(const float* x_in, float* x_out, const float* eps, cons
   a.logq = logq; a.logq_out = logq_out; a.kappa_out = kappa_out; a.xstats_out = xstats_out;
   a.sc.alpha = alpha; a.sc.alpha_bar = alpha_bar; a.sc.beta = beta;
   a.sc.draw_index = noise ? 0 : draw_index;
+  step_scalars_fill(a.sc);
   a.temperature = temperature; a.bias = bias; a.seed = seed; a.sample_offset = sample_offset;
   a.B = B; a.D = D; a.M = M;
   return launch_superpose_update(a, workspace, (cudaStream_t)stream);
@@ -724,6 +726,7 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
     int t = T - 1 - k;
     sc[k].alpha = alphas_host[t]; sc[k].alpha_bar = alpha_bars_host[t]; sc[k].beta = betas_host[t];
     sc[k].draw_index = t > 0 ? k + 1 : -1;  // ddpm.py:36: no noise at t == 0
+    step_scalars_fill(sc[k]);
     trev[k] = t;
   }
   S_CUDA(cudaMalloc(&s->sched, T * sizeof(StepScalars)));
@@ -980,6 +983,7 @@ int sdd_superpose_update_profile(float* x, const float* eps, const float* noise,
   memset(&a, 0, sizeof(a));
   a.x_in = x; a.x_out = x; a.eps = eps; a.noise = noise; a.logq = logq; a.logq_out = logq;
   a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f; a.temperature = 1.0f; a.seed = 1234;
+  step_scalars_fill(a.sc);
   a.B = B; a.D = D; a.M = M;
   int rc = SDD_OK;
   double total = 0.0;
@@ -987,9 +991,8 @@ int sdd_superpose_update_profile(float* x, const float* eps, const float* noise,
     if (flush && flush_bytes) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
     a.sc.draw_index = noise ? 0 : i;
     cudaEventRecord(e0, st);
-    rc = launch_superpose_update(a, ws, st);
-    cudaEventRecord(e1, st);
-    if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("update profile: kernel failed"); rc = SDD_ECUDA; break; }
+    rc = launch_superpose_update(a, ws, st, e1);  // e1 is recorded between the update and the finalize kernel
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("update profile: kernel failed"); rc = SDD_ECUDA; break; }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
     if (i >= 2) total += ms;

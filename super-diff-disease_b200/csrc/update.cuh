@@ -16,7 +16,19 @@ constexpr int kUpdThreads = 256;
 struct StepScalars {
   float alpha, alpha_bar, beta;
   int draw_index;  // Philox draw index / noise-stack slice for this step; < 0 => z = 0 (t == 0)
+  // coefficients of the x update, evaluated ONCE on the host in fp32 with IEEE sqrt / divide -- the same correctly
+  // rounded operations torch performs for ddpm.py:42-44, so every thread no longer repeats ~50 instructions of them:
+  float c1;  // 1 / sqrt(alpha)
+  float c2;  // (1 - alpha) / sqrt(1 - alpha_bar)
+  float c3;  // sqrt(beta)
+  float pad;
 };
+inline void step_scalars_fill(StepScalars& s) {
+  s.c1 = 1.0f / sqrtf(s.alpha);
+  s.c2 = (1.0f - s.alpha) / sqrtf(1.0f - s.alpha_bar);
+  s.c3 = sqrtf(s.beta);
+  s.pad = 0.f;
+}
 
 struct UpdateArgs {
   const float* x_in;
@@ -62,8 +74,9 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t q, uint
   float4 o;
   // accurate logf (the radius is ill-conditioned near u = 1); fast sqrt and sin/cos (angle in (-pi, pi], where the
   // MUFU approximations are good to ~4e-7 absolute).  Normals agree with the float64 oracle to < 5e-6.
-  float rad0 = __fsqrt_rn(-2.0f * logf(u01(r.x)));
-  float rad1 = __fsqrt_rn(-2.0f * logf(u01(r.z)));
+  float rad0, rad1;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(rad0) : "f"(-2.0f * logf(u01(r.x))));
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(rad1) : "f"(-2.0f * logf(u01(r.z))));
   float s0, c0, s1, c1;
   __sincosf(3.14159265358979f * (2.0f * u01(r.y) - 1.0f), &s0, &c0);
   __sincosf(3.14159265358979f * (2.0f * u01(r.w) - 1.0f), &s1, &c1);
@@ -98,15 +111,17 @@ __device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, int b, float 
     lg[m] = a.temperature * a.logq[b * M + m] + (a.bias ? a.bias[m] : 0.0f);
     mx = fmaxf(mx, lg[m]);
   }
+  // fast exp / divide (relative error ~2^-21, far inside the 2e-6 kappa tolerance; exp(0) = 1 and 1/2 stay exact, so
+  // self-superposition still yields kappa == 0.5 bit-for-bit).  The update and the finalize kernel share this function.
   float den = 0.0f;
 #pragma unroll
-  for (int m = 0; m < M; ++m) { kap[m] = expf(lg[m] - mx); den += kap[m]; }
+  for (int m = 0; m < M; ++m) { kap[m] = __expf(lg[m] - mx); den += kap[m]; }
 #pragma unroll
-  for (int m = 0; m < M; ++m) kap[m] = kap[m] / den;
+  for (int m = 0; m < M; ++m) kap[m] = __fdividef(kap[m], den);
 }
 
 template <int M>
-__global__ void __launch_bounds__(kUpdThreads, 4) superpose_update_kernel(const UpdateArgs a) {
+__global__ void __launch_bounds__(kUpdThreads, 5) superpose_update_kernel(const UpdateArgs a) {
   const int b = blockIdx.y, seg = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int step = a.step_ptr ? *a.step_ptr : 0;
@@ -131,9 +146,7 @@ __global__ void __launch_bounds__(kUpdThreads, 4) superpose_update_kernel(const 
   }
   float kap[M];
   softmax_kappa<M>(a, b, kap);
-  const float c1 = 1.0f / sqrtf(sc.alpha);
-  const float c2 = (1.0f - sc.alpha) / sqrtf(1.0f - sc.alpha_bar);
-  const float c3 = sqrtf(sc.beta);
+  const float c1 = sc.c1, c2 = sc.c2, c3 = sc.c3;
   float4* xo4 = reinterpret_cast<float4*>(a.x_out + (size_t)b * a.D);
   const uint32_t gsample = (uint32_t)(a.sample_offset + b);
 
@@ -258,7 +271,7 @@ inline size_t update_workspace_bytes(int B, int D, int /*M*/) {
   return (part + 255) & ~(size_t)255;
 }
 
-int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream);
+int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream, cudaEvent_t after_update);
 
 __global__ void philox_normal_kernel(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw);
 __global__ void copy_f32_kernel(float* dst, const float* src, size_t n);
