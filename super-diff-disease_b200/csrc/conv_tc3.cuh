@@ -64,7 +64,15 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <int COUT>
+// stamps exist only in the kTrace instantiation (timing experiments, tools/conv_exp.py); the product kernel has none
+#define SDD_TRACE3(role, iter, ev)                                                                    \
+  do {                                                                                                \
+    if constexpr (kTrace) {                                                                           \
+      if (a.trace && blockIdx.x < 2 && (iter) < kTraceIters) s_trace[role][iter][ev] = clock64();     \
+    }                                                                                                 \
+  } while (0)
+
+template <int COUT, bool kTrace = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
 conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ConvTc3Args a) {
@@ -84,9 +92,11 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_slot = bar_base + 8u * (2 * kC3MaxStages + 5);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  __shared__ long long s_trace[5][kTraceIters][4];
-  if (a.trace && blockIdx.x < 2)
-    for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) (&s_trace[0][0][0])[i] = 0;
+  __shared__ long long s_trace[kTrace ? 5 : 1][kTrace ? kTraceIters : 1][4];
+  if constexpr (kTrace) {
+    if (a.trace && blockIdx.x < 2)
+      for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) (&s_trace[0][0][0])[i] = 0;
+  }
 
   __shared__ volatile int s_progress_v;  // items the loaders have started (paces the L2 prefetcher, warp 3)
   volatile int* s_progress = &s_progress_v;
@@ -144,12 +154,12 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int pair = pair0; pair < a.num_pairs; pair += pair_stride, ++it) {
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        if (lane == 0) SDD_TRACE(1, it, 0);
+        if (lane == 0) SDD_TRACE3(1, it, 0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait_cluster(ready_bar(stage), phase);
           tc_fence_after();
-          if (lane == 0) SDD_TRACE(1, it, 1 + kc);
+          if (lane == 0) SDD_TRACE3(1, it, 1 + kc);
           const uint32_t sa = a_base + stage * kHaloBytes;
           if (elect_one_sync()) {
 #pragma unroll
@@ -170,7 +180,7 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        if (lane == 0) SDD_TRACE(1, it, 3);
+        if (lane == 0) SDD_TRACE3(1, it, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -225,7 +235,7 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const bool do_store = valid && !(a.dbg & 2);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (e == 0 && lane == 0) SDD_TRACE(3, it, 0);
+      if (e == 0 && lane == 0) SDD_TRACE3(3, it, 0);
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + col0);
       float sg[2] = {0.f, 0.f}, ssg[2] = {0.f, 0.f};
       uint32_t v[2][16];
@@ -265,7 +275,7 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed_remote(tempty_bar(acc), 0);  // orders TMEM reads only, not the stores
-      if (e == 0 && lane == 0) SDD_TRACE(3, it, 1);
+      if (e == 0 && lane == 0) SDD_TRACE3(3, it, 1);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       // warp reduction of (sg0, ssg0, sg1, ssg1) in 6 shuffles: halve the value count while halving the lanes.
       // lane bit 4 selects the group it keeps, bit 3 the statistic; bits 2..0 are summed out.
@@ -282,7 +292,7 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if ((lane & 7) == 0 && do_store && a.out_sums)
           gn_red_add(a.out_sums + ((size_t)n * 4 + hcol * 2 + (lane >> 4)) * 2 + ((lane >> 3) & 1), val);
       }
-      if (e == 0 && lane == 0) SDD_TRACE(3, it, 2);
+      if (e == 0 && lane == 0) SDD_TRACE3(3, it, 2);
     }
   } else {
     // ===================== loaders: global -> registers -> GroupNorm+SiLU -> swizzled shared memory ==========
@@ -398,7 +408,7 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         return pack_bf16x2(rl, rh);
       };
       mbar_wait(empty_bar(stage), phase ^ 1u);
-      if (tt == 0) { *s_progress = item + 1; SDD_TRACE(2, it, kc); }
+      if (tt == 0) { *s_progress = item + 1; SDD_TRACE3(2, it, kc); }
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes;
       if (active) {
         if (fuse && ok_c == (1u << kC3Vecs) - 1u && !(a.dbg & 64)) {
@@ -427,7 +437,8 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // made them visible to the async proxy of THIS CTA's tensor core, which is the only reader; a release at
       // cluster scope would additionally wait ~900 cycles on the in-flight global loads of the next item
       if (lane == 0) mbar_arrive_relaxed_remote(ready_bar(stage), 0);
-      if (tt == 0) SDD_TRACE(2, it, 2 + kc);
+      if (tt == 0) SDD_TRACE3(2, it, 2 + kc);
+      if (lane == 0 && kc == kchunks - 1) SDD_TRACE3((warp < 16 ? 0 : 4), it, (warp & 3));  // every loader warp's arrive
       if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       ++item;
       if (kc_n == 0) ++it;
@@ -442,11 +453,13 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if (a.trace && blockIdx.x < 2)
-    for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) {
-      const int role = i / (kTraceIters * 4), rem = i % (kTraceIters * 4);
-      a.trace[(((size_t)blockIdx.x * 6 + role) * 64 + rem / 4) * 4 + (rem & 3)] = (&s_trace[0][0][0])[i];
-    }
+  if constexpr (kTrace) {
+    if (a.trace && blockIdx.x < 2)
+      for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) {
+        const int role = i / (kTraceIters * 4), rem = i % (kTraceIters * 4);
+        a.trace[(((size_t)blockIdx.x * 6 + role) * 64 + rem / 4) * 4 + (rem & 3)] = (&s_trace[0][0][0])[i];
+      }
+  }
   cluster_sync_all();  // the peer may still be reading our smem / arriving on our barriers
   if (warp == 2) {
     tc_fence_after();

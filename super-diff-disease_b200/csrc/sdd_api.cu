@@ -237,6 +237,10 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
                                   conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
     SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
+    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
+    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
     attr = true;
   }
   ConvTc3Args a;
@@ -255,7 +259,10 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   a.trace = trace;
   const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages);
   const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
-  if (Cout == 64)
+  if (trace) {  // timing-experiment instantiation with clock64 stamps
+    if (Cout == 64) conv3x3_tc3_kernel<64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+    else conv3x3_tc3_kernel<128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+  } else if (Cout == 64)
     conv3x3_tc3_kernel<64><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
   else
     conv3x3_tc3_kernel<128><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);

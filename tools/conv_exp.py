@@ -27,10 +27,13 @@ if os.environ.get("TRACE", "1") == "1":
         tf, ms = bench.conv_roofline(S, dev, 256, chunk, iters=2, cin=cin, cout=cout, impl=impl, flush_l2=True)
         print(tag, f"{ms*1000:.1f} us")
         rows = [list(map(int, l.split())) for l in open(path)]
-        d = collections.defaultdict(dict)
-        for c, r, i, *ev in rows:
-            if r < 5 and c == 0: d[r][i] = ev
-        c0 = min(v for r in d for ev in d[r].values() for v in ev if v)
-        for i in range(4, 12):
-            print("  it", i, " | ".join(roles[r] + ":" + ",".join(str(v - c0) if v else "-" for v in d[r][i]) for r in (2, 1, 3) if i in d[r]))
+        for cta in (0, 1):
+            d = collections.defaultdict(dict)
+            for c, r, i, *ev in rows:
+                if r < 5 and c == cta: d[r][i] = ev
+            c0 = min(v for r in d for ev in d[r].values() for v in ev if v)
+            print(" CTA", cta, "(clock64 is per SM: compare within a CTA only); w12-15 / w16-19 = each loader warp's last arrive of the tile")
+            names = {0: 'w12-15', 4: 'w16-19', 2: 'load', 1: 'mma', 3: 'epi'}
+            for i in range(5, 11):
+                print("  it", i, " | ".join(names[r] + ":" + ",".join(str(v - c0) if v else "-" for v in d[r][i]) for r in (0, 4, 2, 1, 3) if i in d[r]))
     del os.environ["SDD_CONV_TRACE"]
