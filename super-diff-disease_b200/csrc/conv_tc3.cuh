@@ -383,13 +383,19 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint8_t* src; uint32_t ok_c;
     uint4 ra[kC3Vecs], rb[kC3Vecs];
     if (my_items > 0) { item_src(c, 0, src, ok_c); issue_loads(ra, src, ok_c); }
+    // look-ahead: coordinates, source pointer and mask of item j+1 are computed during item j-1's transform, so the
+    // top of an item only has to issue six loads (the serial address arithmetic no longer sits between two items)
+    auto advance = [&](const Cursor& cc, int kk, int pp, Cursor& c2, int& k2, int& p2) {
+      c2 = cc; k2 = kk + 1; p2 = pp;
+      if (k2 == kchunks) { k2 = 0; p2 = pp + pair_stride; c2 = cursor_next(cc, p2); }
+    };
+    Cursor c1; int kc1, pair1; const uint8_t* src1 = nullptr; uint32_t ok1 = 0;
+    advance(c, kc, pair, c1, kc1, pair1);
+    if (my_items > 1) item_src(c1, kc1, src1, ok1);
 
     auto process = [&](uint4 (&cur)[kC3Vecs], uint4 (&nxt)[kC3Vecs]) {
-      // ---- item j+1: coordinates, then its loads go out first
-      Cursor c_n = c; int kc_n = kc + 1, pair_n = pair;
-      if (kc_n == kchunks) { kc_n = 0; pair_n = pair + pair_stride; c_n = cursor_next(c, pair_n); }
-      uint32_t ok_n = 0;
-      if (item + 1 < my_items) { const uint8_t* src_n; item_src(c_n, kc_n, src_n, ok_n); issue_loads(nxt, src_n, ok_n); }
+      // ---- item j+1: its loads go out first (addresses were prepared during the previous item)
+      if (item + 1 < my_items) issue_loads(nxt, src1, ok1);
       // ---- GroupNorm scale / shift of this sample (pre-halved: silu(v) = h + h tanh(h), h = v/2)
       if (fuse && c.n != cur_n) {
         named_bar_sync(2, kC3LoaderThreads);  // previous readers of s_ga/s_gb are done
@@ -431,6 +437,10 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       };
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (tt == 0) { *s_progress = item + 1; SDD_TRACE3(2, it, kc); }
+      // ---- item j+2: coordinates / pointer / mask, interleaved by the scheduler with the transform below
+      Cursor c2; int kc2, pair2; const uint8_t* src2 = nullptr; uint32_t ok2 = 0;
+      advance(c1, kc1, pair1, c2, kc2, pair2);
+      if (item + 2 < my_items) item_src(c2, kc2, src2, ok2);
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes;
       if (active) {
         if (fuse && ok_c == (1u << kC3Vecs) - 1u && !(a.dbg & 64)) {
@@ -463,8 +473,9 @@ conv3x3_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (lane == 0 && kc == kchunks - 1) SDD_TRACE3((warp < 16 ? 0 : 4), it, (warp & 3));  // every loader warp's arrive
       if (++stage == a.stages) { stage = 0; phase ^= 1u; }
       ++item;
-      if (kc_n == 0) ++it;
-      c = c_n; kc = kc_n; pair = pair_n; ok_c = ok_n;
+      if (kc1 == 0) ++it;
+      c = c1; kc = kc1; pair = pair1; ok_c = (item < my_items) ? ok1 : 0u;
+      c1 = c2; kc1 = kc2; pair1 = pair2; src1 = src2; ok1 = ok2;
     };
     while (item < my_items) {
       process(ra, rb);
