@@ -92,7 +92,10 @@ class UNet(nn.Module):
             self._handle_key = None
 
     def __del__(self):
-        self._free()
+        try:
+            self._free()
+        except Exception:  # interpreter shutdown: torch internals may already be torn down
+            pass
 
     # ---- forward -----------------------------------------------------------------------------
     @torch.no_grad()

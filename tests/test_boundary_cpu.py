@@ -128,3 +128,21 @@ def test_two_rank_gloo_gather_is_shard_invariant(gb):
         p.join(60)
     single = philox_normal(99, np.arange(gb), 0, 64).reshape(gb, 1, 8, 8)
     assert np.array_equal(res[0], single) and np.array_equal(res[1], single)
+
+
+def test_cli_checkpoint_layout_and_grid(tmp_path):
+    """N1: the CLI resolves checkpoints with the reference's layout (env.py:26, training_logic.py:47-48), accepts plain
+    and ema_pytorch-prefixed state_dicts, and fails like the reference (FileNotFoundError) on a missing file."""
+    import numpy as np
+    import torch
+    from super_diff_disease_b200 import cli
+    assert cli.checkpoint_path("/ck", "exp1", "runA", "TB", 7) == "/ck/exp1/runA/TB/ema_epoch7.pt"
+    assert cli.checkpoint_path("/ck", "exp1", "runA", "PNEUMONIA", 7, ema=False) == "/ck/exp1/runA/PNEUMONIA/ddpm_epoch7.pt"
+    with pytest.raises(FileNotFoundError):
+        cli.main(["--tb", str(tmp_path / "a.pt"), "--pneumonia", str(tmp_path / "b.pt")])
+    x = torch.arange(2 * 16 * 8, dtype=torch.float32).reshape(2, 1, 16, 8)
+    cli.save_grid_pgm(x, str(tmp_path / "g.pgm"), cols=2)
+    raw = open(tmp_path / "g.pgm", "rb").read()
+    assert raw.startswith(b"P5\n16 16\n255\n") and len(raw) == len(b"P5\n16 16\n255\n") + 256
+    img = np.frombuffer(raw[-256:], dtype=np.uint8).reshape(16, 16)
+    assert img[0, 0] == 0 and img[15, 7] == 255 and img[0, 8] == 0 and img[15, 15] == 255
