@@ -1,0 +1,408 @@
+// Product tensor-core 3x3 conv, generation 4 = generation 3 (conv_tc3.cuh: same contract, same MMA / epilogue / barriers)
+// with the loader warps split into TWO groups that work on alternating 64-channel items (see the loader section).
+#pragma once
+#include "conv_tc3.cuh"
+
+namespace sdd {
+
+// stamps exist only in the kTrace instantiation (timing experiments, tools/conv_exp.py); the product kernel has none
+#define SDD_TRACE4(role, iter, ev)                                                                    \
+  do {                                                                                                \
+    if constexpr (kTrace) {                                                                           \
+      if (a.trace && blockIdx.x < 2 && (iter) < kTraceIters) s_trace[role][iter][ev] = clock64();     \
+    }                                                                                                 \
+  } while (0)
+
+template <int COUT, bool kTrace = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
+conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const ConvTc3Args a) {
+  constexpr int kWSlot = (COUT / 2) * 128;  // bytes of one (tap, chunk) weight slice held by this CTA
+  constexpr int kTmemCols = 2 * COUT;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int kchunks = a.Cin / 64;
+  const uint32_t w_bytes = 9u * kchunks * kWSlot;
+  const uint32_t a_base = smem_base + w_bytes;
+  const uint32_t bar_base = a_base + (uint32_t)a.stages * kHaloBytes;
+  auto ready_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kC3MaxStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + 2 + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kC3MaxStages + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kC3MaxStages + 5);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  __shared__ long long s_trace[kTrace ? 5 : 1][kTrace ? kTraceIters : 1][4];
+  if constexpr (kTrace) {
+    if (a.trace && blockIdx.x < 2)
+      for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) (&s_trace[0][0][0])[i] = 0;
+  }
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
+  if (warp == 1 && lane == 0) {
+    // ready: one loader group (4 warps) per CTA and item -> 8 arrivals
+    for (int s = 0; s < a.stages; ++s) { mbar_init(ready_bar(s), kC3LoaderWarps); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  // tile of this CTA in a pair-iteration; an odd tile count leaves one dummy (clamped, computed, not stored)
+  auto tile_of = [&](int pair, bool& valid) {
+    int t = 2 * pair + (int)rank;
+    valid = t < a.num_tiles;
+    return valid ? t : a.num_tiles - 1;
+  };
+
+  // Register re-partitioning by warpgroup: the kernel is launched with 96 registers per thread (61440 per CTA, and only
+  // registers the CTA itself releases can be re-acquired): control warps 96 -> 40 (frees 7168), epilogue 96 -> 88
+  // (frees 2048), and the two loader warpgroups (two 24-register load buffers + the transform) 96 -> 128 (takes 8192).
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  if (warp == 0) {
+    // ===================== resident weights: this CTA's Cout/2 rows of all 9 taps, once =====================
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(w_bar, w_bytes);
+      for (int tap = 0; tap < 9; ++tap)
+        for (int kc = 0; kc < kchunks; ++kc)
+          tma_load_3d(smem_base + (uint32_t)(tap * kchunks + kc) * kWSlot, &tmB, w_bar, kc * 64,
+                      (int)rank * (COUT / 2), tap);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) ===
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, COUT);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      int it = 0;
+      for (int pair = pair0; pair < a.num_pairs; pair += pair_stride, ++it) {
+        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        if (lane == 0) SDD_TRACE4(1, it, 0);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait_cluster(ready_bar(stage), phase);
+          tc_fence_after();
+          if (lane == 0) SDD_TRACE4(1, it, 1 + kc);
+          const uint32_t sa = a_base + stage * kHaloBytes;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                const uint64_t adesc = umma_desc_sw128(sa + (ky * kHaloW + kx) * 128, kHaloW * 128);
+                const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)((kx * 3 + ky) * kchunks + kc) * kWSlot);
+                if (a.dbg & 4) continue;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // 4 x UMMA_K (16 bf16 = 32 B) inside the 128-byte swizzle row
+                  umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                 (kc | kx | ky | k) ? 1u : 0u);
+              }
+            umma_commit_2cta(empty_bar(stage));                         // frees the stage in both CTAs
+            if (kc == kchunks - 1) umma_commit_2cta(tfull_bar(acc));    // accumulator complete -> both epilogues
+          }
+          __syncwarp();
+          if (++stage == a.stages) { stage = 0; phase ^= 1u; }
+        }
+        if (lane == 0) SDD_TRACE4(1, it, 3);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  }
+  } else if (warp < 12) {
+    // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    constexpr int COLS = COUT / 2;  // columns drained by this warp (two GroupNorm groups)
+    constexpr int G = COLS / 16;    // 16-channel chunks per pixel and warp: 4 (Cout = 128) or 2 (Cout = 64)
+    const int e = warp - 4, q = e & 3, hcol = e >> 2;
+    const int col0 = hcol * COLS;
+    const int m = q * 32 + lane;  // accumulator row = pixel within the tile
+    const float* bias_row = a.bias.base + (a.bias.row_ptr ? (int64_t)(*a.bias.row_ptr) : 0) * a.bias.row_stride + col0;
+    int acc = 0; uint32_t acc_phase = 0;
+    int it = 0;
+    for (int pair = pair0; pair < a.num_pairs; pair += pair_stride, ++it) {
+      bool valid;
+      const int tile = tile_of(pair, valid);
+      const int n = tile / a.tiles_per_sample, tr = tile - n * a.tiles_per_sample;
+      const int th = tr / a.tiles_w, tw = tr - th * a.tiles_w;
+      const int h = th * kTileH + (m >> 3), w = tw * kTileW + (m & 7);
+      const float* bp = bias_row + (int64_t)n * a.bias.batch_stride;
+      __nv_bfloat16* orow = a.out + (((size_t)n * a.H + h) * a.W + w) * COUT + col0;
+      const bool do_store = valid && !(a.dbg & 2);  // dbg 2: no stores (statistics stay), dbg 8: no statistics
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      if (e == 0 && lane == 0) SDD_TRACE4(3, it, 0);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + col0);
+      float sg[2] = {0.f, 0.f}, ssg[2] = {0.f, 0.f};
+      uint32_t v[2][16];
+      uint32_t pk[G][8];  // this lane's pixel: G chunks of 16 channels (32 B each), packed bf16
+      tmem_ld_32x16(taddr, v[0]);
+#pragma unroll
+      for (int st = 0; st < G; ++st) {
+        float4 b4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bp + st * 16 + j * 4));
+        tmem_ld_wait();
+        if (st + 1 < G) tmem_ld_32x16(taddr + (uint32_t)((st + 1) * 16), v[(st + 1) & 1]);
+        const uint32_t* vv = v[st & 1];
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[4 * j] = __uint_as_float(vv[4 * j]) + b4[j].x;         f[4 * j + 1] = __uint_as_float(vv[4 * j + 1]) + b4[j].y;
+          f[4 * j + 2] = __uint_as_float(vv[4 * j + 2]) + b4[j].z; f[4 * j + 3] = __uint_as_float(vv[4 * j + 3]) + b4[j].w;
+        }
+        // two GroupNorm groups per warp; 4 independent partial accumulators per statistic
+        const int g = (st * 16 >= COLS / 2) ? 1 : 0;
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          p0 += f[j]; p1 += f[j + 1]; p2 += f[j + 2]; p3 += f[j + 3];
+          r0 = fmaf(f[j], f[j], r0); r1 = fmaf(f[j + 1], f[j + 1], r1);
+          r2 = fmaf(f[j + 2], f[j + 2], r2); r3 = fmaf(f[j + 3], f[j + 3], r3);
+        }
+        sg[g] += (p0 + p1) + (p2 + p3);
+        ssg[g] += (r0 + r1) + (r2 + r3);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[st][j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed_remote(tempty_bar(acc), 0);  // orders TMEM reads only, not the stores
+      if (do_store) {
+        // G x G transpose of 32-byte chunks inside each group of G lanes (G consecutive pixels of one image row): lane j
+        // of a group ends up with chunk j of all G pixels, so one store instruction writes G*32 contiguous bytes per
+        // group -- 128-byte lines for Cout = 128 -- instead of 32 isolated sectors: 4x (2x) fewer L1 wavefronts.
+        // Measured before the change: the stores cost 19 % of the launch through LSU contention with the loaders.
+#pragma unroll
+        for (int mbit = 1; mbit < G; mbit <<= 1) {
+          const bool up = (lane & mbit) != 0;
+#pragma unroll
+          for (int c = 0; c < G; ++c) {
+            if (c & mbit) continue;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t send = up ? pk[c][j] : pk[c | mbit][j];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, mbit);
+              if (up) pk[c][j] = recv; else pk[c | mbit][j] = recv;
+            }
+          }
+        }
+        // pk[i] now holds chunk (lane % G) of pixel (lane - lane % G + i)
+        __nv_bfloat16* obase = orow - (size_t)(lane & (G - 1)) * COUT + (lane & (G - 1)) * 16;
+#pragma unroll
+        for (int i = 0; i < G; ++i) st_global_v8(obase + (size_t)i * COUT, pk[i]);
+      }
+      if (e == 0 && lane == 0) SDD_TRACE4(3, it, 1);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      // warp reduction of (sg0, ssg0, sg1, ssg1) in 6 shuffles: halve the value count while halving the lanes.
+      // lane bit 4 selects the group it keeps, bit 3 the statistic; bits 2..0 are summed out.
+      {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        const float keep_s = up16 ? sg[1] : sg[0], keep_ss = up16 ? ssg[1] : ssg[0];
+        const float send_s = up16 ? sg[0] : sg[1], send_ss = up16 ? ssg[0] : ssg[1];
+        const float s2 = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 16);
+        const float ss2 = keep_ss + __shfl_xor_sync(0xffffffffu, send_ss, 16);
+        float val = (up8 ? ss2 : s2) + __shfl_xor_sync(0xffffffffu, up8 ? s2 : ss2, 8);
+        val += __shfl_xor_sync(0xffffffffu, val, 4);
+        val += __shfl_xor_sync(0xffffffffu, val, 2);
+        val += __shfl_xor_sync(0xffffffffu, val, 1);
+        if ((lane & 7) == 0 && valid && !(a.dbg & 8) && a.out_sums)
+          gn_red_add(a.out_sums + ((size_t)n * 4 + hcol * 2 + (lane >> 4)) * 2 + ((lane >> 3) & 1), val);
+      }
+      if (e == 0 && lane == 0) SDD_TRACE4(3, it, 2);
+    }
+  } else {
+    // ===================== loaders: global -> registers -> GroupNorm+SiLU -> swizzled shared memory ==========
+    // TWO groups of four warps work on ALTERNATING items (group g: items g, g+2, ...).  Measured on the single-group
+    // version: ~2500 cycles of serial control code per item plus up to ~4000 cycles of exposed load latency, against
+    // 2304 cycles of MMA -- so one group's chain is allowed to take two item times while the other group feeds the
+    // tensor core.  A thread owns twelve 16-byte vectors of its item (halo rows col + 16 i) in ONE register buffer:
+    // the loads of the group's next item are issued right after its arrive, i.e. after the MEMBAR inside
+    // fence.proxy.async (which would otherwise wait for them), and have the other group's whole item to land.
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    constexpr int kVecs = 12;
+    const int tt = threadIdx.x - 384;        // 0..255
+    const int grp = tt >> 7, tg = tt & 127;  // group, thread in group
+    const int piece = tg & 7, col = tg >> 3; // col 0..15
+    __shared__ __align__(16) float s_ga[2][128], s_gb[2][128];
+    const bool fuse = (a.in_sums != nullptr) || (a.in_meanrstd != nullptr);
+    const uint8_t* in_bytes = reinterpret_cast<const uint8_t*>(a.in);
+    const int tiles_h = a.H / kTileH;
+    // vector i <-> halo row r = col + 16 i (pixel (r / 10, r % 10) of the 18 x 10 box); r & 7 == col & 7 for every i
+    const int nvec = (col < kHaloRowsV2 - 16 * (kVecs - 1)) ? kVecs : kVecs - 1;  // rows >= 180 do not exist
+    uint32_t goff[kVecs];  // byte offset of the vector from the box origin (chunk 0)
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const int r = col + 16 * i, hr = r / kHaloW, wr = r - hr * kHaloW;
+      goff[i] = (uint32_t)((hr * a.W + wr) * a.Cin * 2 + piece * 16);
+    }
+    const uint32_t soff = (uint32_t)col * 128u + (uint32_t)((piece ^ (col & 7)) << 4);  // + i * 2048
+
+    // item j of this CTA = (pair iteration j / kchunks, chunk j % kchunks); this group's items are grp, grp + 2, ...
+    // so with two chunks a group always has the same chunk, with one chunk it takes every other tile
+    const int my_items = ((a.num_pairs - pair0 + pair_stride - 1) / pair_stride) * kchunks;
+    const int kc = (kchunks == 2) ? grp : 0;
+    const int gstep_pairs = (2 / kchunks) * pair_stride;  // pairs between two items of a group
+    struct Cursor { int n, th, tw; };
+    const int step = 2 * gstep_pairs;                     // tiles
+    const int d_n = step / a.tiles_per_sample, d_r = step - d_n * a.tiles_per_sample;
+    const int d_th = d_r / a.tiles_w, d_tw = d_r - d_th * a.tiles_w;
+    auto cursor_of = [&](int pair) {
+      bool valid;
+      const int tile = tile_of(pair, valid);
+      Cursor c;
+      c.n = tile / a.tiles_per_sample;
+      const int tr = tile - c.n * a.tiles_per_sample;
+      c.th = tr / a.tiles_w; c.tw = tr - c.th * a.tiles_w;
+      return c;
+    };
+    auto cursor_next = [&](Cursor c, int next_pair) {
+      if (2 * next_pair + (int)rank >= a.num_tiles) {   // dummy tile of an odd count, or past the end: any valid tile
+        return c;
+      }
+      c.tw += d_tw; c.th += d_th; c.n += d_n;
+      if (c.tw >= a.tiles_w) { c.tw -= a.tiles_w; ++c.th; }
+      if (c.th >= tiles_h) { c.th -= tiles_h; ++c.n; }
+      return c;
+    };
+    // pointer to the box origin of a tile (chunk kc) and the mask of this thread's in-image vectors
+    auto tile_src = [&](const Cursor& c, const uint8_t*& base, uint32_t& okmask) {
+      const int h0 = c.th * kTileH - 1, w0 = c.tw * kTileW - 1;
+      base = in_bytes + (((long long)c.n * a.H + h0) * a.W + w0) * (long long)(a.Cin * 2) + kc * 128;
+      const uint32_t all = (1u << nvec) - 1u;
+      const bool interior = c.th > 0 && c.th < tiles_h - 1 && c.tw > 0 && c.tw < a.tiles_w - 1;
+      if (interior) { okmask = all; return; }
+      okmask = 0;
+#pragma unroll
+      for (int i = 0; i < kVecs; ++i) {
+        const int r = col + 16 * i, hr = r / kHaloW, wr = r - hr * kHaloW;
+        if (i < nvec && (h0 + hr) >= 0 && (h0 + hr) < a.H && (w0 + wr) >= 0 && (w0 + wr) < a.W) okmask |= 1u << i;
+      }
+    };
+    uint4 r[kVecs];
+    auto issue_loads = [&](const uint8_t* base, uint32_t okmask) {
+      if (okmask == (1u << kVecs) - 1u) {
+#pragma unroll
+        for (int i = 0; i < kVecs; ++i) r[i] = ldg_nc_v4(base + goff[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < kVecs; ++i)
+          r[i] = ((okmask >> i) & 1u) ? ldg_nc_v4(base + goff[i]) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
+
+    int item = grp;                                      // this group's current item
+    int pair = pair0 + (item / kchunks) * pair_stride;
+    Cursor c = cursor_of(pair < a.num_pairs ? pair : pair0);
+    const uint8_t* base = nullptr; uint32_t ok_c = 0;
+    if (item < my_items) { tile_src(c, base, ok_c); issue_loads(base, ok_c); }
+    int stage = grp % a.stages; uint32_t phase = (uint32_t)((grp / a.stages) & 1);
+    int cur_n = -1;
+    uint64_t ga2[4], gb2[4];
+    mbar_wait(w_bar, 0);  // this CTA's weights have landed (the MMA warp relies on the loaders for this)
+
+    auto xform_pair = [&](uint32_t u, int j) -> uint32_t {
+      const uint64_t h = fma_f32x2(pack_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)), ga2[j], gb2[j]);
+      float hl, hh;
+      unpack_f32x2(h, hl, hh);
+      const uint64_t q2 = fma_f32x2(h, pack_f32x2(tanh_approx(hl), tanh_approx(hh)), h);
+      float rl, rh;
+      unpack_f32x2(q2, rl, rh);
+      return pack_bf16x2(rl, rh);
+    };
+
+    while (item < my_items) {
+      // ---- GroupNorm scale / shift: this group's chunk is fixed, so the registers only change with the sample
+      if (fuse && c.n != cur_n) {
+        named_bar_sync(2 + grp, 128);  // previous readers of this group's s_ga/s_gb are done
+        if (tg < 64) {
+          const int ch = kc * 64 + tg;
+          const int g = ch / (a.Cin / 4);
+          float mean, rstd;
+          if (a.in_sums)
+            gn_mean_rstd_from_sums(a.in_sums + ((size_t)c.n * 4 + g) * 2, (double)a.H * (double)a.W * (double)(a.Cin / 4),
+                                   kGnEps, mean, rstd);
+          else { mean = a.in_meanrstd[(c.n * 4 + g) * 2]; rstd = a.in_meanrstd[(c.n * 4 + g) * 2 + 1]; }
+          const float sc = rstd * a.in_gamma[ch];
+          s_ga[grp][tg] = 0.5f * sc;                       // pre-halved: silu(v) = h + h tanh(h), h = v / 2
+          s_gb[grp][tg] = 0.5f * (a.in_beta[ch] - mean * sc);
+        }
+        named_bar_sync(2 + grp, 128);
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          const float4 x = *reinterpret_cast<const float4*>(&s_ga[grp][piece * 8 + 2 * j]);
+          const float4 y = *reinterpret_cast<const float4*>(&s_gb[grp][piece * 8 + 2 * j]);
+          ga2[j] = pack_f32x2(x.x, x.y); ga2[j + 1] = pack_f32x2(x.z, x.w);
+          gb2[j] = pack_f32x2(y.x, y.y); gb2[j + 1] = pack_f32x2(y.z, y.w);
+        }
+        cur_n = c.n;
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      if (tg == 0) SDD_TRACE4(2, item / kchunks, grp);
+      const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes + soff;
+      if (fuse && ok_c == (1u << kVecs) - 1u && !(a.dbg & 64)) {
+        // interior tile, full thread: straight-line code, the twelve vectors' chains interleave freely
+#pragma unroll
+        for (int i = 0; i < kVecs; ++i)
+          sts_v4(dst + (uint32_t)i * 2048u,
+                 make_uint4(xform_pair(r[i].x, 0), xform_pair(r[i].y, 1), xform_pair(r[i].z, 2), xform_pair(r[i].w, 3)));
+      } else {
+#pragma unroll
+        for (int i = 0; i < kVecs; ++i) {
+          uint4 v = r[i];
+          if (fuse && ((ok_c >> i) & 1u) && !(a.dbg & 64))
+            v = make_uint4(xform_pair(v.x, 0), xform_pair(v.y, 1), xform_pair(v.z, 2), xform_pair(v.w, 3));
+          if (i < nvec) sts_v4(dst + (uint32_t)i * 2048u, v);  // padding pixels hold the zeros they were "loaded" as
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      // relaxed: the proxy fence has completed this thread's shared-memory writes and made them visible to the async
+      // proxy of THIS CTA's tensor core, the only reader
+      if (lane == 0) mbar_arrive_relaxed_remote(ready_bar(stage), 0);
+      if (tg == 0) SDD_TRACE4(2, item / kchunks, 2 + grp);
+      // ---- this group's next item: coordinates, then its loads (nothing of this thread is in flight at a MEMBAR)
+      item += 2;
+      stage += 2; if (stage >= a.stages) { stage -= a.stages; phase ^= 1u; }
+      if (a.stages == 1) phase ^= 1u;  // two wraps per step when there is a single stage
+      pair += gstep_pairs;
+      if (item < my_items) {
+        c = cursor_next(c, pair);
+        tile_src(c, base, ok_c);
+        issue_loads(base, ok_c);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if constexpr (kTrace) {
+    if (a.trace && blockIdx.x < 2)
+      for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) {
+        const int role = i / (kTraceIters * 4), rem = i % (kTraceIters * 4);
+        a.trace[(((size_t)blockIdx.x * 6 + role) * 64 + rem / 4) * 4 + (rem & 3)] = (&s_trace[0][0][0])[i];
+      }
+  }
+  cluster_sync_all();  // the peer may still be reading our smem / arriving on our barriers
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace sdd

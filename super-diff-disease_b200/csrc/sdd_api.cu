@@ -10,6 +10,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "conv_tc3.cuh"
+#include "conv_tc4.cuh"
 #include "unet_kernels.cuh"
 #include "update.cuh"
 
@@ -259,7 +260,26 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   a.trace = trace;
   const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages);
   const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
-  if (trace) {  // timing-experiment instantiation with clock64 stamps
+  static const bool v4 = getenv("SDD_CONV_V3") == nullptr;  // product: two loader groups on alternating items (v4); SDD_CONV_V3=1 selects the single-group loader for A/B
+  if (v4) {
+    static bool attr4 = false;
+    if (!attr4) {
+      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
+      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
+      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
+      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
+      attr4 = true;
+    }
+    if (trace) {
+      if (Cout == 64) conv3x3_tc4_kernel<64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+      else conv3x3_tc4_kernel<128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+    } else if (Cout == 64) conv3x3_tc4_kernel<64><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+    else conv3x3_tc4_kernel<128><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+  } else if (trace) {  // timing-experiment instantiation with clock64 stamps
     if (Cout == 64) conv3x3_tc3_kernel<64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
     else conv3x3_tc3_kernel<128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
   } else if (Cout == 64)
