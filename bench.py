@@ -27,6 +27,18 @@ CONV_MAC_PER_PIXEL = 664713          # all 10 convs of one UNet for
 MAC_128x128 = 147456                 # one 128->128 3x3 conv, per pixel
 
 
+def ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two roofline kernels from the committed
+    `ncu --set full` captures (profiles/r1_v4_ncu.md); taken at exactly the launch shapes timed below."""
+    p = os.path.join(ROOT, "profiles", "r1_v4_traffic.json")
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p))
+    conv = next((v for k, v in d.items() if k.startswith("conv3x3")), None)
+    upd = next((v for k, v in d.items() if k.startswith("superpose_update")), None)
+    return (conv["traffic_MB"] * 1e6 if conv else None), (upd["traffic_MB"] * 1e6 if upd else None)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -292,6 +304,9 @@ def main():
         hbm, tf_burst, tf_sust, src = peaks()
         chunk = int(os.environ.get("SDD_CHUNK", "0")) or max(1, min(B, (1536 << 20) // (R * R * 128 * 2)))
         conv_tf, conv_ms = conv_roofline(S, dev, R, chunk)
+        conv_traffic, upd_traffic = ncu_traffic()
+        if not (B == 64 and R == 256 and chunk == 64):
+            conv_traffic = upd_traffic = None  # the captures were taken at the default launch shapes only
         upd_gbs, upd_ms = update_roofline(S, dev, B, D)
         step_flops = 2.0 * CONV_MAC_PER_PIXEL * D * M * T  # per sample
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -300,13 +315,13 @@ def main():
                 "config": workload_config(args, world), "clocks": clk,
                 "gpu_launches": int(launches) * args.steps * world,
                 "whole_path_tensor_frac_of_sustained": value / world * step_flops / (tf_sust * 1e12),
-                "roofline": {"kernel": "conv3x3_tc3_kernel<128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)", "bound": "tensor",
+                "roofline": {"kernel": "conv3x3_tc4_kernel<128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)", "bound": "tensor",
                              "achieved": conv_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_tf / tf_burst,
-                             "traffic": None, "peak_source": f"{src} bf16 burst", "launch_ms": conv_ms,
+                             "traffic": conv_traffic, "algorithmic_bytes": 2.0 * chunk * R * R * 128 * 2, "peak_source": f"{src} bf16 burst", "launch_ms": conv_ms,
                              "how": f"kernel alone at the sampler's launch shape ({chunk}x{R}x{R}x128), CUDA events "
                                     "around each launch on the launching stream, L2 flushed between launches"},
                 "roofline_update": {"kernel": "superpose_update_kernel<2>", "bound": "hbm", "achieved": upd_gbs,
-                                    "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm, "traffic": None,
+                                    "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm, "traffic": upd_traffic,
                                     "bytes_per_element": 16, "launch_ms": upd_ms, "peak_source": f"{src} copy"},
                 }
         if e2e:
