@@ -135,8 +135,8 @@ int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, cons
 /* Kernel-only timing for the roofline numbers (bench.py): `iters` launches, each bracketed by CUDA events
  * on the launching stream; `flush` (may be NULL) is rewritten before every launch to evict L2.
  * *ms_host receives the mean kernel duration in milliseconds. */
-/* impl: 0 = v1 kernel (streamed weights, pre-activated input), 1 = product kernel without the fused GroupNorm,
- * 2 = product kernel with the fused GroupNorm+SiLU (identity statistics). */
+/* impl: 0 = bring-up kernel (cta_group::1, streamed weights, pre-activated input), 1 = product kernel without the fused
+ * GroupNorm, 2 = product kernel with the fused GroupNorm+SiLU (identity statistics). */
 int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W,
                         int Cin, int Cout, int impl, int iters, void* flush, size_t flush_bytes, float* ms_host,
                         void* stream);

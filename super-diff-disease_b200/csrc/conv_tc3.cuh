@@ -25,7 +25,7 @@
 #pragma once
 #include "common.cuh"
 #include "conv_tc.cuh"
-#include "conv_tc2.cuh"
+#include "cluster.cuh"
 
 namespace sdd {
 

@@ -8,7 +8,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
-#include "conv_tc2.cuh"
+#include "cluster.cuh"
 #include "conv_tc3.cuh"
 #include "conv_tc4.cuh"
 #include "unet_kernels.cuh"
@@ -172,49 +172,6 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, __nv_b
     conv3x3_tc_kernel<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(tmA, tmB, a);
   else
     conv3x3_tc_kernel<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(tmA, tmB, a);
-  SDD_LAUNCH_CHECK();
-  return SDD_OK;
-}
-
-struct GnInput {  // GroupNorm(4, Cin) + SiLU applied to the conv's input inside the kernel (nullptr: none)
-  const float* meanrstd;
-  const float* gamma;
-  const float* beta;
-};
-
-static int launch_conv_tc2(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2, __nv_bfloat16* out, BiasRef bias,
-                           GnInput in, GnScratch gn, int B, int H, int W, int Cin, int Cout, cudaStream_t st,
-                           int dbg = 0, long long* trace = nullptr) {
-  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
-  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
-  static bool attr = false;
-  if (!attr) {
-    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_tc2_smem_bytes(64, 128, conv_tc2_stages(64, 128))));
-    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_tc2_smem_bytes(128, 128, conv_tc2_stages(128, 128))));
-    attr = true;
-  }
-  ConvTc2Args a;
-  a.in = nullptr; a.out = out; a.bias = bias;
-  a.in_meanrstd = in.meanrstd; a.in_gamma = in.gamma; a.in_beta = in.beta;
-  a.partials = gn.partials; a.counters = gn.counters; a.meanrstd = gn.meanrstd;
-  a.B = B; a.H = H; a.W = W; a.Cin = Cin;
-  a.tiles_w = W / kTileW;
-  a.tiles_per_sample = (H / kTileH) * a.tiles_w;
-  a.num_tiles = B * a.tiles_per_sample;
-  a.num_pairs = (a.num_tiles + 1) / 2;
-  a.stages = conv_tc2_stages(Cout, Cin);
-  a.dbg = dbg;
-  a.trace = trace;
-  static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 8;
-  a.prefetch = prefetch;
-  const int smem = conv_tc2_smem_bytes(Cout, Cin, a.stages);
-  const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
-  if (Cout == 64)
-    conv3x3_tc2_kernel<64><<<grid, kC2Threads, smem, st>>>(tmA_halo, tmB2, a);
-  else
-    conv3x3_tc2_kernel<128><<<grid, kC2Threads, smem, st>>>(tmA_halo, tmB2, a);
   SDD_LAUNCH_CHECK();
   return SDD_OK;
 }
@@ -940,7 +897,7 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
     rc = make_act_map(&tmA, act, B, H, W, Cin, (impl & 15) != 0);
   }
   if (rc == SDD_OK) rc = (impl & 15) == 0 ? make_wt_map(&tmB, wt, Cout, Cin) : make_wt_map2(&tmB, wt, Cout, Cin);
-  GnInput gi{nullptr, nullptr, nullptr};
+  GnInput3 gi{nullptr, nullptr, nullptr, nullptr};
   const int dbg = impl >> 4;
   impl &= 15;
   long long* trace = nullptr;
@@ -948,7 +905,7 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
   const char* trace_path = getenv("SDD_CONV_TRACE");
   if (trace_path && impl != 0) { cudaMalloc(&trace, 2 * 6 * 64 * 4 * sizeof(long long)); }
   if (rc == SDD_OK && cudaMalloc(&osums, (size_t)B * 8 * sizeof(long long)) != cudaSuccess) rc = SDD_ENOMEM;
-  if (impl == 2 || impl == 4) gi = GnInput{gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128};
+  if (impl == 2) gi = GnInput3{nullptr, gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128};
   if (rc == SDD_OK && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) rc = SDD_ECUDA;
   BiasRef br{bias, nullptr, 0, 0};
   double total = 0.0;
@@ -959,12 +916,9 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
     cudaEventRecord(e0, st);
     if (impl == 0)
       rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
-    else if (impl <= 2)
-      rc = launch_conv_tc3(tmA, tmB, (const __nv_bfloat16*)act, (__nv_bfloat16*)out, br,
-                           GnInput3{nullptr, gi.meanrstd, gi.gamma, gi.beta}, osums, B, H, W, Cin, Cout, st, dbg, trace);
     else
-      rc = launch_conv_tc2(tmA, tmB, (__nv_bfloat16*)out, br, gi, GnScratch{partials, counters, mr}, B,
-                           H, W, Cin, Cout, st, dbg, trace);
+      rc = launch_conv_tc3(tmA, tmB, (const __nv_bfloat16*)act, (__nv_bfloat16*)out, br, gi, osums, B, H, W, Cin, Cout,
+                           st, dbg, trace);
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("conv profile: kernel failed"); rc = SDD_ECUDA; break; }
     float ms = 0.f;

@@ -1,5 +1,5 @@
 """Timing experiments on the product conv at large chunks: dbg variants + per-role clock64 traces (CTA pair 0).
-impl codes of sdd_conv3x3_profile: 1/2 = v3 plain/fused, 3/4 = v2 plain/fused, 0 = v1; dbg bits << 4."""
+impl codes of sdd_conv3x3_profile: 1/2 = product kernel plain/fused (SDD_CONV_V3=1 selects the single-group loader), 0 = bring-up kernel; dbg bits << 4."""
 import sys, os, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
@@ -15,9 +15,7 @@ for cin, cout in [(64, 64), (128, 128), (64, 128), (128, 64)]:
         tf, ms = bench.conv_roofline(S, dev, 256, chunk, iters=4, cin=cin, cout=cout, impl=2 + 16 * dbg, flush_l2=True)
         line += f"{nm} {ms*1000:.0f}" + (f" ({tf/1626.5:.3f})" if dbg == 0 else "") + " | "
     tf, ms = bench.conv_roofline(S, dev, 256, chunk, iters=4, cin=cin, cout=cout, impl=1, flush_l2=True)
-    line += f"plain {ms*1000:.0f} | "
-    tf, ms = bench.conv_roofline(S, dev, 256, chunk, iters=4, cin=cin, cout=cout, impl=4, flush_l2=True)
-    line += f"v2 fused {ms*1000:.0f}"
+    line += f"plain {ms*1000:.0f}"
     print(line, flush=True)
 if os.environ.get("TRACE", "1") == "1":
     roles = {0: 'prod', 1: 'mma', 2: 'load', 3: 'epi', 4: 'pub'}
