@@ -42,6 +42,7 @@ SYMBOLS = {
     "sdd_conv3x3_fused_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "sdd_gn_silu_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdd_conv3x3_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, ctypes.POINTER(_f), _vp]),
+    "sdd_superpose_update_profile_rotating": (_i, [_i, _i, _i, _i, _i, _sz, ctypes.POINTER(_f), _vp]),
     "sdd_superpose_update_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, ctypes.POINTER(_f), _vp]),
 }
 

@@ -385,6 +385,12 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         c = cursor_next(c, pair);
         tile_src(c, base, ok_c);
         issue_loads(base, ok_c);
+        // pull the box of this group's item AFTER that one into L2 (TMA prefetch: no smem, no barrier).  With a single
+        // register buffer the loads above are on the group's chain; this turns their DRAM latency into an L2 hit.
+        if (a.prefetch > 0 && tg == 0 && item + 2 < my_items) {
+          const Cursor cp = cursor_next(c, pair + gstep_pairs);
+          tma_prefetch_l2_4d(&tmA, kc * 64, cp.tw * kTileW - 1, cp.th * kTileH - 1, cp.n);
+        }
       }
     }
   }

@@ -211,7 +211,7 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   a.num_tiles = B * a.tiles_per_sample;
   a.num_pairs = (a.num_tiles + 1) / 2;
   a.stages = conv_tc3_stages(Cout, Cin);
-  static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 0;  // measured: no effect (0, 3, 6, 12 within 1 %)
+  static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 1;  // v4: TMA L2 prefetch of a loader group's item after next; measured +3..6 % (v3's paced prefetch warp: no effect)
   a.prefetch = prefetch;
   a.dbg = dbg;
   a.trace = trace;
@@ -551,20 +551,34 @@ size_t sdd_superpose_update_workspace(int B, int D, int M) { return update_works
 }  // extern "C"
 
 namespace sdd {
-int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st, cudaEvent_t after_update = nullptr) {
+template <int STEPS>
+static void launch_update_kernel(const UpdateArgs& a, dim3 grid, cudaStream_t st) {
+  switch (a.M) {
+    case 1: superpose_update_kernel<1, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
+    case 2: superpose_update_kernel<2, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
+    case 3: superpose_update_kernel<3, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
+    default: superpose_update_kernel<4, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
+  }
+}
+
+int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st, cudaEvent_t after_update = nullptr,
+                            bool finalize = true) {
   SDD_CHECK(a.M >= 1 && a.M <= kMaxModels, "1 <= M <= 4");
   SDD_CHECK(a.D % 4 == 0 && a.D > 0 && a.B > 0, "D must be a positive multiple of 4");
-  a.nblk = update_blocks_per_sample(a.D);
   a.partials = reinterpret_cast<float*>(workspace);
-  dim3 grid(a.nblk, a.B);
-  switch (a.M) {
-    case 1: superpose_update_kernel<1><<<grid, kUpdThreads, 0, st>>>(a); break;
-    case 2: superpose_update_kernel<2><<<grid, kUpdThreads, 0, st>>>(a); break;
-    case 3: superpose_update_kernel<3><<<grid, kUpdThreads, 0, st>>>(a); break;
-    default: superpose_update_kernel<4><<<grid, kUpdThreads, 0, st>>>(a); break;
+  {
+    // sub-steps per segment: a build-time constant (or an experiment override), never a function of B
+    static const int steps = getenv("SDD_UPD_STEPS") ? atoi(getenv("SDD_UPD_STEPS")) : kSegSteps;
+    SDD_CHECK(steps == 1 || steps == 2 || steps == 4, "SDD_UPD_STEPS must be 1, 2 or 4");
+    a.nblk = update_blocks_per_sample(a.D, steps);
+    dim3 grid(a.nblk, a.B);
+    if (steps == 1) launch_update_kernel<1>(a, grid, st);
+    else if (steps == 2) launch_update_kernel<2>(a, grid, st);
+    else launch_update_kernel<4>(a, grid, st);
   }
   SDD_LAUNCH_CHECK();
   if (after_update) cudaEventRecord(after_update, st);  // roofline timing of the HBM pass alone
+  if (!finalize) return SDD_OK;
   switch (a.M) {
     case 1: superpose_finalize_kernel<1><<<a.B, 256, 0, st>>>(a); break;
     case 2: superpose_finalize_kernel<2><<<a.B, 256, 0, st>>>(a); break;
@@ -981,6 +995,59 @@ int sdd_superpose_update_profile(float* x, const float* eps, const float* noise,
   cudaStreamSynchronize(st);
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws);
   if (rc == SDD_OK) *ms_host = (float)(total / iters);
+  return rc;
+}
+
+int sdd_superpose_update_profile_rotating(int B, int D, int M, int use_noise, int iters, size_t rot_bytes,
+                                          float* ms_host, void* stream) {
+  SDD_CHECK(ms_host && iters > 0 && B > 0 && D > 0 && D % 4 == 0 && M >= 1 && M <= kMaxModels, "bad argument");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t BD = (size_t)B * D;
+  const size_t set_floats = BD * (size_t)(1 + M + (use_noise ? 1 : 0));
+  int nsets = (int)((rot_bytes + set_floats * 4 - 1) / (set_floats * 4));
+  nsets = nsets < 2 ? 2 : (nsets > 512 ? 512 : nsets);
+  float* pool = nullptr; float* logq = nullptr; void* ws = nullptr;
+  const size_t wb = update_workspace_bytes(B, D, M);
+  if (cudaMalloc(&pool, set_floats * 4 * nsets) != cudaSuccess || cudaMalloc(&logq, (size_t)B * M * 4) != cudaSuccess ||
+      cudaMalloc(&ws, wb) != cudaSuccess) {
+    cudaFree(pool); cudaFree(logq); cudaFree(ws);
+    set_error("cudaMalloc failed"); return SDD_ENOMEM;
+  }
+  cudaMemsetAsync(ws, 0, wb, st);
+  cudaMemsetAsync(logq, 0, (size_t)B * M * 4, st);
+  {  // standard normals everywhere (values only matter for not being denormal / NaN)
+    const size_t total = set_floats * nsets;
+    const size_t nq = total / 4;
+    philox_normal_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(pool, 1, (int)(nq * 4 > 0x7ffffff0 ? 0x7ffffff0 : nq * 4), 99, 0, 0);
+    if (nq * 4 > 0x7ffffff0) cudaMemsetAsync(pool + 0x7ffffff0, 0, (total - 0x7ffffff0) * 4, st);
+  }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  UpdateArgs a;
+  memset(&a, 0, sizeof(a));
+  a.logq = logq; a.logq_out = logq;
+  a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f; a.temperature = 1.0f; a.seed = 1234;
+  step_scalars_fill(a.sc);
+  a.B = B; a.D = D; a.M = M;
+  int rc = SDD_OK;
+  auto run = [&](int n, int first) {
+    for (int i = 0; rc == SDD_OK && i < n; ++i) {
+      float* set = pool + (size_t)((first + i) % nsets) * set_floats;
+      a.x_in = set; a.x_out = set; a.eps = set + BD; a.noise = use_noise ? set + BD * (1 + M) : nullptr;
+      a.sc.draw_index = use_noise ? 0 : first + i;
+      rc = launch_superpose_update(a, ws, st, nullptr, /*finalize=*/false);
+    }
+  };
+  run(nsets, 0);  // warm-up: code, constants, TLBs; every set touched once
+  cudaEventRecord(e0, st);
+  run(iters, nsets);
+  cudaEventRecord(e1, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("update profile: kernel failed"); rc = SDD_ECUDA; }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws); cudaFree(logq); cudaFree(pool);
+  if (rc == SDD_OK) *ms_host = ms / iters;
   return rc;
 }
 

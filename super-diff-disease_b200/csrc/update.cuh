@@ -96,12 +96,22 @@ __device__ __forceinline__ float ddpm_x_update(float x, float eb, float z, float
   return __fadd_rn(__fmul_rn(c1, __fsub_rn(x, __fmul_rn(c2, eb))), __fmul_rn(c3, z));
 }
 
-// One CTA = one segment of one sample: kSegVecPerThread float4 per thread and array (2048 elements), all loads
-// issued before any use.  Segment boundaries and every reduction order are fixed functions of D alone, so
-// logq / statistics are bit-identical for any batch sharding.  No atomics, no fences: per-segment partial sums go
-// to a small buffer and superpose_finalize_kernel (one CTA per sample) reduces them in a fixed order.
+// One CTA = one segment of one sample = STEPS sub-steps of kSegVecPerThread float4 per thread and array (STEPS = 2:
+// 4096 elements).  Per sub-step all loads are issued before any use; the per-thread sums are carried across the
+// sub-steps, so the ~320 instructions of per-thread prologue + reduction are paid once per 32 elements (they were 43 %
+// of all issued instructions at 8 elements per thread).  The first sub-step's x / eps loads are issued BEFORE the
+// dependent chain step counter -> schedule row -> log q -> kappa is walked (two L2 round trips).  Segment boundaries
+// and every reduction order are fixed functions of D alone, so logq / statistics are bit-identical for any batch
+// sharding.  No atomics, no fences: per-segment partial sums go to a small buffer and superpose_finalize_kernel (one
+// CTA per sample) reduces them in a fixed order.
+// Measured (B200, rotating buffers, D = 65536, M = 2; us per launch Philox / noise tensor): STEPS 1: B=64 18.8 / 16.5,
+// B=256 59.5 / 51.9; STEPS 2: 18.4 / 17.4, 53.0 / 53.3; STEPS 4: 18.5 / 17.5, 52.4 / 53.6 (B=16: 8.2, 8.2, 10.3).
+// Tried and rejected: persistent CTAs (2-3 per SM) fed by a cp.async.bulk + mbarrier shared-memory ring -- 22.3 / 19.1
+// at B=64 and 65.4 / 58.0 at B=256: the Philox variant is issue-bound and wants the 32 warps per SM this version has.
 constexpr int kSegVecPerThread = 2;
-constexpr int kSegVec = kUpdThreads * kSegVecPerThread;  // float4 per segment
+constexpr int kSegSteps = 2;
+constexpr int kSubVec = kUpdThreads * kSegVecPerThread;  // float4 per sub-step
+constexpr int kSegVec = kSubVec * kSegSteps;             // float4 per segment
 
 template <int M>
 __device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, int b, float (&kap)[M]) {
@@ -120,69 +130,83 @@ __device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, int b, float 
   for (int m = 0; m < M; ++m) kap[m] = __fdividef(kap[m], den);
 }
 
-template <int M>
-__global__ void __launch_bounds__(kUpdThreads, 5) superpose_update_kernel(const UpdateArgs a) {
+template <int M, int STEPS>
+__global__ void __launch_bounds__(kUpdThreads, STEPS == 1 ? 5 : 4) superpose_update_kernel(const UpdateArgs a) {
   const int b = blockIdx.y, seg = blockIdx.x, tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int nq = a.D >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
+  const float4* e4 = reinterpret_cast<const float4*>(a.eps + (size_t)b * a.D);
+  const size_t e_stride = (size_t)a.B * (size_t)nq;  // float4 between models
+  float4* xo4 = reinterpret_cast<float4*>(a.x_out + (size_t)b * a.D);
+  const int q0 = seg * (kSubVec * STEPS) + tid;
+
+  float4 xv[kSegVecPerThread], ev[M][kSegVecPerThread], zv[kSegVecPerThread];
+  auto load_xe = [&](int s) {
+#pragma unroll
+    for (int i = 0; i < kSegVecPerThread; ++i) {
+      const int q = q0 + s * kSubVec + i * kUpdThreads;
+      const bool ok = q < nq;
+      xv[i] = ok ? __ldcs(x4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int m = 0; m < M; ++m) ev[m][i] = ok ? __ldcs(e4 + m * e_stride + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load_xe(0);  // in flight while the scalar chain below is walked
+
   const int step = a.step_ptr ? *a.step_ptr : 0;
   const StepScalars sc = a.table ? a.table[step] : a.sc;
-  const int nq = a.D >> 2;
   const bool have_noise = sc.draw_index >= 0;
   const bool noise_tensor = a.noise != nullptr && have_noise;
-
-  // ---- all global loads first (up to 4 * (2 + M) float4 in flight per thread)
-  const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
   const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(a.noise + (size_t)sc.draw_index * a.noise_step_stride + (size_t)b * a.D) : nullptr;
-  float4 xv[kSegVecPerThread], ev[M][kSegVecPerThread], zv[kSegVecPerThread];
-#pragma unroll
-  for (int i = 0; i < kSegVecPerThread; ++i) {
-    const int q = seg * kSegVec + i * kUpdThreads + tid;
-    const bool ok = q < nq;
-    xv[i] = ok ? __ldcs(x4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int m = 0; m < M; ++m)
-      ev[m][i] = ok ? __ldcs(reinterpret_cast<const float4*>(a.eps + ((size_t)m * a.B + b) * a.D) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    zv[i] = (ok && noise_tensor) ? __ldcs(n4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
   float kap[M];
   softmax_kappa<M>(a, b, kap);
   const float c1 = sc.c1, c2 = sc.c2, c3 = sc.c3;
-  float4* xo4 = reinterpret_cast<float4*>(a.x_out + (size_t)b * a.D);
   const uint32_t gsample = (uint32_t)(a.sample_offset + b);
 
   float accA[M], accB[M], accC[M], sx = 0.0f, sxx = 0.0f;
 #pragma unroll
   for (int m = 0; m < M; ++m) accA[m] = accB[m] = accC[m] = 0.0f;
+
+#pragma unroll 1
+  for (int s = 0; s < STEPS; ++s) {
+    if (s > 0) load_xe(s);
 #pragma unroll
-  for (int i = 0; i < kSegVecPerThread; ++i) {
-    const int q = seg * kSegVec + i * kUpdThreads + tid;
-    if (q >= nq) continue;
-    float4 z = zv[i];
-    if (have_noise && !noise_tensor) z = philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
-    const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-    const float zs[4] = {z.x, z.y, z.z, z.w};
-    float xn[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float es[M];
-#pragma unroll
-      for (int m = 0; m < M; ++m)
-        es[m] = (j == 0 ? ev[m][i].x : j == 1 ? ev[m][i].y : j == 2 ? ev[m][i].z : ev[m][i].w);
-      float eb = __fmul_rn(kap[0], es[0]);
-#pragma unroll
-      for (int m = 1; m < M; ++m) eb = __fadd_rn(eb, __fmul_rn(kap[m], es[m]));
-      xn[j] = ddpm_x_update(xs[j], eb, zs[j], c1, c2, c3);
-      const float dx = xn[j] - xs[j];
-#pragma unroll
-      for (int m = 0; m < M; ++m) {
-        accA[m] = fmaf(es[m], dx, accA[m]);
-        accB[m] = fmaf(xs[j], es[m], accB[m]);
-        accC[m] = fmaf(es[m], es[m], accC[m]);
-      }
-      sx += xn[j];
-      sxx = fmaf(xn[j], xn[j], sxx);
+    for (int i = 0; i < kSegVecPerThread; ++i) {
+      const int q = q0 + s * kSubVec + i * kUpdThreads;
+      zv[i] = (noise_tensor && q < nq) ? __ldcs(n4 + q) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __stcs(xo4 + q, make_float4(xn[0], xn[1], xn[2], xn[3]));
+#pragma unroll
+    for (int i = 0; i < kSegVecPerThread; ++i) {
+      const int q = q0 + s * kSubVec + i * kUpdThreads;
+      if (q >= nq) continue;
+      float4 z = zv[i];
+      if (have_noise && !noise_tensor) z = philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
+      const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+      const float zs[4] = {z.x, z.y, z.z, z.w};
+      float xn[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float es[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          es[m] = (j == 0 ? ev[m][i].x : j == 1 ? ev[m][i].y : j == 2 ? ev[m][i].z : ev[m][i].w);
+        float eb = __fmul_rn(kap[0], es[0]);
+#pragma unroll
+        for (int m = 1; m < M; ++m) eb = __fadd_rn(eb, __fmul_rn(kap[m], es[m]));
+        xn[j] = ddpm_x_update(xs[j], eb, zs[j], c1, c2, c3);
+        const float dx = xn[j] - xs[j];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          accA[m] = fmaf(es[m], dx, accA[m]);
+          accB[m] = fmaf(xs[j], es[m], accB[m]);
+          accC[m] = fmaf(es[m], es[m], accC[m]);
+        }
+        sx += xn[j];
+        sxx = fmaf(xn[j], xn[j], sxx);
+      }
+      __stcs(xo4 + q, make_float4(xn[0], xn[1], xn[2], xn[3]));
+    }
   }
 
   // segment reduce: shuffle within warps, fixed-order sum across the 8 warps
@@ -259,19 +283,19 @@ __global__ void __launch_bounds__(256) superpose_finalize_kernel(const UpdateArg
   }
 }
 
-// Segments per sample depend on D only (2048 elements each).
-inline int update_blocks_per_sample(int D) {
+// Segments per sample depend on D only (steps * 2048 elements each).
+inline int update_blocks_per_sample(int D, int steps = kSegSteps) {
   int nq = D / 4;
-  int nb = (nq + kSegVec - 1) / kSegVec;
+  int nb = (nq + kSubVec * steps - 1) / (kSubVec * steps);
   return nb < 1 ? 1 : nb;
 }
 
 inline size_t update_workspace_bytes(int B, int D, int /*M*/) {
-  size_t part = (size_t)B * update_blocks_per_sample(D) * kPartialsPerBlock * sizeof(float);
+  size_t part = (size_t)B * update_blocks_per_sample(D, 1) * kPartialsPerBlock * sizeof(float);  // sized for any steps
   return (part + 255) & ~(size_t)255;
 }
 
-int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream, cudaEvent_t after_update);
+int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream, cudaEvent_t after_update, bool finalize);
 
 __global__ void philox_normal_kernel(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw);
 __global__ void copy_f32_kernel(float* dst, const float* src, size_t n);
