@@ -84,6 +84,16 @@ int sdd_superpose_update(const float* x_in, float* x_out, const float* eps, cons
                          uint64_t seed, int64_t sample_offset, int draw_index,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* SuperDiff "AND" step: same contract as sdd_superpose_update, but kappa[b,:] solves
+ *   sum_j kappa_j = 1,   inc_i(kappa) = inc_0(kappa)  for i = 1..M-1
+ * where inc_i is model i's log q increment of THIS step (affine in kappa through x_out - x_in); a singular system
+ * (identical models) gives kappa = 1/M.  Two passes over x / eps / z (Gram reductions, then the update). */
+int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, const float* noise,
+                             const float* logq, float* logq_out, float* kappa_out, float* xstats_out,
+                             int B, int D, int M, float alpha, float alpha_bar, float beta,
+                             uint64_t seed, int64_t sample_offset, int draw_index,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* Philox standard normals, same definition as the in-kernel noise (for x_T and for tests). */
 int sdd_philox_normal(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw_index,
                       void* stream);
@@ -99,6 +109,8 @@ typedef struct {
   float* kappa_traj;        /* device [T,B,M] or NULL */
   float* logq_traj;         /* device [T+1,B,M] or NULL */
   int use_graph;            /* 1: replay one captured step graph T times */
+  int mode;                 /* 0 = SuperDiff OR (kappa = softmax of the running log q); 1 = AND (kappa solved per
+                               sample and step so that all models' log-density increments are equal; 8(f) N3) */
 } sdd_sample_args;
 
 /* models[M] are borrowed and must outlive the sampler.  alphas/alpha_bars/betas are HOST fp32[T]

@@ -17,7 +17,7 @@ def lib_path():
 class SampleArgs(ctypes.Structure):
     _fields_ = [("noise_stack", ctypes.c_void_p), ("seed", ctypes.c_uint64), ("sample_offset", ctypes.c_int64),
                 ("temperature", ctypes.c_float), ("bias", ctypes.c_void_p), ("x_out", ctypes.c_void_p),
-                ("kappa_traj", ctypes.c_void_p), ("logq_traj", ctypes.c_void_p), ("use_graph", ctypes.c_int)]
+                ("kappa_traj", ctypes.c_void_p), ("logq_traj", ctypes.c_void_p), ("use_graph", ctypes.c_int), ("mode", ctypes.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/sdd_b200.h declares.
@@ -33,6 +33,8 @@ SYMBOLS = {
     "sdd_superpose_update_workspace": (_sz, [_i, _i, _i]),
     "sdd_superpose_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _u64,
                                   _i64, _i, _vp, _sz, _vp]),
+    "sdd_superpose_update_and": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _u64, _i64, _i,
+                                      _vp, _sz, _vp]),
     "sdd_philox_normal": (_i, [_vp, _i, _i, _u64, _i64, _i, _vp]),
     "sdd_sampler_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdd_sampler_run": (_i, [_vp, ctypes.POINTER(SampleArgs), _vp]),

@@ -68,6 +68,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--temperature", type=float, default=1.0)
     ap.add_argument("--bias", type=float, nargs="*", default=None, help="per-model logit bias l_i")
+    ap.add_argument("--mode", choices=["or", "and"], default="or", help="SuperDiff OR (softmax of log q) or AND (equal densities)")
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--out", default="superposed_samples.npz")
     ap.add_argument("--grid", default=None, help="also write a PGM contact sheet here")
@@ -90,7 +91,7 @@ def main(argv=None):
     shape = (args.batch, 1, args.resolution, args.resolution)
     bias = torch.tensor(args.bias, dtype=torch.float32) if args.bias else None
     x, kappa, logq = superposed_sample(models, ddpm, shape, dev, seed=args.seed, temperature=args.temperature,
-                                       bias=bias, return_trajectory=True)
+                                       bias=bias, return_trajectory=True, mode=args.mode)
     torch.cuda.synchronize(dev)
     np.savez_compressed(args.out, samples=x.cpu().numpy(), kappa=kappa.cpu().numpy(), logq=logq.cpu().numpy(),
                         checkpoints=np.array(paths), seed=args.seed, steps=args.steps)

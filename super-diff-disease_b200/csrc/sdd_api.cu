@@ -566,12 +566,26 @@ int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st, cuda
   SDD_CHECK(a.M >= 1 && a.M <= kMaxModels, "1 <= M <= 4");
   SDD_CHECK(a.D % 4 == 0 && a.D > 0 && a.B > 0, "D must be a positive multiple of 4");
   a.partials = reinterpret_cast<float*>(workspace);
+  a.and_partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + update_ws_part_bytes(a.B, a.D));
+  a.kappa_in = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + update_ws_part_bytes(a.B, a.D) +
+                                        update_ws_and_bytes(a.B, a.D));
+  SDD_CHECK(a.mode == 0 || a.mode == 1, "mode must be 0 (OR) or 1 (AND)");
   {
     // sub-steps per segment: a build-time constant (or an experiment override), never a function of B
     static const int steps = getenv("SDD_UPD_STEPS") ? atoi(getenv("SDD_UPD_STEPS")) : kSegSteps;
     SDD_CHECK(steps == 1 || steps == 2 || steps == 4, "SDD_UPD_STEPS must be 1, 2 or 4");
     a.nblk = update_blocks_per_sample(a.D, steps);
     dim3 grid(a.nblk, a.B);
+    if (a.mode == 1) {  // AND: Gram pass + per-sample solve write kappa_in before the update pass reads it
+      switch (a.M) {
+        case 1: superpose_and_gram_kernel<1><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<1><<<a.B, 256, 0, st>>>(a); break;
+        case 2: superpose_and_gram_kernel<2><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<2><<<a.B, 256, 0, st>>>(a); break;
+        case 3: superpose_and_gram_kernel<3><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<3><<<a.B, 256, 0, st>>>(a); break;
+        default: superpose_and_gram_kernel<4><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<4><<<a.B, 256, 0, st>>>(a); break;
+      }
+      ++g_launches;
+      SDD_LAUNCH_CHECK();
+    }
     if (steps == 1) launch_update_kernel<1>(a, grid, st);
     else if (steps == 2) launch_update_kernel<2>(a, grid, st);
     else launch_update_kernel<4>(a, grid, st);
@@ -626,6 +640,25 @@ int sdd_superpose_update(const float* x_in, float* x_out, const float* eps, cons
   return launch_superpose_update(a, workspace, (cudaStream_t)stream);
 }
 
+int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, const float* noise, const float* logq,
+                             float* logq_out, float* kappa_out, float* xstats_out, int B, int D, int M, float alpha,
+                             float alpha_bar, float beta, uint64_t seed, int64_t sample_offset, int draw_index,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  SDD_CHECK(x_in && x_out && eps && logq && logq_out && workspace, "null argument");
+  SDD_CHECK(workspace_bytes >= update_workspace_bytes(B, D, M), "workspace too small");
+  SDD_TRY(device_check());
+  UpdateArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_in = x_in; a.x_out = x_out; a.eps = eps; a.noise = noise; a.noise_step_stride = 0;
+  a.logq = logq; a.logq_out = logq_out; a.kappa_out = kappa_out; a.xstats_out = xstats_out;
+  a.sc.alpha = alpha; a.sc.alpha_bar = alpha_bar; a.sc.beta = beta;
+  a.sc.draw_index = noise ? 0 : draw_index;
+  step_scalars_fill(a.sc);
+  a.temperature = 1.0f; a.seed = seed; a.sample_offset = sample_offset;
+  a.B = B; a.D = D; a.M = M; a.mode = 1;
+  return launch_superpose_update(a, workspace, (cudaStream_t)stream);
+}
+
 int sdd_philox_normal(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw_index, void* stream) {
   SDD_CHECK(out && B > 0 && D > 0 && D % 4 == 0, "bad argument");
   SDD_TRY(device_check());
@@ -672,7 +705,7 @@ int enqueue_step(sdd_sampler* s, const sdd_sample_args& ar, cudaStream_t st) {
   a.kappa_traj = ar.kappa_traj; a.logq_traj = ar.logq_traj;
   a.table = s->sched; a.step_ptr = s->step;
   a.temperature = ar.temperature; a.bias = ar.bias; a.seed = ar.seed; a.sample_offset = ar.sample_offset;
-  a.B = s->B; a.D = s->D; a.M = s->M;
+  a.B = s->B; a.D = s->D; a.M = s->M; a.mode = ar.mode;
   SDD_TRY(launch_superpose_update(a, s->upd_ws, st));
   advance_step_kernel<<<1, 1, 0, st>>>(s->step);
   SDD_LAUNCH_CHECK();
@@ -682,7 +715,7 @@ int enqueue_step(sdd_sampler* s, const sdd_sample_args& ar, cudaStream_t st) {
 bool same_args(const sdd_sample_args& a, const sdd_sample_args& b) {
   return a.noise_stack == b.noise_stack && a.seed == b.seed && a.sample_offset == b.sample_offset &&
          a.temperature == b.temperature && a.bias == b.bias && a.kappa_traj == b.kappa_traj &&
-         a.logq_traj == b.logq_traj;
+         a.logq_traj == b.logq_traj && a.mode == b.mode;
 }
 
 }  // namespace

@@ -50,10 +50,15 @@ struct UpdateArgs {
   uint64_t seed;
   int64_t sample_offset;
   float* partials;           // [B][nblk][kPartialsPerBlock]
+  // "AND" mode: kappa solved per sample from a first reduction pass instead of the softmax
+  float* and_partials;       // [B][nblk][kAndPartialsPerBlock] or nullptr
+  float* kappa_in;           // [B][M]: written by superpose_and_solve_kernel, read by the update / finalize kernels
+  int mode;                  // 0 = OR (softmax of log q), 1 = AND (equal log-density increments)
   int B, D, M, nblk;
 };
 
 constexpr int kPartialsPerBlock = 3 * kMaxModels + 2;
+constexpr int kAndPartialsPerBlock = kMaxModels * (kMaxModels + 1) / 2 + 2 * kMaxModels;  // G_ij (i <= j), <eps,x>, <eps,z>
 
 // ------------------------------------------------------------------------------------- Philox
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -115,6 +120,11 @@ constexpr int kSegVec = kSubVec * kSegSteps;             // float4 per segment
 
 template <int M>
 __device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, int b, float (&kap)[M]) {
+  if (a.mode == 1) {  // AND: solved by superpose_and_solve_kernel earlier on the stream
+#pragma unroll
+    for (int m = 0; m < M; ++m) kap[m] = a.kappa_in[b * M + m];
+    return;
+  }
   float lg[M], mx = -INFINITY;
 #pragma unroll
   for (int m = 0; m < M; ++m) {
@@ -230,6 +240,146 @@ __global__ void __launch_bounds__(kUpdThreads, STEPS == 1 ? 5 : 4) superpose_upd
   }
 }
 
+// ------------------------------------------------------------------------------------------------ AND mode
+// First pass of the "AND" step (oracle.and_kappa): per-sample G_ij = <eps_i, eps_j>, a_i = <eps_i, x>, b_i = <eps_i, z>
+// with the update kernel's segmentation and reduction tree (shard-invariant, no atomics).  Reads x, eps, z once more
+// than the OR step: 4 + 4M (+ 4 with a noise tensor) extra bytes per element, L2 hits at the sampler's sizes.
+template <int M>
+__global__ void __launch_bounds__(kUpdThreads, 4) superpose_and_gram_kernel(const UpdateArgs a) {
+  constexpr int NG = M * (M + 1) / 2, NVAL = NG + 2 * M;
+  const int b = blockIdx.y, seg = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int nq = a.D >> 2;
+  const int step = a.step_ptr ? *a.step_ptr : 0;
+  const StepScalars sc = a.table ? a.table[step] : a.sc;
+  const bool have_noise = sc.draw_index >= 0;
+  const bool noise_tensor = a.noise != nullptr && have_noise;
+  const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
+  const float4* e4 = reinterpret_cast<const float4*>(a.eps + (size_t)b * a.D);
+  const size_t e_stride = (size_t)a.B * (size_t)nq;
+  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(a.noise + (size_t)sc.draw_index * a.noise_step_stride + (size_t)b * a.D) : nullptr;
+  const uint32_t gsample = (uint32_t)(a.sample_offset + b);
+  const int per_seg = nq / a.nblk + ((nq % a.nblk) ? 1 : 0);  // == kSubVec * steps for full segments
+  float acc[NVAL];
+#pragma unroll
+  for (int j = 0; j < NVAL; ++j) acc[j] = 0.0f;
+  const int q_end = min(nq, (seg + 1) * per_seg);
+#pragma unroll 1
+  for (int q = seg * per_seg + tid; q < q_end; q += kUpdThreads) {
+    const float4 xv = __ldg(x4 + q);
+    float4 ev[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) ev[m] = __ldg(e4 + m * e_stride + q);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (noise_tensor) z = __ldg(n4 + q);
+    else if (have_noise) z = philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
+    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+    const float zs[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float es[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) es[m] = (j == 0 ? ev[m].x : j == 1 ? ev[m].y : j == 2 ? ev[m].z : ev[m].w);
+      int g = 0;
+#pragma unroll
+      for (int i = 0; i < M; ++i)
+#pragma unroll
+        for (int k = i; k < M; ++k) { acc[g] = fmaf(es[i], es[k], acc[g]); ++g; }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        acc[NG + m] = fmaf(es[m], xs[j], acc[NG + m]);
+        acc[NG + M + m] = fmaf(es[m], zs[j], acc[NG + M + m]);
+      }
+    }
+  }
+  __shared__ float red[kUpdThreads / 32][NVAL];
+#pragma unroll
+  for (int j = 0; j < NVAL; ++j) acc[j] = warp_sum(acc[j]);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < NVAL; ++j) red[warp][j] = acc[j];
+  }
+  __syncthreads();
+  if (tid < NVAL) {
+    float v = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kUpdThreads / 32; ++w) v += red[w][tid];
+    a.and_partials[((size_t)b * a.nblk + seg) * kAndPartialsPerBlock + tid] = v;
+  }
+}
+
+// One CTA per sample: fixed-order reduce of the Gram partials, then the M x M solve in double (Gaussian elimination
+// with partial pivoting); a singular system (identical models) yields the uniform weights, as in the oracle.
+template <int M>
+__global__ void __launch_bounds__(256) superpose_and_solve_kernel(const UpdateArgs a) {
+  constexpr int NG = M * (M + 1) / 2, NVAL = NG + 2 * M;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int step = a.step_ptr ? *a.step_ptr : 0;
+  const StepScalars sc = a.table ? a.table[step] : a.sc;
+  __shared__ float fin[8][32];
+  __shared__ double tot[NVAL];
+  {
+    const int j = tid & 31, g = tid >> 5;
+    float v = 0.0f;
+    if (j < NVAL) {
+      const float* src = a.and_partials + (size_t)b * a.nblk * kAndPartialsPerBlock + j;
+      for (int p = g; p < a.nblk; p += 8) v += src[(size_t)p * kAndPartialsPerBlock];
+    }
+    fin[g][j] = v;
+  }
+  __syncthreads();
+  if (tid < NVAL) {
+    double v = 0.0;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) v += (double)fin[g][tid];
+    tot[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double G[M][M], av[M], bv[M];
+    int g = 0;
+    for (int i = 0; i < M; ++i)
+      for (int k = i; k < M; ++k) { G[i][k] = G[k][i] = tot[g]; ++g; }
+    for (int m = 0; m < M; ++m) { av[m] = tot[NG + m]; bv[m] = tot[NG + M + m]; }
+    const double c1 = (double)sc.c1, c2 = (double)sc.c2, c3 = (double)sc.c3, beta = (double)sc.beta;
+    const double sig = sqrt(1.0 - (double)sc.alpha_bar);
+    double r[M];
+    for (int i = 0; i < M; ++i)
+      r[i] = -((c1 - 1.0) * av[i] + c3 * bv[i]) / sig + beta / (2.0 * sig) * av[i] - beta / (2.0 * sig * sig) * G[i][i];
+    double A[M][M + 1];
+    for (int j = 0; j < M; ++j) A[0][j] = 1.0;
+    A[0][M] = 1.0;
+    const double coef = c1 * c2 / sig;
+    double scale = 1.0;
+    for (int i = 1; i < M; ++i) {
+      for (int j = 0; j < M; ++j) { A[i][j] = coef * (G[i][j] - G[0][j]); scale = fmax(scale, fabs(A[i][j])); }
+      A[i][M] = r[0] - r[i];
+    }
+    bool singular = false;
+    for (int c = 0; c < M && !singular; ++c) {
+      int piv = c;
+      for (int i = c + 1; i < M; ++i) if (fabs(A[i][c]) > fabs(A[piv][c])) piv = i;
+      if (fabs(A[piv][c]) <= 1e-12 * scale) { singular = true; break; }
+      if (piv != c) for (int j = 0; j <= M; ++j) { const double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+      for (int i = c + 1; i < M; ++i) {
+        const double f = A[i][c] / A[c][c];
+        for (int j = c; j <= M; ++j) A[i][j] -= f * A[c][j];
+      }
+    }
+    double kap[M];
+    if (!singular) {
+      for (int i = M - 1; i >= 0; --i) {
+        double v = A[i][M];
+        for (int j = i + 1; j < M; ++j) v -= A[i][j] * kap[j];
+        kap[i] = v / A[i][i];
+      }
+    } else {
+      for (int m = 0; m < M; ++m) kap[m] = 1.0 / M;
+    }
+    for (int m = 0; m < M; ++m) a.kappa_in[b * M + m] = (float)kap[m];
+  }
+}
+
 // One CTA (256 threads) per sample: fixed-order reduce of the segment partials (16 strided lanes per value, then the
 // 16 lanes in order), Ito log-density increment in double, kappa, GroupNorm(1,1) statistics of x'.
 template <int M>
@@ -290,9 +440,15 @@ inline int update_blocks_per_sample(int D, int steps = kSegSteps) {
   return nb < 1 ? 1 : nb;
 }
 
+// workspace = [update partials | AND partials | AND kappa[B][kMaxModels]], each 256-byte aligned
+inline size_t update_ws_part_bytes(int B, int D) {
+  return ((size_t)B * update_blocks_per_sample(D, 1) * kPartialsPerBlock * sizeof(float) + 255) & ~(size_t)255;  // any steps
+}
+inline size_t update_ws_and_bytes(int B, int D) {
+  return ((size_t)B * update_blocks_per_sample(D, 1) * kAndPartialsPerBlock * sizeof(float) + 255) & ~(size_t)255;
+}
 inline size_t update_workspace_bytes(int B, int D, int /*M*/) {
-  size_t part = (size_t)B * update_blocks_per_sample(D, 1) * kPartialsPerBlock * sizeof(float);  // sized for any steps
-  return (part + 255) & ~(size_t)255;
+  return update_ws_part_bytes(B, D) + update_ws_and_bytes(B, D) + (((size_t)B * kMaxModels * sizeof(float) + 255) & ~(size_t)255);
 }
 
 int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream, cudaEvent_t after_update, bool finalize);

@@ -72,18 +72,25 @@ def clear_cache():
         _SAMPLERS.pop(k).close()
 
 
+_MODES = {"or": 0, "and": 1}
+
+
 @torch.no_grad()
 def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bias=None, noise=None, seed=None,
-                      return_trajectory=False, use_graph=True, sample_offset=0, return_launches=False):
+                      return_trajectory=False, use_graph=True, sample_offset=0, return_launches=False, mode="or"):
     """Sample from the superposition of ``models`` (one model == DDPM.sample).
 
     models: sequence of super_diff_disease_b200.UNet on ``device``; ddpm: DDPM (schedule);
     image_shape: (B, 1, H, W), H % 16 == 0, W % 8 == 0.
     noise: fp32 [T, B, 1, H, W] stack (parity mode), or seed: int for in-kernel Philox keyed by
     (seed, sample_offset + b, draw, element) -- shard-invariant.  Exactly one of the two.
+    mode: "or" (kappa = softmax(temperature * log q + bias)) or "and" (kappa solved per sample and
+    step so that every model's log-density increment is equal; temperature / bias unused).
     Returns x [B,1,H,W]; with return_trajectory also kappas [T,B,M] and logq [T+1,B,M]
     (row k <-> loop iteration k, t = T-1-k).
     """
+    if mode not in _MODES:
+        raise _lib.SddError(f"mode must be 'or' or 'and', got {mode!r}")
     device = torch.device(device)
     if device.type != "cuda":
         raise _lib.SddError("superposed_sample runs on a CUDA device only (no CPU fallback)")
@@ -126,6 +133,7 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
         args.kappa_traj, args.logq_traj = kap.data_ptr(), lq.data_ptr()
         keep += [kap, lq]
     args.use_graph = 1 if use_graph else 0
+    args.mode = _MODES[mode]
     with torch.cuda.device(device):
         _lib.check(_lib.lib().sdd_sampler_run(s.ptr, ctypes.byref(args), _lib.stream_ptr(device)))
     s.keep = keep  # the stream may still be reading these
@@ -137,8 +145,8 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
 
 @torch.no_grad()
 def superpose_update(x, eps, logq, alpha, alpha_bar, beta, *, noise=None, seed=None, sample_offset=0, draw_index=0,
-                     temperature=1.0, bias=None, out=None, workspace=None):
-    """One fused superposition update (operator form of A7; wraps sdd_superpose_update).
+                     temperature=1.0, bias=None, out=None, workspace=None, mode="or"):
+    """One fused superposition update (operator form of A7; wraps sdd_superpose_update / sdd_superpose_update_and).
 
     x [B,...] fp32, eps [M,B,...] fp32, logq [B,M] fp32.  noise [B,...] or seed (Philox) or neither
     (z = 0, the t == 0 step).  Returns (x_new, logq_new, kappa[B,M], xstats[B,2]).
@@ -166,6 +174,16 @@ def superpose_update(x, eps, logq, alpha, alpha_bar, beta, *, noise=None, seed=N
     if bias is not None:
         bias = torch.as_tensor(bias, dtype=torch.float32, device=x.device).contiguous()
         bptr = bias.data_ptr()
+    if mode not in _MODES:
+        raise _lib.SddError(f"mode must be 'or' or 'and', got {mode!r}")
+    if mode == "and":
+        with torch.cuda.device(x.device):
+            _lib.check(L.sdd_superpose_update_and(xc.data_ptr(), x_new.data_ptr(), ec.data_ptr(), nptr, lq.data_ptr(),
+                                                  lq_new.data_ptr(), kap.data_ptr(), xst.data_ptr(), B, D, M,
+                                                  float(alpha), float(alpha_bar), float(beta),
+                                                  int(seed or 0) & 0xFFFFFFFFFFFFFFFF, int(sample_offset), int(di),
+                                                  ws.data_ptr(), ws.numel(), _lib.stream_ptr(x.device)))
+        return x_new, lq_new, kap, xst
     with torch.cuda.device(x.device):
         _lib.check(L.sdd_superpose_update(xc.data_ptr(), x_new.data_ptr(), ec.data_ptr(), nptr, lq.data_ptr(),
                                           lq_new.data_ptr(), kap.data_ptr(), xst.data_ptr(), B, D, M, float(alpha),

@@ -105,6 +105,70 @@ def test_update_kernel_identity_and_inplace(S, dev):
     assert torch.equal(x3, x1)
 
 
+@pytest.mark.parametrize("B,D,M", [(3, 256, 2), (2, 16384, 2), (4, 65536, 2), (2, 4096, 3), (1, 262144, 4)])
+@pytest.mark.parametrize("noisy", [True, False])
+def test_and_update_matches_oracle(S, dev, B, D, M, noisy):
+    """SuperDiff AND step: kappa from the per-sample linear solve, then the same update.
+    Tolerances: kappa abs <= 2e-4 (fp32 Gram sums feeding a double solve), x' <= 2e-5 * max|x'|, and the defining
+    property -- all models' log q increments equal -- to 2e-3 absolute on increments of magnitude O(D * beta)."""
+    g = torch.Generator().manual_seed(B * 77 + D + M)
+    x = torch.randn(B, D, generator=g) * 2
+    eps = torch.randn(M, B, D, generator=g) + 0.2 * x
+    z = torch.randn(B, D, generator=g) if noisy else None
+    logq = torch.randn(B, M, generator=g)
+    s = O.Schedule(100)
+    t = 61
+    a, ab, b = s.alphas[t], s.alpha_bars[t], s.betas[t]
+    xr, lr, kr = O.superpose_step(x, [eps[i] for i in range(M)], z if noisy else torch.zeros_like(x), logq, a, ab, b,
+                                  mode="and")
+    xn, ln, kn, st = S.superpose_update(x.to(dev), eps.to(dev), logq.to(dev), a.item(), ab.item(), b.item(),
+                                        noise=z.to(dev) if noisy else None, mode="and")
+    xn, ln, kn = xn.cpu(), ln.cpu(), kn.cpu()
+    ek = (kn - kr).abs().max().item()
+    ex = (xn - xr).abs().max().item() / xr.abs().max().item()
+    inc = ln - logq
+    spread = (inc - inc[:, :1]).abs().max().item()
+    _report(test="and_update", B=B, D=D, M=M, noisy=noisy, kappa_abs=ek, x_relmax=ex, inc_spread=spread,
+            kappa_min=kr.min().item(), kappa_max=kr.max().item())
+    assert ek <= 2e-4 and ex <= 2e-5 and spread <= 2e-3
+    assert torch.allclose(kn.sum(1), torch.ones(B), atol=1e-5)
+
+
+def test_and_identical_models_fall_back_to_uniform(S, dev):
+    g = torch.Generator().manual_seed(5)
+    B, D = 2, 4096
+    x = torch.randn(B, D, generator=g).to(dev)
+    e = torch.randn(1, B, D, generator=g).to(dev)
+    z = torch.randn(B, D, generator=g).to(dev)
+    s = O.Schedule(50)
+    args = (s.alphas[9].item(), s.alpha_bars[9].item(), s.betas[9].item())
+    x1, _, _, _ = S.superpose_update(x, e, torch.zeros(B, 1, device=dev), *args, noise=z)
+    x2, l2, k2, _ = S.superpose_update(x, torch.cat([e, e]), torch.zeros(B, 2, device=dev), *args, noise=z, mode="and")
+    assert torch.equal(k2, torch.full_like(k2, 0.5)) and torch.equal(x1, x2)
+
+
+@pytest.mark.parametrize("T,shape", [(12, (2, 1, 16, 16)), (20, (2, 1, 64, 64))])
+def test_and_sampler_matches_oracle_and_keeps_densities_equal(S, dev, T, shape):
+    params, models = _models(S, dev, [0, 1])
+    g = torch.Generator().manual_seed(100 + T)
+    stack = torch.randn((T,) + shape, generator=g)
+    xr, kr, lr = O.superposed_sample(params, O.Schedule(T), stack, mode="and")
+    x, kap, lq = S.superposed_sample(models, S.DDPM(T), shape, dev, noise=stack.to(dev), return_trajectory=True,
+                                     mode="and")
+    xe, kape, lqe = S.superposed_sample(models, S.DDPM(T), shape, dev, noise=stack.to(dev), return_trajectory=True,
+                                        mode="and", use_graph=False)
+    assert torch.equal(x, xe) and torch.equal(kap, kape) and torch.equal(lq, lqe)  # graph replay == eager
+    rel = _rel(x.cpu(), xr)
+    el = ((lq.cpu() - lr).abs().max() / lr.abs().max()).item()
+    # the AND invariant on the GPU trajectory itself: log q_0 == log q_1 at every step (to accumulated fp32 rounding)
+    gap = ((lq[..., 0] - lq[..., 1]).abs().max() / lq.abs().max()).item()
+    # kappa of the AND solve is ill-conditioned where the two models nearly agree, so compare it through its effect
+    ek = (kap.cpu() - kr).abs().max().item()
+    _report(test="and_sampler", T=T, shape=list(shape), x_rel_l2=rel, logq_rel=el, logq_gap_rel=gap, kappa_abs=ek,
+            kappa_min=kr.min().item(), kappa_max=kr.max().item())
+    assert rel <= 5e-2 and el <= 2e-2 and gap <= 1e-5
+
+
 def test_philox_normals_match_oracle(S, dev):
     import ctypes
     B, D, seed, off, draw = 3, 1024, 0x1234ABCD5678, 5, 7

@@ -101,6 +101,36 @@ def test_k4_kappa_properties():
     assert not torch.allclose(lq1[:, 0] - logq[:, 0], lq1[:, 1] - logq[:, 1])
 
 
+def test_and_mode_equalises_log_density_increments():
+    """with the AND weights every model's Ito log-density increment of the step is the same
+    (the defining property), kappa sums to 1, and identical models give the uniform weights."""
+    g = torch.Generator().manual_seed(11)
+    B, shape = 3, (1, 32, 32)
+    x = torch.randn((B,) + shape, generator=g)
+    z = torch.randn((B,) + shape, generator=g)
+    s = O.Schedule(100)
+    t = 40
+    for M in (2, 3, 4):
+        eps = [torch.randn((B,) + shape, generator=g) + 0.1 * m * x for m in range(M)]
+        logq = torch.randn(B, M, generator=g)
+        _, lq, kap = O.superpose_step(x, eps, z, logq, s.alphas[t], s.alpha_bars[t], s.betas[t], mode="and")
+        inc = lq - logq
+        assert torch.allclose(kap.sum(1), torch.ones(B), atol=1e-5)
+        assert (inc - inc[:, :1]).abs().max().item() <= 1e-3
+    _, lq, kap = O.superpose_step(x, [eps[0], eps[0]], z, torch.zeros(B, 2), s.alphas[t], s.alpha_bars[t], s.betas[t],
+                                  mode="and")
+    assert torch.equal(kap, torch.full((B, 2), 0.5))
+
+
+def test_and_mode_sampler_keeps_densities_equal():
+    params = [O.init_unet_params(0), O.init_unet_params(1)]
+    T, shape = 6, (2, 1, 16, 16)
+    stack = torch.randn((T,) + shape, generator=torch.Generator().manual_seed(3))
+    x, kap, lq = O.superposed_sample(params, O.Schedule(T), stack, mode="and")
+    assert torch.isfinite(x).all()
+    assert ((lq[..., 0] - lq[..., 1]).abs().max() / lq.abs().max()).item() <= 1e-5
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for philox4x32-10."""
     kat = [
