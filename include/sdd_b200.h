@@ -94,6 +94,18 @@ int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, 
                              uint64_t seed, int64_t sample_offset, int draw_index,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Training-side reuse: forward noising and the eps-MSE, forward only ----
+ * out[b,:] = sqrt_ab[b] * x_start[b,:] + sqrt_1mab[b] * noise[b,:]                         (ddpm.py:13-17)
+ * sqrt_ab / sqrt_1mab: device fp32[B], = torch.sqrt(alpha_bar[t_b]) and torch.sqrt(1 - alpha_bar[t_b]).
+ * Same expression tree as the reference (no FMA contraction): bit-identical for the same inputs. */
+int sdd_q_sample(const float* x_start, const float* noise, const float* sqrt_ab, const float* sqrt_1mab,
+                 float* out, int B, int D, void* stream);
+/* *out (device fp32 scalar) = mean((pred - target)^2) over n elements = F.mse_loss(pred, target), ddpm.py:24.
+ * Deterministic (fixed-order double-precision partial sums in `workspace`, sdd_mse_workspace() bytes). */
+size_t sdd_mse_workspace(void);
+int sdd_mse(const float* pred, const float* target, size_t n, float* out, void* workspace,
+            size_t workspace_bytes, void* stream);
+
 /* Philox standard normals, same definition as the in-kernel noise (for x_T and for tests). */
 int sdd_philox_normal(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw_index,
                       void* stream);

@@ -35,6 +35,9 @@ SYMBOLS = {
                                   _i64, _i, _vp, _sz, _vp]),
     "sdd_superpose_update_and": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _u64, _i64, _i,
                                       _vp, _sz, _vp]),
+    "sdd_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "sdd_mse_workspace": (_sz, []),
+    "sdd_mse": (_i, [_vp, _vp, _sz, _vp, _vp, _sz, _vp]),
     "sdd_philox_normal": (_i, [_vp, _i, _i, _u64, _i64, _i, _vp]),
     "sdd_sampler_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdd_sampler_run": (_i, [_vp, ctypes.POINTER(SampleArgs), _vp]),

@@ -13,6 +13,7 @@
 #include "conv_tc4.cuh"
 #include "unet_kernels.cuh"
 #include "update.cuh"
+#include "train_eval.cuh"
 
 namespace sdd {
 
@@ -657,6 +658,35 @@ int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, 
   a.temperature = 1.0f; a.seed = seed; a.sample_offset = sample_offset;
   a.B = B; a.D = D; a.M = M; a.mode = 1;
   return launch_superpose_update(a, workspace, (cudaStream_t)stream);
+}
+
+int sdd_q_sample(const float* x_start, const float* noise, const float* sqrt_ab, const float* sqrt_1mab, float* out,
+                 int B, int D, void* stream) {
+  SDD_CHECK(x_start && noise && sqrt_ab && sqrt_1mab && out, "null argument");
+  SDD_CHECK(B > 0 && D > 0 && D % 4 == 0, "D must be a positive multiple of 4");
+  SDD_TRY(device_check());
+  const int nq = D / 4;
+  dim3 grid((unsigned)std::min((nq + 255) / 256, 4 * num_sms()), (unsigned)B);
+  q_sample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x_start, noise, sqrt_ab, sqrt_1mab, out, D);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+size_t sdd_mse_workspace(void) { return kMseBlocks * sizeof(double); }
+
+int sdd_mse(const float* pred, const float* target, size_t n, float* out, void* workspace, size_t workspace_bytes,
+            void* stream) {
+  SDD_CHECK(pred && target && out && workspace, "null argument");
+  SDD_CHECK(n > 0 && n % 4 == 0, "n must be a positive multiple of 4");
+  SDD_CHECK(workspace_bytes >= sdd_mse_workspace(), "workspace too small");
+  SDD_TRY(device_check());
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)kMseBlocks);
+  mse_partial_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, target, n4, reinterpret_cast<double*>(workspace));
+  SDD_LAUNCH_CHECK();
+  mse_final_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(workspace), blocks, (double)n, out);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
 }
 
 int sdd_philox_normal(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw_index, void* stream) {

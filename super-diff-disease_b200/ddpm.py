@@ -18,6 +18,53 @@ class DDPM:
         self.alphas = 1.0 - self.betas
         self.alpha_bars = torch.cumprod(self.alphas, dim=0)
 
+    # ---- training-side forward pieces: evaluation only, no autograd graph is built
+    @torch.no_grad()
+    def q_sample(self, x_start, t, noise=None):
+        """Forward noising (ddpm.py:13-17) on the GPU; bit-identical to the reference for the same inputs."""
+        _lib.require_cuda(x_start, "x_start")
+        if noise is None:
+            noise = torch.randn_like(x_start)  # same draw as ddpm.py:15
+        dev = x_start.device
+        # coefficients by the reference's own ops on the CPU fp32 table (ddpm.py:16-17), then one fused pass
+        ab = self.alpha_bars[t.detach().cpu().long()]
+        ca = torch.sqrt(ab).to(dev).contiguous()
+        cb = torch.sqrt(1 - ab).to(dev).contiguous()
+        x0 = x_start.to(torch.float32).contiguous()
+        nz = noise.to(torch.float32).contiguous()
+        out = torch.empty_like(x0)
+        B, D = x0.shape[0], x0[0].numel()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().sdd_q_sample(x0.data_ptr(), nz.data_ptr(), ca.data_ptr(), cb.data_ptr(),
+                                               out.data_ptr(), B, D, _lib.stream_ptr(dev)))
+        return out
+
+    @torch.no_grad()
+    def p_losses(self, denoise_model, x_start, t, noise=None):
+        """eps-MSE of ddpm.py:20-24, forward only (validation loss): q_sample -> UNet forward on the sampler's
+        kernels -> deterministic MSE reduction.  Returns a 0-dim CUDA tensor.  ``noise=`` pins the draw for parity."""
+        _lib.require_cuda(x_start, "x_start")
+        if noise is None:
+            noise = torch.randn_like(x_start)
+        noise = noise.to(torch.float32).contiguous()
+        x_noisy = self.q_sample(x_start, t, noise)
+        pred = denoise_model(x_noisy, t).contiguous()
+        L = _lib.lib()
+        dev = x_start.device
+        ws = torch.empty(L.sdd_mse_workspace(), dtype=torch.uint8, device=dev)
+        out = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.sdd_mse(pred.data_ptr(), noise.data_ptr(), pred.numel(), out.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), _lib.stream_ptr(dev)))
+        return out
+
+    @torch.no_grad()
+    def training_step(self, model, x):
+        """ddpm.py:26-29 (same t draw), forward only: the value of the training loss, not a differentiable graph."""
+        bsz = x.size(0)
+        t = torch.randint(0, self.T, (bsz,), device=x.device).long()
+        return self.p_losses(model, x, t)
+
     def draw_noise_stack(self, image_shape, device):
         """[T, *image_shape] noise with the reference's draw order and generators (ddpm.py:33,36)."""
         x = torch.randn(image_shape).to(device)

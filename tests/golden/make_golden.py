@@ -84,6 +84,23 @@ def main():
     out["sched1000_betas"] = d.betas.numpy()
     out["sched1000_alpha_bars"] = d.alpha_bars.numpy()
     np.savez_compressed(os.path.join(HERE, "ddpm_sample.npz"), **out)
+    # N4: q_sample and p_losses (ddpm.py:13-24) -- the loss draws its noise first thing, so seeding and drawing
+    # randn_like(x0) ourselves reproduces the reference's draw
+    out = {}
+    for name, wseed, nseed, shape, T, ts in [("a", 0, 21, (3, 1, 32, 32), 100, [0, 57, 99]),
+                                             ("b", 1, 22, (2, 1, 64, 64), 1000, [3, 998])]:
+        m, _ = ref_model(wseed)
+        d = DDPM(num_timesteps=T)
+        x0 = torch.tanh(seeded_input(nseed, shape))
+        t = torch.tensor(ts, dtype=torch.long)
+        torch.manual_seed(nseed)
+        noise = torch.randn_like(x0)
+        out[f"q_{name}"] = d.q_sample(x0, t, noise).numpy()
+        torch.manual_seed(nseed)
+        with torch.no_grad():
+            out[f"loss_{name}"] = np.float32(d.p_losses(m, x0, t).item())
+        out[f"meta_{name}"] = np.array([wseed, nseed, T, *shape, *ts], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "train_eval.npz"), **out)
     print("golden written")
 
 

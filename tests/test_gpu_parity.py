@@ -413,6 +413,42 @@ def test_superposed_matches_oracle_at_baseline_resolutions(S, dev, T, shape):
     assert torch.allclose(kap.sum(-1), torch.ones_like(kap[..., 0]), atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_n4_q_sample_and_p_losses_match_reference_golden(S, dev, golden_dir, name):
+    """SURVEY 8(f) N4 (ddpm.py:13-24): q_sample is bit-exact against the reference's output; the eps-MSE through the
+    bf16-operand UNet is within 2e-2 relative of the reference's fp32 loss; the MSE reduction alone within 1e-6."""
+    g = np.load(os.path.join(golden_dir, "train_eval.npz"))
+    meta = g[f"meta_{name}"]
+    wseed, nseed, T = (int(v) for v in meta[:3])
+    shape = tuple(int(v) for v in meta[3:7])
+    t = torch.tensor([int(v) for v in meta[7:]], dtype=torch.long)
+    x0 = torch.tanh(torch.randn(shape, generator=torch.Generator().manual_seed(nseed)))
+    torch.manual_seed(nseed)
+    noise = torch.randn_like(x0)
+    d = S.DDPM(T)
+    q = d.q_sample(x0.to(dev), t.to(dev), noise.to(dev))
+    assert np.array_equal(q.cpu().numpy(), g[f"q_{name}"])
+    _, models = _models(S, dev, [wseed])
+    loss = d.p_losses(models[0], x0.to(dev), t.to(dev), noise=noise.to(dev)).item()
+    ref = float(g[f"loss_{name}"])
+    _report(test="n4_p_losses", name=name, loss=loss, ref=ref, rel=abs(loss - ref) / abs(ref))
+    assert abs(loss - ref) <= 2e-2 * abs(ref)
+    # reduction alone: same fp32 prediction on both sides
+    pred = models[0](q, t.to(dev))
+    import ctypes
+    L = S.lib()
+    ws = torch.empty(L.sdd_mse_workspace(), dtype=torch.uint8, device=dev)
+    out = torch.empty((), device=dev)
+    assert L.sdd_mse(pred.data_ptr(), noise.to(dev).data_ptr(), pred.numel(), out.data_ptr(), ws.data_ptr(), ws.numel(), None) == 0
+    torch.cuda.synchronize()
+    want = F.mse_loss(pred.cpu(), noise).item()
+    assert abs(out.item() - want) <= 1e-6 * abs(want)
+    # training_step: same t draw as ddpm.py:28 under the same seed, finite loss
+    torch.manual_seed(5)
+    ls = d.training_step(models[0], x0.to(dev))
+    assert torch.isfinite(ls).item()
+
+
 def test_graph_equals_eager_and_philox_shard_invariance(S, dev):
     _, models = _models(S, dev, [0, 1])
     d = S.DDPM(8)

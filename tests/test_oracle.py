@@ -131,6 +131,28 @@ def test_and_mode_sampler_keeps_densities_equal():
     assert ((lq[..., 0] - lq[..., 1]).abs().max() / lq.abs().max()).item() <= 1e-5
 
 
+def _train_eval_case(g, name):
+    meta = g[f"meta_{name}"]
+    wseed, nseed, T = (int(v) for v in meta[:3])
+    shape = tuple(int(v) for v in meta[3:7])
+    t = torch.tensor([int(v) for v in meta[7:]], dtype=torch.long)
+    x0 = torch.tanh(_seeded_input(nseed, shape))
+    torch.manual_seed(nseed)
+    noise = torch.randn_like(x0)
+    return wseed, T, x0, t, noise
+
+
+@pytest.mark.parametrize("name", ["a", "b"])
+def test_n4_q_sample_and_p_losses_match_reference(golden_dir, name):
+    """q_sample bit-exact, p_losses to fp32 reduction order, vs the reference's own ddpm.py:13-24."""
+    g = np.load(os.path.join(golden_dir, "train_eval.npz"))
+    wseed, T, x0, t, noise = _train_eval_case(g, name)
+    s = O.Schedule(T)
+    assert np.array_equal(O.q_sample(s, x0, t, noise).numpy(), g[f"q_{name}"])
+    loss = O.p_losses(O.init_unet_params(wseed), s, x0, t, noise).item()
+    assert abs(loss - float(g[f"loss_{name}"])) <= 1e-6 * abs(float(g[f"loss_{name}"]))
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for philox4x32-10."""
     kat = [

@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q --timeout 120 -x -k "and_ or update or k3 or k5 or graph" > gpurun_out/pytest_and.log 2>&1; echo "pytest rc=$?"; grep -E "PARITY.*and_|passed|failed|Error|assert" gpurun_out/pytest_and.log | tail -30
+timeout 600 python -m pytest tests -m gpu -q --timeout 120 -x -k "n4 or and_" > gpurun_out/pytest_n4.log 2>&1; echo "pytest rc=$?"; grep -E "PARITY.*n4|passed|failed|Error|assert" gpurun_out/pytest_n4.log | tail -30
