@@ -29,8 +29,8 @@ MAC_128x128 = 147456                 # one 128->128 3x3 conv, per pixel
 
 def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two roofline kernels from the committed
-    `ncu --set full` captures (profiles/r1_v4_ncu.md); taken at exactly the launch shapes timed below."""
-    p = os.path.join(ROOT, "profiles", "r1_v4_traffic.json")
+    `ncu --set full` captures (profiles/r1_final_ncu.md); taken at exactly the launch shapes timed below."""
+    p = os.path.join(ROOT, "profiles", "r1_final_traffic.json")
     if not os.path.exists(p):
         return None, None
     d = json.load(open(p))
