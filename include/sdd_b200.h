@@ -94,6 +94,17 @@ int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, 
                              uint64_t seed, int64_t sample_offset, int draw_index,
                              void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Self-attention core (north-star-only extension, NO reference code -- the reference
+ * UNet, unet.py:37-65, has no attention; oracle = this repo's oracle.attention_core) ----
+ * out[bh,q,:] = softmax_k(scale * <q[bh,q,:], k[bh,k,:]>) @ v[bh,k,:]   fused flash-style on tcgen05 / TMEM / TMA:
+ * the S x S scores never leave the SM.  All tensors bf16, device, contiguous:
+ *   q, k, out: [BH][S][64];   vt: V TRANSPOSED, [BH][64][S].   head_dim == 64, S % 128 == 0 (32^2 = 1024, 16^2 = 256). */
+int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
+                      float scale, void* stream);
+/* `iters` back-to-back launches between one CUDA-event pair; *ms_host = mean launch duration. */
+int sdd_attention_profile(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
+                          float scale, int iters, float* ms_host, void* stream);
+
 /* ---- Training-side reuse: forward noising and the eps-MSE, forward only ----
  * out[b,:] = sqrt_ab[b] * x_start[b,:] + sqrt_1mab[b] * noise[b,:]                         (ddpm.py:13-17)
  * sqrt_ab / sqrt_1mab: device fp32[B], = torch.sqrt(alpha_bar[t_b]) and torch.sqrt(1 - alpha_bar[t_b]).

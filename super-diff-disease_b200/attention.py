@@ -1,0 +1,41 @@
+"""Self-attention core on the B200.
+
+A north-star-only extension: the reference UNet (src/models/unet.py:37-65) has NO attention, so there is no reference
+parity to claim here -- the checker is this repo's own ``oracle.attention_core``.  ``attention_core`` wraps
+``sdd_attention_fwd``: the fused flash-style tcgen05 / TMEM / TMA kernel in csrc/attention.cuh, sized for the 32^2 and
+16^2 feature maps the north star names (1024 / 256 tokens, head_dim 64).  No fallback: CUDA tensors only.
+"""
+import math
+
+import torch
+
+from super_diff_disease_b200 import _lib
+
+
+@torch.no_grad()
+def attention_core(q, k, v, scale=None, *, v_is_transposed=False):
+    """softmax(scale * q k^T) v per (batch, head).
+
+    q, k: bf16 CUDA [B, heads, S, 64];  v: bf16 [B, heads, S, 64], or [B, heads, 64, S] with v_is_transposed=True (the
+    layout the kernel consumes; a producer that writes V^T directly saves the transpose).  S % 128 == 0.
+    Returns bf16 [B, heads, S, 64].
+    """
+    for name, t in (("q", q), ("k", k), ("v", v)):
+        _lib.require_cuda(t, name)
+        if t.dtype != torch.bfloat16 or t.dim() != 4:
+            raise _lib.SddError(f"{name} must be a 4-d bfloat16 tensor")
+    B, Hh, S, D = q.shape
+    if D != 64 or S % 128 != 0:
+        raise _lib.SddError(f"head_dim must be 64 and S a multiple of 128, got S={S}, head_dim={D}")
+    if tuple(k.shape) != (B, Hh, S, D):
+        raise _lib.SddError("k must have q's shape")
+    vt = v if v_is_transposed else v.transpose(2, 3)
+    if tuple(vt.shape) != (B, Hh, D, S):
+        raise _lib.SddError("v must be [B, heads, S, 64] (or [B, heads, 64, S] with v_is_transposed=True)")
+    qc, kc, vtc = q.contiguous(), k.contiguous(), vt.contiguous()
+    out = torch.empty_like(qc)
+    sc = float(scale) if scale is not None else 1.0 / math.sqrt(D)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.lib().sdd_attention_fwd(qc.data_ptr(), kc.data_ptr(), vtc.data_ptr(), out.data_ptr(), B * Hh, S,
+                                                D, sc, _lib.stream_ptr(q.device)))
+    return out

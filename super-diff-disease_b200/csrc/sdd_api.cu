@@ -14,6 +14,7 @@
 #include "unet_kernels.cuh"
 #include "update.cuh"
 #include "train_eval.cuh"
+#include "attention.cuh"
 
 namespace sdd {
 
@@ -36,15 +37,23 @@ static int device_check() {
     cudaGetLastError();
     return SDD_ENODEV;
   }
-  cudaDeviceProp p;
-  e = cudaGetDeviceProperties(&p, dev);
-  if (e != cudaSuccess) {
-    set_error(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
-    cudaGetLastError();
-    return SDD_ENODEV;
+  // compute capability, cached per device ordinal (cudaGetDeviceProperties costs ~1 ms per call)
+  static int major_of[64], minor_of[64];
+  static bool known[64];
+  int major = 0, minor = 0;
+  if (dev >= 0 && dev < 64 && known[dev]) {
+    major = major_of[dev]; minor = minor_of[dev];
+  } else {
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+      set_error("cudaDeviceGetAttribute(compute capability) failed");
+      cudaGetLastError();
+      return SDD_ENODEV;
+    }
+    if (dev >= 0 && dev < 64) { major_of[dev] = major; minor_of[dev] = minor; known[dev] = true; }
   }
-  if (p.major != 10) {
-    set_error("device is sm_" + std::to_string(p.major) + std::to_string(p.minor) +
+  if (major != 10) {
+    set_error("device is sm_" + std::to_string(major) + std::to_string(minor) +
               "; this library contains sm_100a code only (no fallback)");
     return SDD_ENODEV;
   }
@@ -124,6 +133,24 @@ static int make_wt_map2(CUtensorMap* m, const void* base, int Cout, int Cin) {
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(wt2) failed: " + std::to_string((int)r));
+    return SDD_ECUDA;
+  }
+  return SDD_OK;
+}
+
+// bf16 [BH][rows][cols] (cols contiguous) -> box (64 cols = 128 B, box_rows, 1), 128-byte swizzle
+static int make_attn_map(CUtensorMap* m, const void* base, int BH, int rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)BH};
+  cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(attention) failed: " + std::to_string((int)r));
     return SDD_ECUDA;
   }
   return SDD_OK;
@@ -658,6 +685,50 @@ int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, 
   a.temperature = 1.0f; a.seed = seed; a.sample_offset = sample_offset;
   a.B = B; a.D = D; a.M = M; a.mode = 1;
   return launch_superpose_update(a, workspace, (cudaStream_t)stream);
+}
+
+int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
+                      float scale, void* stream) {
+  SDD_CHECK(q && k && vt && out, "null argument");
+  SDD_CHECK(head_dim == kAttnD, "head_dim must be 64");
+  SDD_CHECK(BH > 0 && S >= kAttnBN && S % kAttnBN == 0, "S must be a positive multiple of 128");
+  SDD_CHECK(BH <= 65535, "batch * heads must be <= 65535");
+  SDD_TRY(device_check());
+  CUtensorMap tmQ, tmK, tmVt;
+  SDD_TRY(make_attn_map(&tmQ, q, BH, S, kAttnD, kAttnBM));
+  SDD_TRY(make_attn_map(&tmK, k, BH, S, kAttnD, kAttnBN));
+  SDD_TRY(make_attn_map(&tmVt, vt, BH, kAttnD, S, kAttnD));
+  static bool attr = false;
+  if (!attr) {
+    SDD_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+    attr = true;
+  }
+  AttnArgs a;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out); a.S = S; a.BH = BH;
+  a.scale_log2e = scale * 1.4426950408889634f;
+  attention_fwd_kernel<<<dim3((unsigned)(S / kAttnBM), (unsigned)BH), kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(
+      tmQ, tmK, tmVt, a);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+int sdd_attention_profile(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
+                          float scale, int iters, float* ms_host, void* stream) {
+  SDD_CHECK(ms_host && iters > 0, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = SDD_OK;
+  for (int i = 0; rc == SDD_OK && i < 3; ++i) rc = sdd_attention_fwd(q, k, vt, out, BH, S, head_dim, scale, stream);
+  cudaEventRecord(e0, st);
+  for (int i = 0; rc == SDD_OK && i < iters; ++i) rc = sdd_attention_fwd(q, k, vt, out, BH, S, head_dim, scale, stream);
+  cudaEventRecord(e1, st);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("attention profile: kernel failed"); rc = SDD_ECUDA; }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc == SDD_OK) *ms_host = ms / iters;
+  return rc;
 }
 
 int sdd_q_sample(const float* x_start, const float* noise, const float* sqrt_ab, const float* sqrt_1mab, float* out,

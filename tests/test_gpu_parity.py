@@ -449,6 +449,46 @@ def test_n4_q_sample_and_p_losses_match_reference_golden(S, dev, golden_dir, nam
     assert torch.isfinite(ls).item()
 
 
+@pytest.mark.parametrize("B,heads,S_", [(1, 1, 128), (2, 2, 256), (3, 2, 1024), (1, 1, 2048)])
+@pytest.mark.parametrize("spread", [1.0, 6.0])
+def test_attention_core_matches_oracle(S, dev, B, heads, S_, spread):
+    """Extension (oracle = ours, no reference code): fused flash-style tcgen05 attention vs
+    fp32 softmax(q k^T / sqrt(d)) v of the same bf16 operands.  P is rounded to bf16 before the second GEMM and the
+    output is bf16: max-abs <= 2e-2 * max|ref|, rel-L2 <= 1e-2.  spread = 6 makes the softmax peaky (online-softmax
+    rescaling across key blocks is exercised: the row maximum moves between blocks)."""
+    g = torch.Generator().manual_seed(B * 1000 + S_ + int(spread))
+    q = (torch.randn(B, heads, S_, 64, generator=g) * spread).to(torch.bfloat16)
+    k = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16)
+    v = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16)
+    ref = O.attention_core(q, k, v)
+    out = S.attention_core(q.to(dev), k.to(dev), v.to(dev)).float().cpu()
+    out_t = S.attention_core(q.to(dev), k.to(dev), v.to(dev).transpose(2, 3).contiguous(), v_is_transposed=True).float().cpu()
+    assert torch.equal(out, out_t)
+    rel = _rel(out, ref)
+    mx = ((out - ref).abs().max() / ref.abs().max()).item()
+    _report(test="attention", B=B, heads=heads, S=S_, spread=spread, rel_l2=rel, max_abs_rel=mx)
+    assert rel <= 1e-2 and mx <= 2e-2
+
+
+def test_attention_core_properties(S, dev):
+    """Size-independent properties: constant V rows pass through unchanged (softmax rows sum to 1), identical keys give
+    the mean of V, and the kernel is deterministic."""
+    g = torch.Generator().manual_seed(9)
+    B, heads, S_ = 2, 2, 1024
+    q = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16).to(dev)
+    k = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16).to(dev)
+    vrow = torch.randn(B, heads, 1, 64, generator=g).to(torch.bfloat16).to(dev)
+    out = S.attention_core(q, k, vrow.expand(B, heads, S_, 64).contiguous())
+    assert torch.allclose(out.float(), vrow.float().expand_as(out), atol=2e-2, rtol=1e-2)
+    v = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16).to(dev)
+    k_same = k[:, :, :1].expand(B, heads, S_, 64).contiguous()
+    out2 = S.attention_core(q, k_same, v)
+    assert torch.allclose(out2.float(), v.float().mean(2, keepdim=True).expand_as(out2), atol=2e-2)
+    assert torch.equal(S.attention_core(q, k, v), S.attention_core(q, k, v))
+    with pytest.raises(S.SddError):
+        S.attention_core(q[:, :, :100], k[:, :, :100], v[:, :, :100])
+
+
 def test_graph_equals_eager_and_philox_shard_invariance(S, dev):
     _, models = _models(S, dev, [0, 1])
     d = S.DDPM(8)

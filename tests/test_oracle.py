@@ -153,6 +153,16 @@ def test_n4_q_sample_and_p_losses_match_reference(golden_dir, name):
     assert abs(loss - float(g[f"loss_{name}"])) <= 1e-6 * abs(float(g[f"loss_{name}"]))
 
 
+def test_attention_core_oracle_properties():
+    g = torch.Generator().manual_seed(2)
+    q = torch.randn(1, 2, 32, 8, generator=g); k = torch.randn(1, 2, 32, 8, generator=g)
+    v = torch.randn(1, 2, 32, 8, generator=g)
+    out = O.attention_core(q, k, v)
+    want = torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    assert torch.allclose(out, want, atol=1e-5)
+    assert torch.allclose(O.attention_core(q, k[:, :, :1].expand_as(k), v), v.mean(2, keepdim=True).expand_as(v), atol=1e-5)
+
+
 def test_philox_known_answers():
     """Random123 known-answer vectors for philox4x32-10."""
     kat = [
