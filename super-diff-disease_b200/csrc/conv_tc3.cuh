@@ -48,6 +48,7 @@ struct ConvTc3Args {
   int B, H, W, Cin;
   int tiles_w, tiles_per_sample, num_tiles, num_pairs;
   int stages;
+  int raw_slots;               // generation 5 (kRaw): raw TMA slots behind the operand stages (0 = register-path loader)
   int prefetch;                // halo boxes pulled into L2 this many items ahead (0 = off)
   int dbg;                     // timing experiments only (results invalid): 2 = no stores/stats, 4 = no MMA, 64 = no transform math
   long long* trace;
@@ -58,6 +59,11 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
   asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint4 v) {

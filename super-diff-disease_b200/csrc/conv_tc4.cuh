@@ -13,7 +13,17 @@ namespace sdd {
     }                                                                                                 \
   } while (0)
 
-template <int COUT, bool kTrace = false>
+// kRaw (generation 5, layers whose resident weights leave >= 3 spare 23 KB slots: every layer but 128->128): the
+// halo boxes are not fetched by the loader threads' own global loads but by TMA into a ring of RAW shared-memory slots,
+// issued by the otherwise idle warp 3 up to `raw_slots` items ahead.  Measured on v4: every layer spends 3800-3900
+// cycles per 64-channel item because a loader group can keep only ONE item of loads in flight (its single 48-register
+// buffer; the MEMBAR.ALL.CTA that ptxas puts in front of fence.proxy.async waits for every outstanding load of the
+// thread, so loads cannot be left in flight across a hand-off) -- ~1.2 items = 24-48 KB per SM at 1400-4400 cycles
+// of latency.  With the ring 70-90 KB per SM are in flight without any registers, the loaders read their vectors with
+// conflict-free LDS.128 from the same swizzled offsets they write to (the TMA box lands in the UMMA layout), no thread
+// has a global load outstanding at the fence, and address arithmetic leaves the loaders entirely.  Cost: one more
+// shared-memory write + read per byte (23 KB + 23 KB per item), affordable where the MMA leaves bandwidth.
+template <int COUT, bool kTrace = false, bool kRaw = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
 conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ConvTc3Args a) {
@@ -24,7 +34,10 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int kchunks = a.Cin / 64;
   const uint32_t w_bytes = 9u * kchunks * kWSlot;
   const uint32_t a_base = smem_base + w_bytes;
-  const uint32_t bar_base = a_base + (uint32_t)a.stages * kHaloBytes;
+  const uint32_t raw_base = a_base + (uint32_t)a.stages * kHaloBytes;
+  const uint32_t bar_base = raw_base + (uint32_t)(kRaw ? a.raw_slots : 0) * kHaloBytes;
+  auto raw_full_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + 6 + s); };
+  auto raw_empty_bar = [&](int s) { return bar_base + 8u * (3 * kC3MaxStages + 6 + s); };
   auto ready_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kC3MaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + s); };
@@ -49,6 +62,8 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int s = 0; s < a.stages; ++s) { mbar_init(ready_bar(s), kC3LoaderWarps); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
     mbar_init(w_bar, 1);
+    if constexpr (kRaw)
+      for (int s = 0; s < a.raw_slots; ++s) { mbar_init(raw_full_bar(s), 1); mbar_init(raw_empty_bar(s), 4); }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -121,6 +136,24 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         if (lane == 0) SDD_TRACE4(1, it, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== kRaw: TMA producer of the raw halo boxes, `raw_slots` items ahead =====================
+    if constexpr (kRaw) {
+      if (lane == 0) {
+        const int my_items = ((a.num_pairs - pair0 + pair_stride - 1) / pair_stride) * kchunks;
+        for (int j = 0; j < my_items; ++j) {
+          const int slot = j % a.raw_slots;
+          if (j >= a.raw_slots) mbar_wait(raw_empty_bar(slot), (uint32_t)(((j / a.raw_slots) - 1) & 1));
+          bool valid;
+          const int tile = tile_of(pair0 + (j / kchunks) * pair_stride, valid);
+          const int n = tile / a.tiles_per_sample, tr = tile - n * a.tiles_per_sample;
+          const int th = tr / a.tiles_w, tw = tr - th * a.tiles_w;
+          mbar_arrive_expect_tx(raw_full_bar(slot), (uint32_t)(kHaloRowsV2 * 128));
+          tma_load_4d(raw_base + (uint32_t)slot * kHaloBytes, &tmA, raw_full_bar(slot), (j % kchunks) * 64,
+                      tw * kTileW - 1, th * kTileH - 1, n);
+        }
       }
     }
   }
@@ -310,7 +343,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int pair = pair0 + (item / kchunks) * pair_stride;
     Cursor c = cursor_of(pair < a.num_pairs ? pair : pair0);
     const uint8_t* base = nullptr; uint32_t ok_c = 0;
-    if (item < my_items) { tile_src(c, base, ok_c); issue_loads(base, ok_c); }
+    if (item < my_items) { tile_src(c, base, ok_c); if constexpr (!kRaw) issue_loads(base, ok_c); }
     int stage = grp % a.stages; uint32_t phase = (uint32_t)((grp / a.stages) & 1);
     int cur_n = -1;
     uint64_t ga2[4], gb2[4];
@@ -352,6 +385,16 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         cur_n = c.n;
       }
+      if constexpr (kRaw) {
+        // the raw box of this item (TMA, swizzled exactly like the operand stage): same offsets as the stores below;
+        // out-of-image pixels arrive as zeros (TMA fill) and stay zeros (ok_c)
+        const int slot = item % a.raw_slots;
+        mbar_wait(raw_full_bar(slot), (uint32_t)((item / a.raw_slots) & 1));
+        const uint32_t src = raw_base + (uint32_t)slot * kHaloBytes + soff;
+#pragma unroll
+        for (int i = 0; i < kVecs; ++i)
+          if (i < nvec) r[i] = lds_v4(src + (uint32_t)i * 2048u);
+      }
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (tg == 0) SDD_TRACE4(2, item / kchunks, grp);
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes + soff;
@@ -375,6 +418,9 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // relaxed: the proxy fence has completed this thread's shared-memory writes and made them visible to the async
       // proxy of THIS CTA's tensor core, the only reader
       if (lane == 0) mbar_arrive_relaxed_remote(ready_bar(stage), 0);
+      if constexpr (kRaw) {  // every lane's LDS results were consumed by the stores above: the raw slot is free
+        if (lane == 0) mbar_arrive(raw_empty_bar(item % a.raw_slots));
+      }
       if (tg == 0) SDD_TRACE4(2, item / kchunks, 2 + grp);
       // ---- this group's next item: coordinates, then its loads (nothing of this thread is in flight at a MEMBAR)
       item += 2;
@@ -384,10 +430,10 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (item < my_items) {
         c = cursor_next(c, pair);
         tile_src(c, base, ok_c);
-        issue_loads(base, ok_c);
+        if constexpr (!kRaw) issue_loads(base, ok_c);
         // pull the box of this group's item AFTER that one into L2 (TMA prefetch: no smem, no barrier).  With a single
         // register buffer the loads above are on the group's chain; this turns their DRAM latency into an L2 hit.
-        if (a.prefetch > 0 && tg == 0 && item + 2 < my_items) {
+        if (!kRaw && a.prefetch > 0 && tg == 0 && item + 2 < my_items) {
           const Cursor cp = cursor_next(c, pair + gstep_pairs);
           tma_prefetch_l2_4d(&tmA, kc * 64, cp.tw * kTileW - 1, cp.th * kTileH - 1, cp.n);
         }

@@ -239,12 +239,40 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   a.num_tiles = B * a.tiles_per_sample;
   a.num_pairs = (a.num_tiles + 1) / 2;
   a.stages = conv_tc3_stages(Cout, Cin);
+  a.raw_slots = 0;
   static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 1;  // v4: TMA L2 prefetch of a loader group's item after next; measured +3..6 % (v3's paced prefetch warp: no effect)
   a.prefetch = prefetch;
   a.dbg = dbg;
   a.trace = trace;
-  const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages);
+  // generation 5 (kRaw): TMA-filled raw ring behind 3 operand stages.  Measured (32 x 256^2 chunk, us, v4 -> raw):
+  // 64->128 314 -> 287, 128->64 369 -> 348, 64->64 227 -> 244 (slower: one item per tile, the per-tile epilogue and
+  // hand-offs bind there, not the loads), 128->128 has no room for the ring.  So: the two Cin != Cout layers only.
+  // SDD_CONV_RAW=0 selects the register-path loader everywhere, =2 forces the ring wherever it fits (A/B).
+  static const int raw_env = getenv("SDD_CONV_RAW") ? atoi(getenv("SDD_CONV_RAW")) : 1;
+  static const int raw_stages = getenv("SDD_CONV_RAW_STAGES") ? atoi(getenv("SDD_CONV_RAW_STAGES")) : 3;
+  static const int raw_max = getenv("SDD_CONV_RAW_SLOTS") ? atoi(getenv("SDD_CONV_RAW_SLOTS")) : 4;
+  bool use_raw = false;
+  if (raw_env && (raw_env == 2 || Cin != Cout) && !trace && getenv("SDD_CONV_V3") == nullptr) {
+    int slots = raw_max;
+    while (slots > 0 && conv_tc3_smem_bytes(Cout, Cin, raw_stages + slots) > kC2SmemLimit - 2048) --slots;
+    if (slots >= 3) { use_raw = true; a.stages = raw_stages; a.raw_slots = slots; }
+  }
+  const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages + a.raw_slots);
   const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
+  if (use_raw) {
+    static bool attr5 = false;
+    if (!attr5) {
+      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kC2SmemLimit - 2048));
+      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    kC2SmemLimit - 2048));
+      attr5 = true;
+    }
+    if (Cout == 64) conv3x3_tc4_kernel<64, false, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+    else conv3x3_tc4_kernel<128, false, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
+    SDD_LAUNCH_CHECK();
+    return SDD_OK;
+  }
   static const bool v4 = getenv("SDD_CONV_V3") == nullptr;  // product: two loader groups on alternating items (v4); SDD_CONV_V3=1 selects the single-group loader for A/B
   if (v4) {
     static bool attr4 = false;

@@ -9,6 +9,8 @@ os.makedirs("gpurun_out", exist_ok=True)
 chunk = int(os.environ.get("CHUNK", 32))
 print("prefetch =", os.environ.get("SDD_CONV_PREFETCH", "default"), "chunk =", chunk)
 names = [(0, "full"), (2, "no-store"), (8, "no-stats"), (2 | 8, "no-store/stats"), (4, "no-MMA"), (64, "no-xform-math"), (2 | 8 | 4 | 64, "loads+epi-ld only")]
+if os.environ.get("QUICK"):
+    names = names[:1]
 for cin, cout in [(64, 64), (128, 128), (64, 128), (128, 64)]:
     line = f"{cin:3d}->{cout:3d}: "
     for dbg, nm in names:

@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -q --timeout 60 -x -k "attention" > gpurun_out/pytest_attn.log 2>&1; echo "pytest rc=$?"; grep -E "PARITY.*attention|passed|failed|Error|assert|timed out|sdd:" gpurun_out/pytest_attn.log | tail -30
-timeout 120 python tools/attn_bench.py 2>&1 | tail -5
+for R in 0 1 0 1; do
+SDD_CONV_RAW=$R timeout 600 python bench.py --no-cpu-baseline --no-e2e --steps 3 --warmup 3 > gpurun_out/bench_ab_$R.log 2>&1; echo "RAW=$R rc=$?"; tail -1 gpurun_out/bench_ab_$R.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['clocks'])"
+done
