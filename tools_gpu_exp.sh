@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for R in 0 1 0 1; do
-SDD_CONV_RAW=$R timeout 600 python bench.py --no-cpu-baseline --no-e2e --steps 3 --warmup 3 > gpurun_out/bench_ab_$R.log 2>&1; echo "RAW=$R rc=$?"; tail -1 gpurun_out/bench_ab_$R.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['clocks'])"
-done
+# compute-sanitizer memcheck over a small, representative subset of the GPU tests (every kernel family once)
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 99 --log-file gpurun_out/sanitizer_memcheck.log \
+  python -m pytest tests -m gpu -q --timeout 600 -x -k "test_update_kernel_matches_oracle and 256 or test_and_update_matches_oracle and 256 or test_philox or test_n4 and a or test_attention_core_matches_oracle and 256 or test_k3_self or test_conv3x3_fused_2cta_kernel and 16-8 or test_unet_forward_matches_oracle_and_golden and 16" > gpurun_out/sanitizer_pytest.log 2>&1
+echo "memcheck rc=$?"; tail -3 gpurun_out/sanitizer_pytest.log; grep -E "ERROR SUMMARY|Invalid|Error" gpurun_out/sanitizer_memcheck.log | head -10
