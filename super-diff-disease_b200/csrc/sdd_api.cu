@@ -486,8 +486,13 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     }
     // ups.1: GroupNorm(4,64)+SiLU fused into the 64->1 conv (mma.sync), then GN(1,1)+SiLU fused into the 1->1 conv
     const BlockParams& u1 = u->blk[4];
-    conv_out1_mma_kernel<<<eg, 256, 0, st>>>(ws.act[cur], sums(gi), u1.gn1_w, u1.gn1_b, u1.conv1_w, u1.conv1_b, ws.e1,
-                                             sums(gi + 1), H, W);
+    {
+      const int o1_tiles = (int)(eg.x * eg.y * eg.z);
+      // two persistent CTAs per SM at 119 registers (three at the 80-register cap spill and run at the old 85 us)
+      conv_out1_mma_kernel<2><<<std::min(o1_tiles, 2 * num_sms()), 256, 0, st>>>(
+          ws.act[cur], sums(gi), u1.gn1_w, u1.gn1_b, u1.conv1_w, u1.conv1_b, ws.e1, sums(gi + 1), H, W, (int)eg.x,
+          (int)eg.y, o1_tiles);
+    }
     SDD_LAUNCH_CHECK();
     conv_out2_kernel<<<eg, 256, 0, st>>>(ws.e1, sums(gi + 1), u1.gn2_w, u1.gn2_b, u1.conv2_w, bias_time(4),
                                          eps_out + (size_t)b0 * HW, H, W);

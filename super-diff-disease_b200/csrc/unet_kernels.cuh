@@ -319,30 +319,26 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-__global__ void __launch_bounds__(256, 3) conv_out1_mma_kernel(const __nv_bfloat16* __restrict__ raw,
+// PERSISTENT: a CTA walks a CONTIGUOUS range of tiles (tile = (sample, 8 x 32 pixel block); a range rarely crosses a
+// sample, so the per-sample scale/shift is rebuilt about once per CTA).  The weight
+// fragments are loaded once per CTA and the GroupNorm scale/shift once per sample, and each warp issues the raw loads of
+// its first m-tile of the NEXT tile before the current tile's barrier + 9-tap gather, so the tile-to-tile critical path no
+// longer contains a global-load latency.  Measured per 16 samples at 256^2: 84.8 us with one CTA per tile (the ~70 parameter
+// loads of the prologue and three exposed load latencies per 340-pixel tile dominated) -> 63.0 us (2.1 TB/s of input).
+template <int CPS>
+__global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bfloat16* __restrict__ raw,
                                                             const long long* __restrict__ in_sums /*[B][4][2]*/,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ w /*[1][64][3][3]*/,
                                                             const float* __restrict__ bias, float* __restrict__ out,
-                                                            long long* out_sums /*[B][8], first two used*/, int H, int W) {
-  const int b = blockIdx.z;
-  const int h0 = blockIdx.y * kO1TH, w0 = blockIdx.x * kO1TW;
+                                                            long long* out_sums /*[B][8], first two used*/, int H, int W,
+                                                            int tiles_x, int tiles_y, int num_tiles) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = lane & 3, j = lane >> 2;
   __shared__ float tb[kO1MT * 16][kO1Taps + 1];  // T[halo pixel][tap], padded against bank conflicts
+  __shared__ float red[2][8][2];
 
-  // per-lane GroupNorm scale/shift of its 16 channels, and the weight fragments in the permuted K order
-  float ga[16], gb[16];
-  {
-    float mean, rstd;  // lane t owns channels [16t, 16t+16) = exactly GroupNorm group t
-    gn_mean_rstd_from_sums(in_sums + ((size_t)b * 4 + t) * 2, (double)H * (double)W * 16.0, kGnEps, mean, rstd);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int c = t * 16 + i;
-      ga[i] = rstd * gamma[c];
-      gb[i] = beta[c] - mean * ga[i];
-    }
-  }
+  // weight fragments in the permuted K order: once per CTA
   uint32_t bw[2][4][2];
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt)
@@ -354,11 +350,16 @@ __global__ void __launch_bounds__(256, 3) conv_out1_mma_kernel(const __nv_bfloat
         const float w0v = tap < kO1Taps ? w[c * 9 + tap] : 0.f, w1v = tap < kO1Taps ? w[(c + 1) * 9 + tap] : 0.f;
         bw[nt][ks][h] = pack_bf16x2(w0v, w1v);
       }
+  const float bias0 = bias[0];
 
-  const __nv_bfloat16* img = raw + (size_t)b * H * W * 64 + t * 16;
-  // software pipeline over this warp's m-tiles (2 or 3 of them): the raw vectors of m-tile k+1 are in flight while
-  // m-tile k is normalised, activated and multiplied, so a warp pays the global-load latency once, not per m-tile
-  auto load_mt = [&](int mt, uint4 (&v)[2][2], bool (&ok)[2]) {
+  auto tile_coords = [&](int tile, int& b, int& h0, int& w0) {
+    const int per = tiles_x * tiles_y;
+    b = tile / per;
+    const int r = tile - b * per;
+    const int ty = r / tiles_x;
+    h0 = ty * kO1TH; w0 = (r - ty * tiles_x) * kO1TW;
+  };
+  auto load_mt = [&](const __nv_bfloat16* img, int h0, int w0, int mt, uint4 (&v)[2][2], bool (&ok)[2]) {
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
       const int p = mt * 16 + j + 8 * rh;
@@ -374,64 +375,94 @@ __global__ void __launch_bounds__(256, 3) conv_out1_mma_kernel(const __nv_bfloat
       }
     }
   };
+
+  int tile = (int)(((long long)blockIdx.x * num_tiles) / gridDim.x);
+  const int tile_end = (int)(((long long)(blockIdx.x + 1) * num_tiles) / gridDim.x);
+  if (tile >= tile_end) return;
+  int b, h0, w0;
+  tile_coords(tile, b, h0, w0);
+  const __nv_bfloat16* img = raw + (size_t)b * H * W * 64 + t * 16;
   uint4 vc[2][2], vn[2][2];
   bool okc[2], okn[2] = {false, false};
-  load_mt(warp, vc, okc);
-  for (int mt = warp; mt < kO1MT; mt += 8) {
-    if (mt + 8 < kO1MT) load_mt(mt + 8, vn, okn);
-    uint32_t a[2][8];  // [row half][ks*2+h]
-#pragma unroll
-    for (int rh = 0; rh < 2; ++rh) {
-      uint32_t u[8] = {vc[rh][0].x, vc[rh][0].y, vc[rh][0].z, vc[rh][0].w, vc[rh][1].x, vc[rh][1].y, vc[rh][1].z, vc[rh][1].w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (okc[rh]) {
-          __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[i]);
-          const float lo = silu_tanh(fmaf(__low2float(hv), ga[2 * i], gb[2 * i]));
-          const float hi = silu_tanh(fmaf(__high2float(hv), ga[2 * i + 1], gb[2 * i + 1]));
-          u[i] = pack_bf16x2(lo, hi);
-        }
-        a[rh][i] = u[i];
-      }
-    }
-    float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t af[4] = {a[0][ks * 2], a[1][ks * 2], a[0][ks * 2 + 1], a[1][ks * 2 + 1]};
-      mma_bf16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
-      mma_bf16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
-    }
-    // d0: taps 2t, 2t+1 of rows j and j+8; d1: taps 8+2t, 9+2t (only tap 8 exists)
-    const int r0 = mt * 16 + j;
-    tb[r0][2 * t] = d0[0]; tb[r0][2 * t + 1] = d0[1];
-    tb[r0 + 8][2 * t] = d0[2]; tb[r0 + 8][2 * t + 1] = d0[3];
-    if (t == 0) { tb[r0][8] = d1[0]; tb[r0 + 8][8] = d1[2]; }
-#pragma unroll
-    for (int rh = 0; rh < 2; ++rh) { vc[rh][0] = vn[rh][0]; vc[rh][1] = vn[rh][1]; okc[rh] = okn[rh]; }
-  }
-  __syncthreads();
+  load_mt(img, h0, w0, warp, vc, okc);
+  int cur_b = -1;
+  float ga[16], gb[16];
+  int it = 0;
 
-  const int r = tid / kO1TW, c = tid % kO1TW;
-  const int h = h0 + r, ww = w0 + c;
-  float s = 0.f, ss = 0.f;
-  if (h < H && ww < W) {
-    float acc = bias[0];
+  for (; tile < tile_end; ++tile, ++it) {
+    if (b != cur_b) {  // lane t owns channels [16t, 16t+16) = exactly GroupNorm group t
+      float mean, rstd;
+      gn_mean_rstd_from_sums(in_sums + ((size_t)b * 4 + t) * 2, (double)H * (double)W * 16.0, kGnEps, mean, rstd);
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+      for (int i = 0; i < 16; ++i) {
+        ga[i] = rstd * gamma[t * 16 + i];
+        gb[i] = beta[t * 16 + i] - mean * ga[i];
+      }
+      cur_b = b;
+    }
+    // coordinates of this CTA's next tile (its first m-tile is prefetched at the end of the m-tile loop)
+    const int ntile = tile + 1;
+    int nb = b, nh0 = h0, nw0 = w0;
+    if (ntile < tile_end) tile_coords(ntile, nb, nh0, nw0);
+    const __nv_bfloat16* nimg = raw + (size_t)nb * H * W * 64 + t * 16;
+
+    for (int mt = warp; mt < kO1MT; mt += 8) {
+      if (mt + 8 < kO1MT) load_mt(img, h0, w0, mt + 8, vn, okn);
+      else if (ntile < tile_end) load_mt(nimg, nh0, nw0, warp, vn, okn);  // next tile's first m-tile
+      uint32_t a[2][8];  // [row half][ks*2+h]
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) acc += tb[(r + ky) * kO1HW + (c + kx)][ky * 3 + kx];
-    out[((size_t)b * H + h) * W + ww] = acc;
-    s = acc; ss = acc * acc;
-  }
-  __shared__ float red[8][2];
+      for (int rh = 0; rh < 2; ++rh) {
+        uint32_t u[8] = {vc[rh][0].x, vc[rh][0].y, vc[rh][0].z, vc[rh][0].w, vc[rh][1].x, vc[rh][1].y, vc[rh][1].z, vc[rh][1].w};
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-  if (lane == 0) { red[warp][0] = s; red[warp][1] = ss; }
-  __syncthreads();
-  if (tid < 2) {
-    float x0 = 0.f;
-    for (int wq = 0; wq < 8; ++wq) x0 += red[wq][tid];
-    gn_red_add(out_sums + (size_t)b * 8 + tid, x0);
+        for (int i = 0; i < 8; ++i) {
+          if (okc[rh]) {
+            __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[i]);
+            const float lo = silu_tanh(fmaf(__low2float(hv), ga[2 * i], gb[2 * i]));
+            const float hi = silu_tanh(fmaf(__high2float(hv), ga[2 * i + 1], gb[2 * i + 1]));
+            u[i] = pack_bf16x2(lo, hi);
+          }
+          a[rh][i] = u[i];
+        }
+      }
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t af[4] = {a[0][ks * 2], a[1][ks * 2], a[0][ks * 2 + 1], a[1][ks * 2 + 1]};
+        mma_bf16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
+        mma_bf16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
+      }
+      // d0: taps 2t, 2t+1 of rows j and j+8; d1: taps 8+2t, 9+2t (only tap 8 exists)
+      const int r0 = mt * 16 + j;
+      tb[r0][2 * t] = d0[0]; tb[r0][2 * t + 1] = d0[1];
+      tb[r0 + 8][2 * t] = d0[2]; tb[r0 + 8][2 * t + 1] = d0[3];
+      if (t == 0) { tb[r0][8] = d1[0]; tb[r0 + 8][8] = d1[2]; }
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) { vc[rh][0] = vn[rh][0]; vc[rh][1] = vn[rh][1]; okc[rh] = okn[rh]; }
+    }
+    __syncthreads();  // tb complete
+
+    const int r = tid / kO1TW, c = tid % kO1TW;
+    const int h = h0 + r, ww = w0 + c;
+    float s = 0.f, ss = 0.f;
+    if (h < H && ww < W) {
+      float acc = bias0;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc += tb[(r + ky) * kO1HW + (c + kx)][ky * 3 + kx];
+      out[((size_t)b * H + h) * W + ww] = acc;
+      s = acc; ss = acc * acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if (lane == 0) { red[it & 1][warp][0] = s; red[it & 1][warp][1] = ss; }
+    __syncthreads();  // gather reads of tb done (the next tile may overwrite it); red[it & 1] complete
+    if (tid < 2) {
+      float x0 = 0.f;
+      for (int wq = 0; wq < 8; ++wq) x0 += red[it & 1][wq][tid];
+      gn_red_add(out_sums + (size_t)b * 8 + tid, x0);
+    }
+    b = nb; h0 = nh0; w0 = nw0; img = nimg;
   }
 }
 
