@@ -139,8 +139,10 @@ def run_reference_arm(args, rank, world):
 
 
 def workload_config(args, world):
+    which = {(128, 100): "BASELINE configs[1]", (256, 250): "BASELINE configs[2]",
+             (512, 1000): "BASELINE configs[3] per-GPU shard"}.get((args.res, args.diffusion_steps), "custom shape")
     return {"workload": f"TB+Pneumonia superposition {args.res}x{args.res}, batch {args.batch} per GPU, "
-                        f"{args.diffusion_steps}-step DDPM schedule (BASELINE configs[2], reference UNet architecture)",
+                        f"{args.diffusion_steps}-step DDPM schedule ({which}, reference UNet architecture)",
             "per_gpu_batch": args.batch, "global_batch": args.batch * world, "resolution": args.res,
             "diffusion_steps": args.diffusion_steps, "models": 2, "parallelism": f"batch-shard x{world}",
             "l2": "working set per call >> L2 (no flush needed between calls)",

@@ -1,7 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-SDD_CONV_RAW=2 timeout 600 python -m pytest tests -m gpu -q --timeout 120 -x -k "conv3x3_fused or unet_forward or k3 or k5" > gpurun_out/pytest_raw.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|Error|assert|timed out|sdd:" gpurun_out/pytest_raw.log | tail -10
-for R in 0 2; do
-echo "SDD_CONV_RAW=$R"
-SDD_CONV_RAW=$R TRACE=0 timeout 300 python tools/conv_exp.py 2>&1 | grep -v "timed out" | cut -c1-260
-done
+timeout 600 python bench.py --batch 16 --res 128 --diffusion-steps 100 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2.log 2>&1; echo "c2 rc=$?"; tail -1 gpurun_out/bench_c2.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline_update']['frac'], d['config']['workload'])"
+timeout 600 python bench.py --batch 4 --res 512 --diffusion-steps 1000 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c4.log 2>&1; echo "c4 rc=$?"; tail -1 gpurun_out/bench_c4.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d['roofline_update']['frac'], d['config']['workload'])"
+timeout 300 python __graft_entry__.py smoke
