@@ -48,6 +48,7 @@ struct ConvTc3Args {
   int B, H, W, Cin;
   int tiles_w, tiles_per_sample, num_tiles, num_pairs;
   int stages;
+  int contig;                  // generation 4+: contiguous tile-pair ranges per CTA pair (0 = strided by the grid)
   int raw_slots;               // generation 5 (kRaw): raw TMA slots behind the operand stages (0 = register-path loader)
   int prefetch;                // halo boxes pulled into L2 this many items ahead (0 = off)
   int dbg;                     // timing experiments only (results invalid): 2 = no stores/stats, 4 = no MMA, 64 = no transform math

@@ -54,7 +54,14 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  const int pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  // Tile pairs of this CTA pair: a CONTIGUOUS range [pair0, pair_end) (a.contig; default) or every (gridDim.x / 2)-th
+  // pair.  Contiguous ranges keep a loader group inside one sample for hundreds of items, so the per-sample GroupNorm
+  // scale / shift (two named barriers, double-precision statistics, an LDS round trip: 15 % of the loaders' samples in
+  // the 64->64 ncu capture, where the strided order changed sample every ~1.7 items) is rebuilt almost never.
+  const int npp = gridDim.x >> 1, pidx = blockIdx.x >> 1;
+  const int pair0 = a.contig ? (int)(((long long)pidx * a.num_pairs) / npp) : pidx;
+  const int pair_end = a.contig ? (int)(((long long)(pidx + 1) * a.num_pairs) / npp) : a.num_pairs;
+  const int pair_stride = a.contig ? 1 : npp;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
@@ -105,7 +112,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int it = 0;
-      for (int pair = pair0; pair < a.num_pairs; pair += pair_stride, ++it) {
+      for (int pair = pair0; pair < pair_end; pair += pair_stride, ++it) {
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         if (lane == 0) SDD_TRACE4(1, it, 0);
@@ -142,7 +149,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== kRaw: TMA producer of the raw halo boxes, `raw_slots` items ahead =====================
     if constexpr (kRaw) {
       if (lane == 0) {
-        const int my_items = ((a.num_pairs - pair0 + pair_stride - 1) / pair_stride) * kchunks;
+        const int my_items = ((pair_end - pair0 + pair_stride - 1) / pair_stride) * kchunks;
         for (int j = 0; j < my_items; ++j) {
           const int slot = j % a.raw_slots;
           if (j >= a.raw_slots) mbar_wait(raw_empty_bar(slot), (uint32_t)(((j / a.raw_slots) - 1) & 1));
@@ -168,7 +175,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const float* bias_row = a.bias.base + (a.bias.row_ptr ? (int64_t)(*a.bias.row_ptr) : 0) * a.bias.row_stride + col0;
     int acc = 0; uint32_t acc_phase = 0;
     int it = 0;
-    for (int pair = pair0; pair < a.num_pairs; pair += pair_stride, ++it) {
+    for (int pair = pair0; pair < pair_end; pair += pair_stride, ++it) {
       bool valid;
       const int tile = tile_of(pair, valid);
       const int n = tile / a.tiles_per_sample, tr = tile - n * a.tiles_per_sample;
@@ -177,6 +184,13 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const float* bp = bias_row + (int64_t)n * a.bias.batch_stride;
       __nv_bfloat16* orow = a.out + (((size_t)n * a.H + h) * a.W + w) * COUT + col0;
       const bool do_store = valid && !(a.dbg & 2);  // dbg 2: no stores (statistics stay), dbg 8: no statistics
+      // Cout = 64: this warp's 32 bias values are fetched BEFORE the wait for the accumulator (they were 10 % of the
+      // epilogue's stall samples as the first use behind the wait); Cout = 128 has no registers to spare for that.
+      float4 bpre[(G <= 2) ? 4 * G : 1];
+      if constexpr (G <= 2) {
+#pragma unroll
+        for (int j = 0; j < 4 * G; ++j) bpre[j] = __ldg(reinterpret_cast<const float4*>(bp + j * 4));
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (e == 0 && lane == 0) SDD_TRACE4(3, it, 0);
@@ -189,7 +203,10 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int st = 0; st < G; ++st) {
         float4 b4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bp + st * 16 + j * 4));
+        for (int j = 0; j < 4; ++j) {
+          if constexpr (G <= 2) b4[j] = bpre[st * 4 + j];
+          else b4[j] = __ldg(reinterpret_cast<const float4*>(bp + st * 16 + j * 4));
+        }
         tmem_ld_wait();
         if (st + 1 < G) tmem_ld_32x16(taddr + (uint32_t)((st + 1) * 16), v[(st + 1) & 1]);
         const uint32_t* vv = v[st & 1];
@@ -288,7 +305,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     // item j of this CTA = (pair iteration j / kchunks, chunk j % kchunks); this group's items are grp, grp + 2, ...
     // so with two chunks a group always has the same chunk, with one chunk it takes every other tile
-    const int my_items = ((a.num_pairs - pair0 + pair_stride - 1) / pair_stride) * kchunks;
+    const int my_items = ((pair_end - pair0 + pair_stride - 1) / pair_stride) * kchunks;
     const int kc = (kchunks == 2) ? grp : 0;
     const int gstep_pairs = (2 / kchunks) * pair_stride;  // pairs between two items of a group
     struct Cursor { int n, th, tw; };
@@ -329,9 +346,10 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     };
     uint4 r[kVecs];
     auto issue_loads = [&](const uint8_t* base, uint32_t okmask) {
-      if (okmask == (1u << kVecs) - 1u) {
+      if (okmask == (1u << nvec) - 1u) {  // every vector this thread owns is inside the image
 #pragma unroll
-        for (int i = 0; i < kVecs; ++i) r[i] = ldg_nc_v4(base + goff[i]);
+        for (int i = 0; i < kVecs - 1; ++i) r[i] = ldg_nc_v4(base + goff[i]);
+        r[kVecs - 1] = (nvec == kVecs) ? ldg_nc_v4(base + goff[kVecs - 1]) : make_uint4(0u, 0u, 0u, 0u);
       } else {
 #pragma unroll
         for (int i = 0; i < kVecs; ++i)
@@ -341,7 +359,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     int item = grp;                                      // this group's current item
     int pair = pair0 + (item / kchunks) * pair_stride;
-    Cursor c = cursor_of(pair < a.num_pairs ? pair : pair0);
+    Cursor c = cursor_of(pair < pair_end ? pair : (pair0 < a.num_pairs ? pair0 : 0));
     const uint8_t* base = nullptr; uint32_t ok_c = 0;
     if (item < my_items) { tile_src(c, base, ok_c); if constexpr (!kRaw) issue_loads(base, ok_c); }
     int stage = grp % a.stages; uint32_t phase = (uint32_t)((grp / a.stages) & 1);
@@ -398,12 +416,18 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(empty_bar(stage), phase ^ 1u);
       if (tg == 0) SDD_TRACE4(2, item / kchunks, grp);
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes + soff;
-      if (fuse && ok_c == (1u << kVecs) - 1u && !(a.dbg & 64)) {
-        // interior tile, full thread: straight-line code, the twelve vectors' chains interleave freely
+      if (fuse && ok_c == (1u << nvec) - 1u && !(a.dbg & 64)) {
+        // interior tile: straight-line code, the vectors' chains interleave freely.  (Three of a group's four warps own
+        // eleven vectors, not twelve -- rows >= 180 do not exist -- and used to fall into the masked path below on every
+        // item: 78 % of all loader executions, ~1.7x the instructions.)
 #pragma unroll
-        for (int i = 0; i < kVecs; ++i)
+        for (int i = 0; i < kVecs - 1; ++i)
           sts_v4(dst + (uint32_t)i * 2048u,
                  make_uint4(xform_pair(r[i].x, 0), xform_pair(r[i].y, 1), xform_pair(r[i].z, 2), xform_pair(r[i].w, 3)));
+        if (nvec == kVecs)  // warp-uniform: col = tg >> 3, so only the first warp of a group has the twelfth vector
+          sts_v4(dst + (uint32_t)(kVecs - 1) * 2048u,
+                 make_uint4(xform_pair(r[kVecs - 1].x, 0), xform_pair(r[kVecs - 1].y, 1), xform_pair(r[kVecs - 1].z, 2),
+                            xform_pair(r[kVecs - 1].w, 3)));
       } else {
 #pragma unroll
         for (int i = 0; i < kVecs; ++i) {
