@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB] + [os.path.join(CSRC, f) for f in SOURCES]
+           "-o", LIB] + os.environ.get("SDD_NVCC_FLAGS", "").split() + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
