@@ -513,7 +513,7 @@ inline int conv_tc3_smem_bytes(int Cout, int Cin, int stages) {
 }
 inline int conv_tc3_stages(int Cout, int Cin) {
   int s = kC3MaxStages;
-  while (s > 1 && conv_tc3_smem_bytes(Cout, Cin, s) > kC2SmemLimit - 2048 /*static smem*/) --s;
+  while (s > 1 && conv_tc3_smem_bytes(Cout, Cin, s) > kC2SmemLimit - 4096 /*static smem*/) --s;
   return s;
 }
 

@@ -173,6 +173,8 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int col0 = hcol * COLS;
     const int m = q * 32 + lane;  // accumulator row = pixel within the tile
     const float* bias_row = a.bias.base + (a.bias.row_ptr ? (int64_t)(*a.bias.row_ptr) : 0) * a.bias.row_stride + col0;
+    __shared__ __align__(16) float s_bias[8][64];
+    int bias_cur = -1;
     int acc = 0; uint32_t acc_phase = 0;
     int it = 0;
     for (int pair = pair0; pair < pair_end; pair += pair_stride, ++it) {
@@ -184,12 +186,15 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       const float* bp = bias_row + (int64_t)n * a.bias.batch_stride;
       __nv_bfloat16* orow = a.out + (((size_t)n * a.H + h) * a.W + w) * COUT + col0;
       const bool do_store = valid && !(a.dbg & 2);  // dbg 2: no stores (statistics stay), dbg 8: no statistics
-      // Cout = 64: this warp's 32 bias values are fetched BEFORE the wait for the accumulator (they were 10 % of the
-      // epilogue's stall samples as the first use behind the wait); Cout = 128 has no registers to spare for that.
-      float4 bpre[(G <= 2) ? 4 * G : 1];
-      if constexpr (G <= 2) {
-#pragma unroll
-        for (int j = 0; j < 4 * G; ++j) bpre[j] = __ldg(reinterpret_cast<const float4*>(bp + j * 4));
+      // This warp's COLS bias values live in shared memory and are refreshed only when the sample changes (never, when
+      // all samples share one row).  As per-tile global loads they were the first use behind the accumulator wait and
+      // cost 10 % of the epilogue's stall samples: with 213 KB of shared memory there is almost no L1 left to hit in.
+      const int bias_key = a.bias.batch_stride ? n : 0;
+      if (bias_key != bias_cur) {
+        __syncwarp();
+        for (int j = lane; j < COLS; j += 32) s_bias[e][j] = __ldg(bp + j);
+        __syncwarp();
+        bias_cur = bias_key;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
@@ -203,10 +208,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       for (int st = 0; st < G; ++st) {
         float4 b4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if constexpr (G <= 2) b4[j] = bpre[st * 4 + j];
-          else b4[j] = __ldg(reinterpret_cast<const float4*>(bp + st * 16 + j * 4));
-        }
+        for (int j = 0; j < 4; ++j) b4[j] = *reinterpret_cast<const float4*>(&s_bias[e][st * 16 + j * 4]);
         tmem_ld_wait();
         if (st + 1 < G) tmem_ld_32x16(taddr + (uint32_t)((st + 1) * 16), v[(st + 1) & 1]);
         const uint32_t* vv = v[st & 1];

@@ -259,7 +259,7 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   bool use_raw = false;
   if (raw_env && (raw_env == 2 || Cin != Cout) && !trace && getenv("SDD_CONV_V3") == nullptr) {
     int slots = raw_max;
-    while (slots > 0 && conv_tc3_smem_bytes(Cout, Cin, raw_stages + slots) > kC2SmemLimit - 2048) --slots;
+    while (slots > 0 && conv_tc3_smem_bytes(Cout, Cin, raw_stages + slots) > kC2SmemLimit - 4096) --slots;
     if (slots >= 3) { use_raw = true; a.stages = raw_stages; a.raw_slots = slots; }
   }
   const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages + a.raw_slots);
@@ -268,9 +268,9 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
     static bool attr5 = false;
     if (!attr5) {
       SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kC2SmemLimit - 2048));
+                                    kC2SmemLimit - 4096));
       SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kC2SmemLimit - 2048));
+                                    kC2SmemLimit - 4096));
       attr5 = true;
     }
     if (Cout == 64) conv3x3_tc4_kernel<64, false, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);

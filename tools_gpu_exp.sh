@@ -1,4 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_gpu.log
-timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_v6.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_v6.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['clocks'], d['roofline']['frac'], d['whole_path_tensor_frac_of_sustained'])"
+timeout 600 python -m pytest tests -m gpu -q --timeout 120 -x -k "conv3x3 or unet_forward or k3 or k5 or shard" > gpurun_out/pytest_raw.log 2>&1; echo "pytest rc=$?"; tail -1 gpurun_out/pytest_raw.log
+QUICK=1 TRACE=0 timeout 300 python tools/conv_exp.py 2>&1 | grep -v "timed out" | cut -c1-160
+CHUNK=64 QUICK=1 TRACE=0 timeout 300 python tools/conv_exp.py 2>&1 | grep -v "timed out" | cut -c1-160
