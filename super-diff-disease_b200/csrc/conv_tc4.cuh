@@ -82,7 +82,17 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  // CTA-lifetime scalars are NOT kept in registers across the role loops: at 88 (epilogue) / 40 (issuer) registers
+  // ptxas spilled them and reloaded them every tile with LDL, and with 213 KB of shared memory there is no L1 left to
+  // hit in (~17 % of the epilogue's stall samples in the 128->128 ncu capture, and a ~300-cycle bubble per tile in
+  // front of the MMA issue).  The TMEM base is re-read from its shared-memory slot (volatile: one LDS per use) and the
+  // pair stride is re-derived from %nctaid behind a volatile asm, which ptxas cannot hoist.
+#define SDD_TMEM_BASE() (*tmem_slot_ptr)
+  auto pair_step = [&]() -> int {
+    uint32_t g;
+    asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(g));
+    return a.contig ? 1 : (int)(g >> 1);
+  };
 
   // tile of this CTA in a pair-iteration; an odd tile count leaves one dummy (clamped, computed, not stored)
   auto tile_of = [&](int pair, bool& valid) {
@@ -112,11 +122,11 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       int it = 0;
-      for (int pair = pair0; pair < pair_end; pair += pair_stride, ++it) {
+      for (int pair = pair0; pair < pair_end; pair += pair_step(), ++it) {
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         if (lane == 0) SDD_TRACE4(1, it, 0);
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
+        const uint32_t d_tmem = SDD_TMEM_BASE() + (uint32_t)(acc * COUT);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait_cluster(ready_bar(stage), phase);
           tc_fence_after();
@@ -177,7 +187,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int bias_cur = -1;
     int acc = 0; uint32_t acc_phase = 0;
     int it = 0;
-    for (int pair = pair0; pair < pair_end; pair += pair_stride, ++it) {
+    for (int pair = pair0; pair < pair_end; pair += pair_step(), ++it) {
       bool valid;
       const int tile = tile_of(pair, valid);
       const int n = tile / a.tiles_per_sample, tr = tile - n * a.tiles_per_sample;
@@ -199,7 +209,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       if (e == 0 && lane == 0) SDD_TRACE4(3, it, 0);
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + col0);
+      const uint32_t taddr = SDD_TMEM_BASE() + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + col0);
       float sg[2] = {0.f, 0.f}, ssg[2] = {0.f, 0.f};
       uint32_t v[2][16];
       uint32_t pk[G][8];  // this lane's pixel: G chunks of 16 channels (32 B each), packed bf16
@@ -479,7 +489,8 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   cluster_sync_all();  // the peer may still be reading our smem / arriving on our barriers
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(SDD_TMEM_BASE()), "n"(kTmemCols) : "memory");
+#undef SDD_TMEM_BASE
   }
 }
 
