@@ -508,6 +508,27 @@ def test_graph_equals_eager_and_philox_shard_invariance(S, dev):
     assert _rel(a.cpu(), xr) <= 5e-2
 
 
+def test_and_mode_philox_shard_invariance_and_three_models(S, dev):
+    """AND mode with in-kernel Philox: batch sharding changes no bit (the Gram pass regenerates z from the same global
+    counters), graph == eager, and three models keep all three log-densities equal along the trajectory."""
+    _, models = _models(S, dev, [0, 1, 2])
+    d = S.DDPM(8)
+    a, kap, lq = S.superposed_sample(models[:2], d, (4, 1, 32, 32), dev, seed=42, mode="and", return_trajectory=True)
+    b = S.superposed_sample(models[:2], d, (4, 1, 32, 32), dev, seed=42, mode="and", use_graph=False)
+    assert torch.equal(a, b)
+    lo = S.superposed_sample(models[:2], d, (2, 1, 32, 32), dev, seed=42, sample_offset=0, mode="and")
+    hi = S.superposed_sample(models[:2], d, (2, 1, 32, 32), dev, seed=42, sample_offset=2, mode="and")
+    assert torch.equal(torch.cat([lo, hi]), a)
+    assert torch.allclose(kap.sum(-1), torch.ones_like(kap.sum(-1)), atol=1e-5)
+    x3, k3, l3 = S.superposed_sample(models, d, (2, 1, 32, 32), dev, seed=7, mode="and", return_trajectory=True)
+    assert torch.isfinite(x3).all()
+    gap = (l3 - l3[..., :1]).abs().max() / l3.abs().max()
+    _report(test="and_three_models", logq_gap_rel=gap.item(), kappa_min=k3.min().item(), kappa_max=k3.max().item())
+    assert gap.item() <= 1e-5
+    with pytest.raises(S.SddError):
+        S.superposed_sample(models[:2], d, (2, 1, 32, 32), dev, seed=1, mode="xor")
+
+
 def test_size_independent_properties_at_full_size(S, dev):
     """At BASELINE config-2 size (128x128, batch 16): kappa rows sum to 1, logq[0] = 0, finite output,
     determinism across calls."""
@@ -542,3 +563,9 @@ def test_cli_end_to_end_from_reference_layout_checkpoints(S, dev, tmp_path):
     x = S.superposed_sample(models, S.DDPM(5), (2, 1, 32, 32), dev, seed=9)
     assert np.array_equal(z["samples"], x.cpu().numpy())
     assert os.path.getsize(tmp_path / "g.pgm") > 32 * 64
+    out2 = tmp_path / "s_and.npz"
+    assert cli.main(["--tb", str(root / "exp" / "run0" / "TB" / "ema_epoch3.pt"), "--pneumonia",
+                     str(root / "exp" / "run0" / "PNEUMONIA" / "ema_epoch3.pt"), "--batch", "2", "--resolution", "32",
+                     "--steps", "5", "--seed", "9", "--mode", "and", "--out", str(out2)]) == 0
+    x_and = S.superposed_sample(models, S.DDPM(5), (2, 1, 32, 32), dev, seed=9, mode="and")
+    assert np.array_equal(np.load(out2)["samples"], x_and.cpu().numpy())
