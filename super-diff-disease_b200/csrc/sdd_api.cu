@@ -473,8 +473,13 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
       conv_in_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
                                          sums(0), H, W);
     else
-      conv_in_mma_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
-                                             sums(0), H, W);
+    {
+      const int in_tiles = (int)(eg.x * eg.y * eg.z);
+      static const int in_cps = getenv("SDD_CIN_CPS") ? atoi(getenv("SDD_CIN_CPS")) : 2;  // persistent CTAs per SM
+      conv_in_mma_kernel<<<std::min(in_tiles, in_cps * num_sms()), 256, 0, st>>>(
+          xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0], sums(0), H, W, (int)eg.x, (int)eg.y,
+          in_tiles);
+    }
     SDD_LAUNCH_CHECK();
     // every tensor-core conv normalises + activates its own input (GroupNorm+SiLU fused on the operand path)
     SDD_TRY(launch_conv_tc3(ws.tm_halo[0][0], d0.tm_w2h, ws.act[0], ws.act[1], bias_time(0),

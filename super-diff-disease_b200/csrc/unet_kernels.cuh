@@ -183,85 +183,134 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
 }
 constexpr int kCinTS = 40;  // tile row stride in floats: the four tap groups of a warp's gather hit disjoint banks
 
-__global__ void __launch_bounds__(256) conv_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ xstats,
+// PERSISTENT (like conv_out1_mma_kernel): a CTA walks a contiguous range of (sample, 8 x 32 pixel) tiles; the weight
+// fragments are loaded once per CTA, the bias row / GroupNorm(1,1) scalars once per sample, and the next tile's x values
+// are already in flight (two registers per thread) while the current tile is multiplied and stored.  Two CTAs per SM
+// (~100 live registers: three at the 80-register cap spill).  Measured per 16 samples at 256^2: 48.4 -> 42.1 us.
+__global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ xstats,
                                                           const float* __restrict__ gn_w, const float* __restrict__ gn_b,
                                                           const float* __restrict__ w /*[64][9]*/, BiasRef bias,
                                                           __nv_bfloat16* __restrict__ out, long long* out_sums /*[B][4][2]*/,
-                                                          int H, int W) {
-  const int b = blockIdx.z;
-  const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
+                                                          int H, int W, int tiles_x, int tiles_y, int num_tiles) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = lane & 3, g = lane >> 2;
   __shared__ uint32_t tile[kCinTH + 2][kCinTS];  // silu(GroupNorm(1,1)(x)) as TF32 bit patterns, 1-pixel halo
-  const float mean = xstats[b * 2], rstd = xstats[b * 2 + 1];
-  const float ga = rstd * gn_w[0], gb = gn_b[0] - mean * rstd * gn_w[0];
-  for (int i = tid; i < (kCinTH + 2) * (kCinTW + 2); i += 256) {
-    const int r = i / (kCinTW + 2), c = i - r * (kCinTW + 2);
-    const int h = h0 + r - 1, ww = w0 + c - 1;
-    float v = 0.f;
-    if (h >= 0 && h < H && ww >= 0 && ww < W) v = silu_f(fmaf(x[((size_t)b * H + h) * W + ww], ga, gb));
-    tile[r][c] = to_tf32(v);
-  }
+  __shared__ float red[2][8][4][2];
+  constexpr int kTileElems = (kCinTH + 2) * (kCinTW + 2);  // 340: at most two per thread
+
   // B fragments: k-step 0 holds taps t and t+4, k-step 1 only tap 8 (lane t == 0); column n = g of n-tile j
   uint32_t bw0[8], bw1[8], bw2[8];
-  float bv[16];
-  const float* bp = bias_ptr(bias, b);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = (g >> 1) * 16 + j * 2 + (g & 1);
     bw0[j] = to_tf32(w[ch * 9 + t]);
     bw1[j] = to_tf32(w[ch * 9 + t + 4]);
     bw2[j] = t == 0 ? to_tf32(w[ch * 9 + 8]) : 0u;
-    bv[2 * j] = bp[t * 16 + 2 * j];
-    bv[2 * j + 1] = bp[t * 16 + 2 * j + 1];
   }
   // tile-relative offsets of this lane's taps: tap k -> (ky, kx) = (k / 3, k % 3)
   const int o0 = (t / 3) * kCinTS + (t % 3), o1 = ((t + 4) / 3) * kCinTS + ((t + 4) % 3), o2 = 2 * kCinTS + 2;
-  __syncthreads();
+  const float gw = gn_w[0], gbias = gn_b[0];
 
-  float s = 0.f, ss = 0.f;
+  auto tile_coords = [&](int tl, int& b, int& h0, int& w0) {
+    const int per = tiles_x * tiles_y;
+    b = tl / per;
+    const int r = tl - b * per;
+    const int ty = r / tiles_x;
+    h0 = ty * kCinTH; w0 = (r - ty * tiles_x) * kCinTW;
+  };
+  // raw x of a tile's halo box: element i (and i + 256) of the 10 x 34 box; NaN marks "outside the image"
+  auto load_raw = [&](int b, int h0, int w0, float (&v)[2]) {
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int mt = warp * 2 + k;               // 16 m-tiles: image row mt/2 of the tile, columns (mt%2)*16 .. +15
-    const int r = mt >> 1, c = (mt & 1) * 16 + g;
-    const uint32_t* tp = &tile[r][c];
-    const uint32_t a0[4] = {tp[o0], tp[o0 + 8], tp[o1], tp[o1 + 8]};          // rows g / g+8, taps t / t+4
-    const uint32_t a1[4] = {t == 0 ? tp[o2] : 0u, t == 0 ? tp[o2 + 8] : 0u, 0u, 0u};  // tap 8
-    float d[8][4];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      d[j][0] = bv[2 * j]; d[j][1] = bv[2 * j + 1]; d[j][2] = bv[2 * j]; d[j][3] = bv[2 * j + 1];
-      mma_tf32_1688(d[j], a0, bw0[j], bw1[j]);
-      mma_tf32_1688(d[j], a1, bw2[j], 0u);
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * 256;
+      const int r = i / (kCinTW + 2), c = i - r * (kCinTW + 2);
+      const int h = h0 + r - 1, ww = w0 + c - 1;
+      const bool ok = i < kTileElems && h >= 0 && h < H && ww >= 0 && ww < W;
+      v[k] = ok ? __ldg(x + ((size_t)b * H + h) * W + ww) : __int_as_float(0x7fc00000);
     }
-    const int h = h0 + r;
+  };
+  auto store_tile = [&](const float (&v)[2], float ga, float gb) {
 #pragma unroll
-    for (int rh = 0; rh < 2; ++rh) {
-      const int ww = w0 + c + 8 * rh;
-      if (h < H && ww < W) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v0 = d[j][2 * rh], v1 = d[j][2 * rh + 1];
-          s += v0 + v1;
-          ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss);
-          pk[j] = pack_bf16x2(v0, v1);
-        }
-        st_global_v8(out + (((size_t)b * H + h) * W + ww) * 64 + t * 16, pk);
+    for (int k = 0; k < 2; ++k) {
+      const int i = tid + k * 256;
+      if (i < kTileElems) {
+        const int r = i / (kCinTW + 2), c = i - r * (kCinTW + 2);
+        const float val = (v[k] != v[k]) ? 0.f : silu_f(fmaf(v[k], ga, gb));  // zero padding AFTER the activation
+        tile[r][c] = to_tf32(val);
       }
     }
-  }
-  // this lane's channels are GroupNorm group t: sum over the 8 lanes sharing t, then over the 8 warps (fixed order)
-  s += __shfl_xor_sync(0xffffffffu, s, 4);   ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-  s += __shfl_xor_sync(0xffffffffu, s, 8);   ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-  s += __shfl_xor_sync(0xffffffffu, s, 16);  ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-  __shared__ float red[8][4][2];
-  if (lane < 4) { red[warp][lane][0] = s; red[warp][lane][1] = ss; }
-  __syncthreads();
-  if (tid < 8) {
-    float acc = 0.f;
-    for (int wq = 0; wq < 8; ++wq) acc += red[wq][tid >> 1][tid & 1];
-    gn_red_add(out_sums + (size_t)b * 8 + tid, acc);
+  };
+
+  int tl = (int)(((long long)blockIdx.x * num_tiles) / gridDim.x);
+  const int tile_end = (int)(((long long)(blockIdx.x + 1) * num_tiles) / gridDim.x);
+  if (tl >= tile_end) return;
+  int b, h0, w0;
+  tile_coords(tl, b, h0, w0);
+  int cur_b = -1;
+  float ga = 0.f, gb = 0.f;
+  float bv[16];
+  float raw[2];
+  load_raw(b, h0, w0, raw);
+  int it = 0;
+  for (; tl < tile_end; ++tl, ++it) {
+    if (b != cur_b) {
+      const float mean = xstats[b * 2], rstd = xstats[b * 2 + 1];
+      ga = rstd * gw; gb = gbias - mean * rstd * gw;
+      const float* bp = bias_ptr(bias, b);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) bv[j] = bp[t * 16 + j];
+      cur_b = b;
+    }
+    store_tile(raw, ga, gb);
+    // next tile's coordinates and raw values (in flight during the MMAs and stores below)
+    int nb = b, nh0 = h0, nw0 = w0;
+    if (tl + 1 < tile_end) { tile_coords(tl + 1, nb, nh0, nw0); load_raw(nb, nh0, nw0, raw); }
+    __syncthreads();  // tile complete
+
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int mt = warp * 2 + k;               // 16 m-tiles: image row mt/2 of the tile, columns (mt%2)*16 .. +15
+      const int r = mt >> 1, c = (mt & 1) * 16 + g;
+      const uint32_t* tp = &tile[r][c];
+      const uint32_t a0[4] = {tp[o0], tp[o0 + 8], tp[o1], tp[o1 + 8]};          // rows g / g+8, taps t / t+4
+      const uint32_t a1[4] = {t == 0 ? tp[o2] : 0u, t == 0 ? tp[o2 + 8] : 0u, 0u, 0u};  // tap 8
+      float d[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        d[j][0] = bv[2 * j]; d[j][1] = bv[2 * j + 1]; d[j][2] = bv[2 * j]; d[j][3] = bv[2 * j + 1];
+        mma_tf32_1688(d[j], a0, bw0[j], bw1[j]);
+        mma_tf32_1688(d[j], a1, bw2[j], 0u);
+      }
+      const int h = h0 + r;
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int ww = w0 + c + 8 * rh;
+        if (h < H && ww < W) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v0 = d[j][2 * rh], v1 = d[j][2 * rh + 1];
+            s += v0 + v1;
+            ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss);
+            pk[j] = pack_bf16x2(v0, v1);
+          }
+          st_global_v8(out + (((size_t)b * H + h) * W + ww) * 64 + t * 16, pk);
+        }
+      }
+    }
+    // this lane's channels are GroupNorm group t: sum over the 8 lanes sharing t, then over the 8 warps (fixed order)
+    s += __shfl_xor_sync(0xffffffffu, s, 4);   ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 8);   ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);  ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+    if (lane < 4) { red[it & 1][warp][lane][0] = s; red[it & 1][warp][lane][1] = ss; }
+    __syncthreads();  // all reads of `tile` done (the next iteration overwrites it); red[it & 1] complete
+    if (tid < 8) {
+      float acc = 0.f;
+      for (int wq = 0; wq < 8; ++wq) acc += red[it & 1][wq][tid >> 1][tid & 1];
+      gn_red_add(out_sums + (size_t)b * 8 + tid, acc);
+    }
+    b = nb; h0 = nh0; w0 = nw0;
   }
 }
 
