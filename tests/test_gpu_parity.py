@@ -385,6 +385,28 @@ def test_k5_superposed_two_models_matches_oracle(S, dev, T, shape):
     assert rel <= 5e-2 and ek <= 5e-2 and el <= 2e-2
 
 
+@pytest.mark.parametrize("M,shape,temperature,use_bias", [(3, (1, 1, 32, 24), 1.0, False), (2, (3, 1, 48, 16), 0.5, True),
+                                                          (4, (2, 1, 16, 40), 2.0, True)])
+def test_superposed_ragged_shapes_models_temperature_bias(S, dev, M, shape, temperature, use_bias):
+    """Edge cases of the superposed sampler against the oracle: non-square images (odd tile counts: the 2-CTA conv pads
+    the last pair with a dummy tile), batch 1 and 3, two to four models, temperature and per-model logit bias."""
+    params, models = _models(S, dev, list(range(M)))
+    T = 10
+    g = torch.Generator().manual_seed(sum(shape) + M)
+    stack = torch.randn((T,) + shape, generator=g)
+    bias = torch.linspace(-0.3, 0.4, M) if use_bias else None
+    xr, kr, lr = O.superposed_sample(params, O.Schedule(T), stack, temperature=temperature, bias=bias)
+    x, kap, lq = S.superposed_sample(models, S.DDPM(T), shape, dev, noise=stack.to(dev), return_trajectory=True,
+                                     temperature=temperature, bias=bias)
+    rel = _rel(x.cpu(), xr)
+    ek = (kap.cpu() - kr).abs().max().item()
+    el = ((lq.cpu() - lr).abs().max() / lr.abs().max()).item()
+    _report(test="superposed_ragged", M=M, shape=list(shape), temperature=temperature, bias=use_bias, x_rel_l2=rel,
+            kappa_abs=ek, logq_rel=el)
+    assert rel <= 5e-2 and ek <= 5e-2 and el <= 2e-2
+    assert torch.allclose(kap.sum(-1), torch.ones_like(kap[..., 0]), atol=1e-6)
+
+
 @pytest.mark.parametrize("T,shape", [(4, (2, 1, 256, 256)), (2, (1, 1, 512, 512))])
 def test_superposed_matches_oracle_at_baseline_resolutions(S, dev, T, shape):
     """BASELINE configs[2] / configs[3] resolutions (256^2, 512^2) at a batch and step count the CPU oracle finishes in

@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python bench.py > gpurun_out/bench_full.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_full.log | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['clocks'], d['roofline']['frac'], d['roofline_update']['frac'], d['roofline_update']['noise_tensor_variant']['frac'], d['whole_path_tensor_frac_of_sustained'], d['cpu_baseline']['value'])"
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-200
+timeout 600 python -m pytest tests -m gpu -q --timeout 120 -x -k "ragged" > gpurun_out/pytest_rag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_rag.log; grep "PARITY.*ragged" gpurun_out/pytest_rag.log | cut -c1-220
