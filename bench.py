@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--diffusion-steps", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone roofline legs (ncu launch lists)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -257,7 +258,7 @@ def main():
     # ---- roofline legs: the two roofline kernels timed ALONE (burst-peak denominators), before the long timed region
     # heats the board into its power cap (measured after it, the same launches read 4-8 % lower and vary run to run)
     roof = None
-    if rank == 0:
+    if rank == 0 and not args.no_roofline:
         chunk = int(os.environ.get("SDD_CHUNK", "0")) or max(1, min(B, (1536 << 20) // (R * R * 128 * 2)))
         conv_roofline(S, dev, R, chunk, iters=3)  # warm-up: module load, attributes, clocks
         conv_tf, conv_ms = conv_roofline(S, dev, R, chunk)
@@ -326,6 +327,9 @@ def main():
 
     if rank == 0:
         hbm, tf_burst, tf_sust, src = peaks()
+        if roof is None:  # --no-roofline (launch-list runs): the line carries no roofline claim
+            nan = float("nan")
+            roof = (max(1, min(B, (1536 << 20) // (R * R * 128 * 2))), nan, nan, nan, nan, nan, nan)
         chunk, conv_tf, conv_ms, upd_gbs, upd_ms, upd_gbs_n, upd_ms_n = roof
         conv_traffic, upd_traffic = ncu_traffic()
         if not (B == 64 and R == 256 and chunk == 64):
