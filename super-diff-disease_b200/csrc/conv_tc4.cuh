@@ -245,6 +245,23 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed_remote(tempty_bar(acc), 0);  // orders TMEM reads only, not the stores
+      // (The statistics come BEFORE the stores: behind them, their first instruction had to wait for the store unit to read
+      // the 256-bit stores' data registers it reuses -- a write-after-read stall worth 9 % of the epilogue's samples.)
+      // warp reduction of (sg0, ssg0, sg1, ssg1) in 6 shuffles: halve the value count while halving the lanes.
+      // lane bit 4 selects the group it keeps, bit 3 the statistic; bits 2..0 are summed out.
+      {
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        const float keep_s = up16 ? sg[1] : sg[0], keep_ss = up16 ? ssg[1] : ssg[0];
+        const float send_s = up16 ? sg[0] : sg[1], send_ss = up16 ? ssg[0] : ssg[1];
+        const float s2 = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 16);
+        const float ss2 = keep_ss + __shfl_xor_sync(0xffffffffu, send_ss, 16);
+        float val = (up8 ? ss2 : s2) + __shfl_xor_sync(0xffffffffu, up8 ? s2 : ss2, 8);
+        val += __shfl_xor_sync(0xffffffffu, val, 4);
+        val += __shfl_xor_sync(0xffffffffu, val, 2);
+        val += __shfl_xor_sync(0xffffffffu, val, 1);
+        if ((lane & 7) == 0 && valid && !(a.dbg & 8) && a.out_sums)
+          gn_red_add(a.out_sums + ((size_t)n * 4 + hcol * 2 + (lane >> 4)) * 2 + ((lane >> 3) & 1), val);
+      }
       if (do_store) {
         // G x G transpose of 32-byte chunks inside each group of G lanes (G consecutive pixels of one image row): lane j
         // of a group ends up with chunk j of all G pixels, so one store instruction writes G*32 contiguous bytes per
@@ -271,21 +288,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       if (e == 0 && lane == 0) SDD_TRACE4(3, it, 1);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      // warp reduction of (sg0, ssg0, sg1, ssg1) in 6 shuffles: halve the value count while halving the lanes.
-      // lane bit 4 selects the group it keeps, bit 3 the statistic; bits 2..0 are summed out.
-      {
-        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
-        const float keep_s = up16 ? sg[1] : sg[0], keep_ss = up16 ? ssg[1] : ssg[0];
-        const float send_s = up16 ? sg[0] : sg[1], send_ss = up16 ? ssg[0] : ssg[1];
-        const float s2 = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 16);
-        const float ss2 = keep_ss + __shfl_xor_sync(0xffffffffu, send_ss, 16);
-        float val = (up8 ? ss2 : s2) + __shfl_xor_sync(0xffffffffu, up8 ? s2 : ss2, 8);
-        val += __shfl_xor_sync(0xffffffffu, val, 4);
-        val += __shfl_xor_sync(0xffffffffu, val, 2);
-        val += __shfl_xor_sync(0xffffffffu, val, 1);
-        if ((lane & 7) == 0 && valid && !(a.dbg & 8) && a.out_sums)
-          gn_red_add(a.out_sums + ((size_t)n * 4 + hcol * 2 + (lane >> 4)) * 2 + ((lane >> 3) & 1), val);
-      }
       if (e == 0 && lane == 0) SDD_TRACE4(3, it, 2);
     }
   } else {

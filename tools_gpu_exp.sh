@@ -1,5 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-RED="--batch 16 --diffusion-steps 3 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-roofline"
-timeout 600 python bench.py $RED > gpurun_out/plain.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 200 --csv --log-file gpurun_out/launches.csv python bench.py $RED > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+for V in A B A B; do
+cp tools/_lib$V.so super-diff-disease_b200/libsdd_b200.so
+echo "variant $V"
+CHUNK=64 QUICK=1 TRACE=0 timeout 300 python tools/conv_exp.py 2>&1 | grep -v "timed out" | grep -- "->" | cut -c1-60
+done
