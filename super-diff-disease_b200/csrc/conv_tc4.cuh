@@ -304,7 +304,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int grp = tt >> 7, tg = tt & 127;  // group, thread in group
     const int piece = tg & 7, col = tg >> 3; // col 0..15
     __shared__ __align__(16) float s_ga[2][128], s_gb[2][128];
-    const bool fuse = (a.in_sums != nullptr) || (a.in_meanrstd != nullptr);
+    const bool fuse = (a.in_sums != nullptr) || (a.in_meanrstd != nullptr) || (a.in_ab != nullptr);
     const uint8_t* in_bytes = reinterpret_cast<const uint8_t*>(a.in);
     const int tiles_h = a.H / kTileH;
     // vector i <-> halo row r = col + 16 i (pixel (r / 10, r % 10) of the 18 x 10 box); r & 7 == col & 7 for every i
@@ -393,6 +393,20 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     while (item < my_items) {
       // ---- GroupNorm scale / shift: this group's chunk is fixed, so the registers only change with the sample
+      if (fuse && c.n != cur_n && a.in_ab) {
+        // precomputed by gn_scale_shift_kernel: this thread's eight channels, four 16-byte loads, no barrier
+        const float* pa = a.in_ab + ((size_t)c.n * a.Cin + kc * 64 + piece * 8);
+        const float* pb = pa + (size_t)a.B * a.Cin;
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          const float4 x = __ldg(reinterpret_cast<const float4*>(pa + 2 * j));
+          const float4 y = __ldg(reinterpret_cast<const float4*>(pb + 2 * j));
+          ga2[j] = pack_f32x2(x.x, x.y); ga2[j + 1] = pack_f32x2(x.z, x.w);
+          gb2[j] = pack_f32x2(y.x, y.y); gb2[j + 1] = pack_f32x2(y.z, y.w);
+        }
+        cur_n = c.n;
+      }
+      // (no precomputed table -- A/B and bring-up only: rebuild them in the group)
       if (fuse && c.n != cur_n) {
         named_bar_sync(2 + grp, 128);  // previous readers of this group's s_ga/s_gb are done
         if (tg < 64) {

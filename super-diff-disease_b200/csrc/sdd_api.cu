@@ -209,6 +209,7 @@ struct GnInput3 {  // GroupNorm(4, Cin) + SiLU of the conv's input: fixed-point 
   const float* meanrstd;
   const float* gamma;
   const float* beta;
+  float* ab = nullptr;  // scratch [2][B][Cin] for gn_scale_shift_kernel (generation 4+); null: the kernel rebuilds the values
 };
 
 static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2, const __nv_bfloat16* in,
@@ -232,6 +233,14 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   ConvTc3Args a;
   a.in = in; a.out = out; a.bias = bias;
   a.in_sums = gi.sums; a.in_meanrstd = gi.meanrstd; a.in_gamma = gi.gamma; a.in_beta = gi.beta;
+  a.in_ab = nullptr;
+  static const bool no_ab = getenv("SDD_CONV_NO_AB") != nullptr;  // A/B: in-kernel scale / shift
+  if (gi.ab && (gi.sums || gi.meanrstd) && !no_ab && getenv("SDD_CONV_V3") == nullptr) {
+    gn_scale_shift_kernel<<<B, Cin, 0, st>>>(gi.sums, gi.meanrstd, gi.gamma, gi.beta,
+                                             (double)H * (double)W * (double)(Cin / 4), kGnEps, gi.ab, B, Cin);
+    SDD_LAUNCH_CHECK();
+    a.in_ab = gi.ab;
+  }
   a.out_sums = out_sums;
   a.B = B; a.H = H; a.W = W; a.Cin = Cin;
   a.tiles_w = W / kTileW;
@@ -349,11 +358,12 @@ struct Workspace {
   int* counters = nullptr;
   long long* gnsums = nullptr;  // 9 x [cap_b][4][2] fixed-point GroupNorm sums, one slab per GroupNorm layer (common.cuh)
   float* xstats = nullptr;    // [cap_b][2] (used when the caller has no stats of x)
+  float* gn_ab = nullptr;     // [2][cap_b][128] fused GroupNorm+SiLU scale / shift of the layer being launched
   CUtensorMap tm_act[2][2];   // [buffer][Cin == 128], v1 box (64, 8, 18)
   CUtensorMap tm_halo[2][2];  // v2 halo box (64, 10, 18)
   void release() {
     cudaFree(act[0]); cudaFree(act[1]); cudaFree(e1); cudaFree(partials); cudaFree(counters);
-    cudaFree(gnsums); cudaFree(xstats);
+    cudaFree(gnsums); cudaFree(xstats); cudaFree(gn_ab);
     int64_t g = generation;
     *this = Workspace();
     generation = g;
@@ -402,6 +412,7 @@ int ensure_workspace(sdd_unet* u, int B, int H, int W) {
   SDD_CUDA(cudaMalloc(&ws.counters, (size_t)need * sizeof(int)));
   SDD_CUDA(cudaMemset(ws.counters, 0, (size_t)need * sizeof(int)));
   SDD_CUDA(cudaMalloc(&ws.gnsums, (size_t)kGnLayers * need * 8 * sizeof(long long)));
+  SDD_CUDA(cudaMalloc(&ws.gn_ab, (size_t)2 * need * 128 * sizeof(float)));
   SDD_CUDA(cudaMalloc(&ws.xstats, (size_t)need * 2 * sizeof(float)));
   for (int bi = 0; bi < 2; ++bi) {
     SDD_TRY(make_act_map(&ws.tm_act[bi][0], ws.act[bi], need, H, W, 64));
@@ -483,15 +494,15 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     SDD_LAUNCH_CHECK();
     // every tensor-core conv normalises + activates its own input (GroupNorm+SiLU fused on the operand path)
     SDD_TRY(launch_conv_tc3(ws.tm_halo[0][0], d0.tm_w2h, ws.act[0], ws.act[1], bias_time(0),
-                            GnInput3{sums(0), nullptr, d0.gn2_w, d0.gn2_b}, sums(1), nb, H, W, 64, 64, st));
+                            GnInput3{sums(0), nullptr, d0.gn2_w, d0.gn2_b, ws.gn_ab}, sums(1), nb, H, W, 64, 64, st));
     int cur = 1, gi = 1;
     for (int bi = 1; bi <= 3; ++bi) {
       const BlockParams& p = u->blk[bi];
       SDD_TRY(launch_conv_tc3(ws.tm_halo[cur][p.cin == 128], p.tm_w1h, ws.act[cur], ws.act[cur ^ 1], bias_const(p.conv1_b),
-                              GnInput3{sums(gi), nullptr, p.gn1_w, p.gn1_b}, sums(gi + 1), nb, H, W, p.cin, p.cout, st));
+                              GnInput3{sums(gi), nullptr, p.gn1_w, p.gn1_b, ws.gn_ab}, sums(gi + 1), nb, H, W, p.cin, p.cout, st));
       cur ^= 1; ++gi;
       SDD_TRY(launch_conv_tc3(ws.tm_halo[cur][p.cout == 128], p.tm_w2h, ws.act[cur], ws.act[cur ^ 1], bias_time(bi),
-                              GnInput3{sums(gi), nullptr, p.gn2_w, p.gn2_b}, sums(gi + 1), nb, H, W, p.cout, p.cout, st));
+                              GnInput3{sums(gi), nullptr, p.gn2_w, p.gn2_b, ws.gn_ab}, sums(gi + 1), nb, H, W, p.cout, p.cout, st));
       cur ^= 1; ++gi;
     }
     // ups.1: GroupNorm(4,64)+SiLU fused into the 64->1 conv (mma.sync), then GN(1,1)+SiLU fused into the 1->1 conv
@@ -1096,7 +1107,9 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
   const char* trace_path = getenv("SDD_CONV_TRACE");
   if (trace_path && impl != 0) { cudaMalloc(&trace, 2 * 6 * 64 * 4 * sizeof(long long)); }
   if (rc == SDD_OK && cudaMalloc(&osums, (size_t)B * 8 * sizeof(long long)) != cudaSuccess) rc = SDD_ENOMEM;
-  if (impl == 2) gi = GnInput3{nullptr, gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128};
+  float* gn_ab = nullptr;
+  if (impl == 2 && rc == SDD_OK && cudaMalloc(&gn_ab, (size_t)2 * B * Cin * sizeof(float)) != cudaSuccess) rc = SDD_ENOMEM;
+  if (impl == 2) gi = GnInput3{nullptr, gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128, gn_ab};
   if (rc == SDD_OK && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) rc = SDD_ECUDA;
   BiasRef br{bias, nullptr, 0, 0};
   double total = 0.0;
@@ -1134,7 +1147,7 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
     cudaFree(trace);
   }
   cudaFree(osums);
-  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr); cudaFree(gin);
+  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr); cudaFree(gin); cudaFree(gn_ab);
   if (rc == SDD_OK) *ms_host = (float)(total / iters);
   return rc;
 }
@@ -1251,17 +1264,21 @@ int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const 
     rc = make_act_map(&tmA, act_raw, B, H, W, Cin, true);
   }
   if (rc == SDD_OK) rc = make_wt_map2(&tmB, wt, Cout, Cin);
+  float* gn_ab = nullptr;
+  if (rc == SDD_OK && in_meanrstd && cudaMalloc(&gn_ab, (size_t)2 * B * Cin * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc failed"); rc = SDD_ENOMEM;
+  }
   if (rc == SDD_OK)
     rc = launch_conv_tc3(tmA, tmB, (const __nv_bfloat16*)act_raw, (__nv_bfloat16*)out,
-                         BiasRef{bias, nullptr, 0, bias_batch_stride}, GnInput3{nullptr, in_meanrstd, in_gamma, in_beta},
-                         osums, B, H, W, Cin, Cout, st);
+                         BiasRef{bias, nullptr, 0, bias_batch_stride},
+                         GnInput3{nullptr, in_meanrstd, in_gamma, in_beta, gn_ab}, osums, B, H, W, Cin, Cout, st);
   if (rc == SDD_OK && gn_meanrstd) {
     gn_sums_to_meanrstd_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(osums, gn_meanrstd, B * 4,
                                                                    (double)H * (double)W * (double)(Cout / 4), kGnEps);
     ++g_launches;
   }
   cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(wt); cudaFree(osums);
+  cudaFree(wt); cudaFree(osums); cudaFree(gn_ab);
   if (rc != SDD_OK) return rc;
   if (e != cudaSuccess) { set_error(std::string("conv3x3_fused: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
   return SDD_OK;
