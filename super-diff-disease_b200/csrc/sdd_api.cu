@@ -249,11 +249,12 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   a.num_pairs = (a.num_tiles + 1) / 2;
   a.stages = conv_tc3_stages(Cout, Cin);
   a.raw_slots = 0;
-  // contiguous tile ranges: measured at the sampler's 64-sample chunk (us, strided -> contiguous): 64->64 399 -> 363,
-  // 64->128 545 -> 528, but 128->64 619 -> 610 / 315 -> 328 at 32 samples and 128->128 899 -> 905: Cin = 64 layers only
+  // contiguous tile ranges: before the scale / shift table they paid off for both Cin = 64 layers (64->64 399 -> 363 us,
+  // 64->128 545 -> 528 us per 64-sample chunk: the per-sample rebuild nearly vanished) and cost the Cin = 128 layers
+  // (128->128 899 -> 905); with the table (same-box A/B): 64->64 382 -> 373, 64->128 508 -> 515.  So: 64->64 only.
   // (SDD_CONV_CONTIG = 0 / 1 forces it off / on everywhere for A/B)
   static const int contig_env = getenv("SDD_CONV_CONTIG") ? atoi(getenv("SDD_CONV_CONTIG")) : -1;
-  a.contig = contig_env >= 0 ? contig_env : (Cin == 64 ? 1 : 0);
+  a.contig = contig_env >= 0 ? contig_env : ((Cin == 64 && Cout == 64) ? 1 : 0);
   static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 1;  // v4: TMA L2 prefetch of a loader group's item after next; measured +3..6 % (v3's paced prefetch warp: no effect)
   a.prefetch = prefetch;
   a.dbg = dbg;
