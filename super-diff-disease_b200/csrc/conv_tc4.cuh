@@ -234,25 +234,38 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_wait();
         if (st + 1 < G) tmem_ld_32x16(taddr + (uint32_t)((st + 1) * 16), v[(st + 1) & 1]);
         const uint32_t* vv = v[st & 1];
-        float f[16];
+        // packed fp32 pairs (FADD2 / FFMA2): bias add, sum and sum of squares at two columns per instruction -- the
+        // epilogue is bound by its own instruction stream on the 64-channel layers
+        uint64_t f2[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          f[4 * j] = __uint_as_float(vv[4 * j]) + b4[j].x;         f[4 * j + 1] = __uint_as_float(vv[4 * j + 1]) + b4[j].y;
-          f[4 * j + 2] = __uint_as_float(vv[4 * j + 2]) + b4[j].z; f[4 * j + 3] = __uint_as_float(vv[4 * j + 3]) + b4[j].w;
+          f2[2 * j] = add_f32x2(pack_f32x2(__uint_as_float(vv[4 * j]), __uint_as_float(vv[4 * j + 1])),
+                                pack_f32x2(b4[j].x, b4[j].y));
+          f2[2 * j + 1] = add_f32x2(pack_f32x2(__uint_as_float(vv[4 * j + 2]), __uint_as_float(vv[4 * j + 3])),
+                                    pack_f32x2(b4[j].z, b4[j].w));
         }
-        // two GroupNorm groups per warp; 4 independent partial accumulators per statistic
+        // two GroupNorm groups per warp; two independent pair accumulators per statistic
         const int g = (st * 16 >= COLS / 2) ? 1 : 0;
-        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+        uint64_t p01 = f2[0], p23 = f2[1];
+        uint64_t r01 = fma_f32x2(f2[0], f2[0], 0ull), r23 = fma_f32x2(f2[1], f2[1], 0ull);
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          p0 += f[j]; p1 += f[j + 1]; p2 += f[j + 2]; p3 += f[j + 3];
-          r0 = fmaf(f[j], f[j], r0); r1 = fmaf(f[j + 1], f[j + 1], r1);
-          r2 = fmaf(f[j + 2], f[j + 2], r2); r3 = fmaf(f[j + 3], f[j + 3], r3);
+        for (int j = 2; j < 8; j += 2) {
+          p01 = add_f32x2(p01, f2[j]); p23 = add_f32x2(p23, f2[j + 1]);
+          r01 = fma_f32x2(f2[j], f2[j], r01); r23 = fma_f32x2(f2[j + 1], f2[j + 1], r23);
         }
-        sg[g] += (p0 + p1) + (p2 + p3);
-        ssg[g] += (r0 + r1) + (r2 + r3);
+        {
+          float a0, a1, a2, a3;
+          unpack_f32x2(add_f32x2(p01, p23), a0, a1);
+          unpack_f32x2(add_f32x2(r01, r23), a2, a3);
+          sg[g] += a0 + a1;
+          ssg[g] += a2 + a3;
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) pk[st][j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        for (int j = 0; j < 8; ++j) {
+          float lo, hi;
+          unpack_f32x2(f2[j], lo, hi);
+          pk[st][j] = pack_bf16x2(lo, hi);
+        }
       }
       tc_fence_before();
       __syncwarp();
