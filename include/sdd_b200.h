@@ -101,6 +101,15 @@ int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, 
  *   q, k, out: [BH][S][64];   vt: V TRANSPOSED, [BH][64][S].   head_dim == 64, S % 128 == 0 (32^2 = 1024, 16^2 = 256). */
 int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
                       float scale, void* stream);
+/* Self-attention BLOCK (same extension; oracle = oracle.attention_block):
+ *   out = x + W_o attention(q, k, v) + b_o,   [q | k | v] = GroupNorm(4, 128)(x) W_qkv^T + b_qkv,   2 heads of 64
+ * x, out: bf16 NHWC [B][S = H*W][128] (out may not alias x); gn_gamma / gn_beta fp32 [128]; w_qkv fp32 [384][128] (rows:
+ * q, k, v; within each, head h = rows 64h..64h+63), b_qkv [384]; w_out fp32 [128][128], b_out [128].  S % 128 == 0.
+ * GroupNorm statistics kernel -> projection GEMM (mma.sync, GroupNorm affine fused on load, head-split / V-transposed
+ * epilogue) -> sdd_attention_fwd -> projection GEMM (+ bias + residual).  Synchronises the stream (scratch is freed). */
+int sdd_attention_block_nhwc(const void* x, const float* gn_gamma, const float* gn_beta, const float* w_qkv,
+                             const float* b_qkv, const float* w_out, const float* b_out, void* out, int B, int S, int C,
+                             int heads, void* stream);
 /* `iters` back-to-back launches between one CUDA-event pair; *ms_host = mean launch duration. */
 int sdd_attention_profile(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
                           float scale, int iters, float* ms_host, void* stream);

@@ -36,6 +36,7 @@ SYMBOLS = {
     "sdd_superpose_update_and": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _u64, _i64, _i,
                                       _vp, _sz, _vp]),
     "sdd_attention_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp]),
+    "sdd_attention_block_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdd_attention_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _i, ctypes.POINTER(_f), _vp]),
     "sdd_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "sdd_mse_workspace": (_sz, []),

@@ -39,3 +39,29 @@ def attention_core(q, k, v, scale=None, *, v_is_transposed=False):
         _lib.check(_lib.lib().sdd_attention_fwd(qc.data_ptr(), kc.data_ptr(), vtc.data_ptr(), out.data_ptr(), B * Hh, S,
                                                 D, sc, _lib.stream_ptr(q.device)))
     return out
+
+
+@torch.no_grad()
+def attention_block(x, gn_weight, gn_bias, w_qkv, b_qkv, w_out, b_out, heads=2):
+    """out = x + proj(attention(q, k, v)) with [q|k|v] = GroupNorm(4, 128)(x) W_qkv^T + b_qkv (2 heads of 64).
+
+    x: bf16 CUDA NHWC [B, H, W, 128] (H*W % 128 == 0: 32^2, 16^2 ...); gn_weight / gn_bias fp32 [128];
+    w_qkv fp32 [384, 128], b_qkv [384]; w_out fp32 [128, 128], b_out [128].  Returns bf16 [B, H, W, 128].
+    Wraps sdd_attention_block_nhwc (GroupNorm statistics -> mma.sync projection with the GroupNorm affine fused on load
+    and a head-split / V-transposed epilogue -> fused tcgen05 attention -> projection + bias + residual)."""
+    _lib.require_cuda(x, "x")
+    if x.dtype != torch.bfloat16 or x.dim() != 4 or x.shape[-1] != 128:
+        raise _lib.SddError("x must be bfloat16 NHWC [B, H, W, 128]")
+    B, H, W, C = x.shape
+    dev = x.device
+    f32 = lambda t: torch.as_tensor(t, dtype=torch.float32, device=dev).contiguous()  # noqa: E731
+    gw, gb, wq, bq, wo, bo = (f32(t) for t in (gn_weight, gn_bias, w_qkv, b_qkv, w_out, b_out))
+    if tuple(wq.shape) != (3 * C, C) or tuple(wo.shape) != (C, C) or bq.numel() != 3 * C or bo.numel() != C:
+        raise _lib.SddError("w_qkv must be [384, 128], b_qkv [384], w_out [128, 128], b_out [128]")
+    xc = x.contiguous()
+    out = torch.empty_like(xc)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().sdd_attention_block_nhwc(xc.data_ptr(), gw.data_ptr(), gb.data_ptr(), wq.data_ptr(),
+                                                       bq.data_ptr(), wo.data_ptr(), bo.data_ptr(), out.data_ptr(), B,
+                                                       H * W, C, int(heads), _lib.stream_ptr(dev)))
+    return out

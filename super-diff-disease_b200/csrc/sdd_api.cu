@@ -15,6 +15,7 @@
 #include "update.cuh"
 #include "train_eval.cuh"
 #include "attention.cuh"
+#include "attention_block.cuh"
 
 namespace sdd {
 
@@ -764,6 +765,46 @@ int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, i
   attention_fwd_kernel<<<dim3((unsigned)(S / kAttnBM), (unsigned)BH), kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(
       tmQ, tmK, tmVt, a);
   SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+int sdd_attention_block_nhwc(const void* x, const float* gn_gamma, const float* gn_beta, const float* w_qkv,
+                             const float* b_qkv, const float* w_out, const float* b_out, void* out, int B, int S, int C,
+                             int heads, void* stream) {
+  SDD_CHECK(x && gn_gamma && gn_beta && w_qkv && b_qkv && w_out && b_out && out, "null argument");
+  SDD_CHECK(C == kAbC && heads == kAbHeads, "attention block supports C = 128 (2 heads of 64)");
+  SDD_CHECK(B > 0 && S >= kAttnBN && S % kAttnBN == 0, "S must be a positive multiple of 128");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t per = (size_t)B * S * kAbC;  // elements of one [B, S, 128] bf16 tensor
+  __nv_bfloat16* buf = nullptr; float* mr = nullptr;
+  if (cudaMalloc(&buf, 4 * per * sizeof(__nv_bfloat16)) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 8 * sizeof(float)) != cudaSuccess) {
+    cudaFree(buf); cudaFree(mr);
+    set_error("cudaMalloc failed"); return SDD_ENOMEM;
+  }
+  __nv_bfloat16 *q = buf, *k = buf + per, *vt = buf + 2 * per, *ao = buf + 3 * per;
+  int rc = SDD_OK;
+  gn_stats_nhwc_kernel<<<B * 4, 256, 0, st>>>((const __nv_bfloat16*)x, mr, S, kAbC);
+  ++g_launches;
+  AttnBlockGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.a = (const __nv_bfloat16*)x; g.w = w_qkv; g.bias = b_qkv; g.meanrstd = mr; g.gamma = gn_gamma; g.beta = gn_beta;
+  g.q = q; g.k = k; g.vt = vt; g.B = B; g.S = S;
+  attn_block_gemm_kernel<0><<<dim3((unsigned)((size_t)B * S / kAbRows), 3 * kAbC / 64), 128, 0, st>>>(g);
+  ++g_launches;
+  if (cudaGetLastError() != cudaSuccess) { set_error("attention block: qkv launch failed"); rc = SDD_ECUDA; }
+  if (rc == SDD_OK) rc = sdd_attention_fwd(q, k, vt, ao, B * kAbHeads, S, kAttnD, 0.125f, stream);
+  if (rc == SDD_OK) {
+    memset(&g, 0, sizeof(g));
+    g.a = ao; g.w = w_out; g.bias = b_out; g.resid = (const __nv_bfloat16*)x; g.out = (__nv_bfloat16*)out; g.B = B; g.S = S;
+    attn_block_gemm_kernel<1><<<dim3((unsigned)((size_t)B * S / kAbRows), kAbC / 64), 128, 0, st>>>(g);
+    ++g_launches;
+    if (cudaGetLastError() != cudaSuccess) { set_error("attention block: proj launch failed"); rc = SDD_ECUDA; }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(buf); cudaFree(mr);
+  if (rc != SDD_OK) return rc;
+  if (e != cudaSuccess) { set_error(std::string("attention block: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
   return SDD_OK;
 }
 
