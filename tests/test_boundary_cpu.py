@@ -146,3 +146,36 @@ def test_cli_checkpoint_layout_and_grid(tmp_path):
     assert raw.startswith(b"P5\n16 16\n255\n") and len(raw) == len(b"P5\n16 16\n255\n") + 256
     img = np.frombuffer(raw[-256:], dtype=np.uint8).reshape(16, 16)
     assert img[0, 0] == 0 and img[15, 7] == 255 and img[0, 8] == 0 and img[15, 15] == 255
+
+
+def test_hot_kernels_are_tcgen05_tma_sass():
+    """The built library's hot kernels really are Blackwell tensor-core / TMA code: the SASS of the product conv and the
+    attention kernel contains UTCHMMA (tcgen05.mma), UTMALDG (TMA tensor loads), LDTM (tcgen05.ld from TMEM) and UTCBAR
+    (tcgen05.commit); checked with cuobjdump, no GPU needed."""
+    import shutil
+    import subprocess
+    import collections
+    import re
+    import __graft_entry__ as G
+    lib = G.build()
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", lib], capture_output=True, text=True, check=True).stdout
+    cur, cnt = None, collections.defaultdict(collections.Counter)
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.search(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m and cur:
+            for key in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
+                if m.group(1).startswith(key):
+                    cnt[cur][key] += 1
+    conv = [f for f in cnt if "conv3x3_tc4_kernel" in f]
+    attn = [f for f in cnt if "attention_fwd_kernel" in f]
+    assert len(conv) >= 4 and len(attn) == 1
+    for f in conv + attn:
+        for key in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
+            assert cnt[f][key] > 0, (f, key)
