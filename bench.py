@@ -222,7 +222,6 @@ def main():
 
     import torch.distributed as dist
     import super_diff_disease_b200 as S
-    from oracle.superdiff_oracle import init_unet_params  # synthetic random-init weights only (not timed)
 
     if not torch.cuda.is_available():
         raise S.SddError("bench.py needs a B200: the product path has no CPU fallback")
@@ -236,9 +235,8 @@ def main():
     D = R * R
     models = []
     for i in range(M):
-        m = S.UNet()
-        m.load_state_dict(init_unet_params(i))
-        models.append(m.to(dev))
+        torch.manual_seed(i)  # random-init weights, PyTorch default init of the reference architecture
+        models.append(S.UNet().to(dev))
     ddpm = S.DDPM(T)
     lo = rank * B  # weak scaling: every rank samples its own B images, global ids [rank*B, (rank+1)*B)
     shape = (B, 1, R, R)
