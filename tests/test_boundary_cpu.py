@@ -42,6 +42,26 @@ def test_no_cpu_fallback():
         S.DDPM(4).sample(m, (1, 1, 16, 16), "cpu")
     with pytest.raises(S.SddError):
         S.superposed_sample([m, m], S.DDPM(4), (1, 1, 16, 16), "cpu", seed=0)
+    with pytest.raises(S.SddError):
+        S.superposed_sample([m, m], S.DDPM(4), (1, 1, 16, 16), "cpu", seed=0, mode="and")
+    with pytest.raises(S.SddError):
+        S.superposed_sample([m, m], S.DDPM(4), (1, 1, 16, 16), "cuda", seed=0, mode="xor")  # rejected before any GPU use
+    # the "next" rows have no CPU path either: N4 forward pieces, attention core / block
+    x0 = torch.zeros(2, 1, 16, 16)
+    with pytest.raises(S.SddError):
+        S.DDPM(4).q_sample(x0, torch.zeros(2, dtype=torch.long), torch.zeros_like(x0))
+    with pytest.raises(S.SddError):
+        S.DDPM(4).p_losses(m, x0, torch.zeros(2, dtype=torch.long))
+    q = torch.zeros(1, 1, 128, 64, dtype=torch.bfloat16)
+    with pytest.raises(S.SddError):
+        S.attention_core(q, q, q)
+    with pytest.raises(S.SddError):
+        S.attention_block(torch.zeros(1, 16, 16, 128, dtype=torch.bfloat16), torch.ones(128), torch.zeros(128),
+                          torch.zeros(384, 128), torch.zeros(384), torch.zeros(128, 128), torch.zeros(128))
+    # the C ABI itself refuses without an sm_100 device (every compute entry point starts with the device check)
+    L = S.lib()
+    assert L.sdd_attention_fwd(None, None, None, None, 1, 128, 64, 0.125, None) != 0
+    assert L.sdd_q_sample(None, None, None, None, None, 1, 4, None) != 0
 
 
 def test_product_does_not_import_oracle():
