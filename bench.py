@@ -4,9 +4,11 @@
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
   python bench.py --impl reference ...                     (the CPU path of the reference, oracle port)
 
-A bench "step" is ONE full sampling call: T reverse-diffusion steps, 2 UNets per step, batch 64 per
-GPU at 256x256 (BASELINE.json configs[2] on the reference UNet architecture).
-Prints ONE JSON line on rank 0.
+A bench "step" is ONE full sampling call: T reverse-diffusion steps, 2 UNets per step, at 256x256 with a GLOBAL batch of
+64 (BASELINE.json configs[2] on the reference UNet architecture; SURVEY.md section 8(d) c3: 64/32/16/8 samples per GPU
+at 1/2/4/8 GPUs = strong scaling, the default).  `--scaling weak` keeps `--batch` samples on every GPU instead.
+Other BASELINE configs: `--res 128 --diffusion-steps 100 --batch 16` (configs[1]); `--res 512 --diffusion-steps 1000
+--batch 32` on 8 GPUs (configs[3]).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -21,16 +23,21 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
-METRIC = "superposed samples/sec at 256^2 (2 UNets, 250 steps)"
 UNIT = "samples/s"
+
+
+def metric_name(args):
+    return f"superposed samples/sec at {args.res}^2 (2 UNets, {args.diffusion_steps} steps)"
+
+
 CONV_MAC_PER_PIXEL = 664713          # all 10 convs of one UNet forward
 MAC_128x128 = 147456                 # one 128->128 3x3 conv, per pixel
 
 
 def ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the two roofline kernels from the committed
-    `ncu --set full` captures (profiles/r1_final_ncu.md); taken at exactly the launch shapes timed below."""
-    p = os.path.join(ROOT, "profiles", "r1_final_traffic.json")
+    `ncu --set full` captures (profiles/r2_ncu.md); taken at exactly the launch shapes timed below."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(p):
         return None, None
     d = json.load(open(p))
@@ -52,8 +59,8 @@ class ClockSampler:
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, index):
-        self.index, self.samples, self.mask, self.max_mhz = index, [], 0, None
+    def __init__(self, index, period=0.2):
+        self.index, self.samples, self.mask, self.max_mhz, self.period = index, [], 0, None, period
         self._stop = threading.Event()
         self._t = None
         try:
@@ -72,7 +79,7 @@ class ClockSampler:
                 self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(self.period)
 
     def start(self):
         if self.nv:
@@ -89,14 +96,32 @@ class ClockSampler:
                 "reasons": [n for b, n in self.REASONS.items() if self.mask & b], "samples": len(s)}
 
 
-# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+# ----------------------------------------------------------------------------- CPU baseline (the reference on CPU)
 def cpu_reference_run(R, T, M, sample_B, n_steps, warm_steps=1):
-    """Time the oracle (the reference's UNet restated + our A7 oracle) on the host cores for a bounded
-    sample: sample_B images, n_steps of the T diffusion steps; returns (samples/s extrapolated, seconds)."""
+    """Time the reference's CPU path on the host cores for a bounded sample: sample_B images, n_steps of the T diffusion
+    steps.  The UNets are the REFERENCE'S OWN modules (baseline/_ref: src/models/unet.py, unmodified) and the schedule
+    its own DDPM when baseline/_ref is installed, else the oracle's restatement of them ("port"); the superposition
+    step around them is the oracle's (the reference has no code for it: src/sampling.py is 0 bytes).
+    Returns (samples/s extrapolated linearly in T, seconds of CPU work, kind)."""
+    from baseline import ref_loader
     from oracle import superdiff_oracle as O
     torch.set_num_threads(os.cpu_count())
     params = [O.init_unet_params(i) for i in range(M)]
-    sched = O.Schedule(T)
+    ref = ref_loader.load()
+    if ref is not None:
+        RefUNet, RefDDPM = ref
+        nets = []
+        for p in params:
+            n = RefUNet()
+            n.load_state_dict(p, strict=True)
+            nets.append(n.eval())
+        sched = RefDDPM(num_timesteps=T)
+        fwd = [lambda x, tt, n=n: n(x, tt) for n in nets]
+        kind = "reference"
+    else:
+        sched = O.Schedule(T)
+        fwd = [lambda x, tt, p=p: O.unet_forward(p, x, tt) for p in params]
+        kind = "port"
     g = torch.Generator().manual_seed(0)
     x = torch.randn((sample_B, 1, R, R), generator=g)
     logq = torch.zeros(sample_B, M)
@@ -107,12 +132,12 @@ def cpu_reference_run(R, T, M, sample_B, n_steps, warm_steps=1):
             z = torch.randn(x.shape, generator=g)
             t0 = time.perf_counter()
             tt = torch.full((sample_B,), t, dtype=torch.long)
-            eps = [O.unet_forward(p, x, tt) for p in params]
+            eps = [f(x, tt) for f in fwd]
             x, logq, _ = O.superpose_step(x, eps, z, logq, sched.alphas[t], sched.alpha_bars[t], sched.betas[t])
             if k >= warm_steps:
                 dt += time.perf_counter() - t0
     per_step = dt / n_steps
-    return sample_B / (per_step * T), dt
+    return sample_B / (per_step * T), dt, kind
 
 
 def run_reference_arm(args, rank, world):
@@ -120,30 +145,43 @@ def run_reference_arm(args, rank, world):
         return
     R, T, M = args.res, args.diffusion_steps, 2
     sB, sN = 4, 4
+    kind = "port"
     for _ in range(args.warmup):
         cpu_reference_run(R, T, M, sB, 1, warm_steps=0)
     vals, t0 = [], time.perf_counter()
     for _ in range(args.steps):
-        v, _ = cpu_reference_run(R, T, M, sB, sN, warm_steps=0)
+        v, _, kind = cpu_reference_run(R, T, M, sB, sN, warm_steps=0)
         vals.append(v)
     wall = time.perf_counter() - t0
     v = sum(vals) / len(vals)
-    sample = f"B={sB}, {sN} of {T} diffusion steps per bench step, extrapolated linearly in T"
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    sample = (f"B={sB}, {sN} of {T} diffusion steps per bench step, extrapolated linearly in T; UNet / DDPM = "
+              + ("the reference's own modules (baseline/_ref)" if kind == "reference" else "oracle restatement")
+              + ", superposition step = oracle (no reference code exists)")
+    line = {"impl": "reference", "metric": metric_name(args), "value": v, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def per_gpu_batch(args, world):
+    if args.scaling == "weak":
+        return args.batch
+    if args.batch % world:
+        raise SystemExit(f"--scaling strong needs --batch ({args.batch}) divisible by the GPU count ({world})")
+    return args.batch // world
+
+
 def workload_config(args, world):
-    which = {(128, 100): "BASELINE configs[1]", (256, 250): "BASELINE configs[2]",
-             (512, 1000): "BASELINE configs[3] per-GPU shard"}.get((args.res, args.diffusion_steps), "custom shape")
-    return {"workload": f"TB+Pneumonia superposition {args.res}x{args.res}, batch {args.batch} per GPU, "
+    which = {(128, 100, 16): "BASELINE configs[1]", (256, 250, 64): "BASELINE configs[2]",
+             (512, 1000, 32): "BASELINE configs[3]"}.get((args.res, args.diffusion_steps, args.batch), "custom shape")
+    pb = per_gpu_batch(args, world)
+    gb = pb * world
+    return {"workload": f"TB+Pneumonia superposition {args.res}x{args.res}, global batch {gb} ({pb} per GPU), "
                         f"{args.diffusion_steps}-step DDPM schedule ({which}, reference UNet architecture)",
-            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "resolution": args.res,
+            "per_gpu_batch": pb, "global_batch": gb, "resolution": args.res,
             "diffusion_steps": args.diffusion_steps, "models": 2, "parallelism": f"batch-shard x{world}",
             "l2": "working set per call >> L2 (no flush needed between calls)",
             "noise": "in-kernel Philox (value) / host noise stack (e2e)"}
@@ -156,10 +194,10 @@ def conv_roofline(S, dev, R, chunk, iters=20, cin=128, cout=128, impl=2, flush_l
     256 MiB rewritten before every launch to flush L2."""
     import ctypes
     lib = S.lib()
-    act = torch.randn(chunk, R, R, cin, device=dev).to(torch.bfloat16)
+    act = torch.randn(chunk, R, R, cin, device=dev).to(torch.float16)
     w = torch.randn(cout, cin, 3, 3, device=dev) * 0.03
     bias = torch.zeros(cout, device=dev)
-    out = torch.empty(chunk, R, R, cout, device=dev, dtype=torch.bfloat16)
+    out = torch.empty(chunk, R, R, cout, device=dev, dtype=torch.float16)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ms = ctypes.c_float()
     rc = lib.sdd_conv3x3_profile(act.data_ptr(), w.data_ptr(), bias.data_ptr(), out.data_ptr(), chunk, R, R, cin, cout,
@@ -171,7 +209,8 @@ def conv_roofline(S, dev, R, chunk, iters=20, cin=128, cout=128, impl=2, flush_l
 
 
 def update_roofline(S, dev, B, D, iters=20, noise=False, rotating=True):
-    """Fused superposition-update kernel alone: M=2, fp32 eps; in-kernel Philox => 16 B/element
+    """The fused superposition-update STEP alone (one launch: HBM pass + per-sample finalize + step-counter bump, exactly
+    what the sampler launches per step): M=2, fp32 eps; in-kernel Philox => 16 B/element
     (explicit noise tensor => 20 B/element).  rotating: `iters` back-to-back launches between one CUDA-event pair,
     each on the next of several buffer sets totalling >= 512 MB (4 x L2), so every launch works on data that is not
     in L2 while the kernel's code stays warm; otherwise: one event pair per launch with an L2 flush before each
@@ -204,7 +243,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (weak scaling)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong (default): --batch is the GLOBAL batch, split over the GPUs (BASELINE configs[2]: 64 -> "
+                         "64/32/16/8 per GPU); weak: --batch samples on EVERY GPU")
+    ap.add_argument("--batch", type=int, default=64, help="global batch (strong scaling) / per-GPU batch (weak)")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--diffusion-steps", type=int, default=250)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -231,16 +273,16 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    B, R, T, M = args.batch, args.res, args.diffusion_steps, 2
+    R, T, M = args.res, args.diffusion_steps, 2
+    B = per_gpu_batch(args, world)   # samples THIS rank computes
+    GB = B * world                   # global batch
     D = R * R
     models = []
     for i in range(M):
         torch.manual_seed(i)  # random-init weights, PyTorch default init of the reference architecture
-        models.append(S.UNet().to(dev))
+        models.append(S.UNet().to(dev).eval())
     ddpm = S.DDPM(T)
-    lo = rank * B  # weak scaling: every rank samples its own B images, global ids [rank*B, (rank+1)*B)
     shape = (B, 1, R, R)
-    gathered = [torch.empty(shape, device=dev) for _ in range(world)] if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -248,21 +290,26 @@ def main():
         torch.cuda.synchronize()
 
     def one_call(seed):
-        x = S.superposed_sample(models, ddpm, shape, dev, seed=seed, sample_offset=lo)
-        if world > 1:
-            dist.all_gather(gathered, x)  # the path's only collective: final sample gather
-        return x
+        # the public multi-GPU entry: rank r samples global ids [r*B, (r+1)*B) (noise keyed by GLOBAL id: the gathered
+        # batch is bit-identical for any GPU count), then the path's only collective -- one all_gather of the samples
+        return S.sharded_sample(lambda lo, hi: S.superposed_sample(models, ddpm, (hi - lo, 1, R, R), dev, seed=seed,
+                                                                   sample_offset=lo), GB, (1, R, R), dev)
 
     # ---- roofline legs: the two roofline kernels timed ALONE (burst-peak denominators), before the long timed region
-    # heats the board into its power cap (measured after it, the same launches read 4-8 % lower and vary run to run)
+    # heats the board into its power cap (measured after it, the same launches read 4-8 % lower and vary run to run);
+    # the clocks during these legs are sampled and reported with them
     roof = None
+    roof_clk = None
     if rank == 0 and not args.no_roofline:
-        chunk = int(os.environ.get("SDD_CHUNK", "0")) or max(1, min(B, (1536 << 20) // (R * R * 128 * 2)))
+        chunk = max(1, min(B, (1536 << 20) // (R * R * 128 * 2)))
         conv_roofline(S, dev, R, chunk, iters=3)  # warm-up: module load, attributes, clocks
-        conv_tf, conv_ms = conv_roofline(S, dev, R, chunk)
         update_roofline(S, dev, B, D, iters=50)
-        upd_gbs, upd_ms = update_roofline(S, dev, B, D, iters=200)
-        upd_gbs_n, upd_ms_n = update_roofline(S, dev, B, D, iters=200, noise=True)
+        rclk = ClockSampler(local, period=0.02)
+        rclk.start()
+        conv_tf, conv_ms = conv_roofline(S, dev, R, chunk)
+        upd_gbs, upd_ms = update_roofline(S, dev, B, D, iters=400)
+        upd_gbs_n, upd_ms_n = update_roofline(S, dev, B, D, iters=400, noise=True)
+        roof_clk = rclk.stop()
         roof = (chunk, conv_tf, conv_ms, upd_gbs, upd_ms, upd_gbs_n, upd_ms_n)
         torch.cuda.empty_cache()
     barrier()
@@ -280,47 +327,70 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
-    _, launches = S.superposed_sample(models, ddpm, shape, dev, seed=1, sample_offset=lo, return_launches=True)
+    _, launches = S.superposed_sample(models, ddpm, shape, dev, seed=1, sample_offset=rank * B, return_launches=True)
     torch.cuda.synchronize()
+    graphs = [s.graph_instantiations() for s in S.sampling._SAMPLERS.values()]
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
-    value = B * world * args.steps / (ms * 1e-3)
+    value = GB * args.steps / (ms * 1e-3)
 
-    # ---- e2e: public API with HOST buffers (pinned noise stack in, samples out), copies inside the timed region
-    e2e = None
+    # ---- e2e: public API with HOST buffers, copies inside the timed region.  (a) the noise stack of the call comes from
+    # pinned host memory and the samples go back to the host (the contract's e2e); (b) throughput mode: the only input
+    # is a seed (noise is generated in-kernel), samples + kappa / log q trajectories go back to the host.
+    e2e = e2e_philox = None
     if not args.no_e2e:
-        S.sampling.clear_cache()
         stack_h = torch.empty((T, B, 1, R, R), dtype=torch.float32).pin_memory()
         stack_h.normal_(generator=torch.Generator().manual_seed(rank))
-        out_h = torch.empty(shape, dtype=torch.float32).pin_memory()
+        out_h = torch.empty((GB, 1, R, R), dtype=torch.float32).pin_memory()
         stack_d = torch.empty_like(stack_h, device=dev)
 
         def e2e_call():
             stack_d.copy_(stack_h, non_blocking=True)
-            x = S.superposed_sample(models, ddpm, shape, dev, noise=stack_d)
-            if world > 1:
-                dist.all_gather(gathered, x)
+            x = S.sharded_sample(lambda lo, hi: S.superposed_sample(models, ddpm, (hi - lo, 1, R, R), dev,
+                                                                    noise=stack_d), GB, (1, R, R), dev)
             out_h.copy_(x, non_blocking=True)
 
-        e2e_call()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kap_h = torch.empty((T, GB, M), dtype=torch.float32).pin_memory()
+        lq_h = torch.empty((T + 1, GB, M), dtype=torch.float32).pin_memory()
+
+        def e2e_philox_call(seed):
+            x, kap, lq = S.sharded_sample(
+                lambda lo, hi: S.superposed_sample(models, ddpm, (hi - lo, 1, R, R), dev, seed=seed, sample_offset=lo,
+                                                   return_trajectory=True), GB, (1, R, R), dev, trajectories=True)
+            out_h.copy_(x, non_blocking=True)
+            kap_h.copy_(kap, non_blocking=True)
+            lq_h.copy_(lq, non_blocking=True)
+
+        def timed(fn, n):
+            fn(0)
+            barrier()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record()
+            for i in range(n):
+                fn(1 + i)
+            f1.record()
+            barrier()
+            t_ms = f0.elapsed_time(f1)
+            if world > 1:
+                tt = torch.tensor([t_ms], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_ms = tt.item()
+            return t_ms
+
         n_e2e = max(1, min(args.steps, 2))
-        f0.record()
-        for _ in range(n_e2e):
-            e2e_call()
-        f1.record()
-        barrier()
-        ems = f0.elapsed_time(f1)
-        if world > 1:
-            t = torch.tensor([ems], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = t.item()
-        e2e = {"value": B * world * n_e2e / (ems * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(stack_h.numel() * 4), "d2h_bytes_per_step": int(out_h.numel() * 4),
-               "calls": n_e2e, "note": "noise stack [T,B,1,H,W] from pinned host memory, samples read back to host"}
+        ems = timed(lambda i: e2e_call(), n_e2e)
+        e2e = {"value": GB * n_e2e / (ems * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(stack_h.numel() * 4) * world, "d2h_bytes_per_step": int(out_h.numel() * 4),
+               "calls": n_e2e, "note": "noise stack [T,B,1,H,W] from pinned host memory (per rank), gathered samples "
+                                       "read back to host on every rank; bytes are whole-job totals for H2D, per rank "
+                                       "for D2H"}
+        pms = timed(lambda i: e2e_philox_call(3000 + i), n_e2e)
+        e2e_philox = {"value": GB * n_e2e / (pms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                      "d2h_bytes_per_step": int((out_h.numel() + kap_h.numel() + lq_h.numel()) * 4), "calls": n_e2e,
+                      "note": "throughput mode: input = a seed (in-kernel Philox noise); samples + kappa / log q "
+                              "trajectories gathered and read back to host"}
         del stack_d, stack_h
 
     if rank == 0:
@@ -333,36 +403,44 @@ def main():
         if not (B == 64 and R == 256 and chunk == 64):
             conv_traffic = upd_traffic = None  # the captures were taken at the default launch shapes only
         step_flops = 2.0 * CONV_MAC_PER_PIXEL * D * M * T  # per sample
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": args.scaling, "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clk,
                 "gpu_launches": int(launches) * args.steps * world,
+                "graph_instantiations_per_sampler": graphs,
                 "whole_path_tensor_frac_of_sustained": value / world * step_flops / (tf_sust * 1e12),
                 "roofline": {"kernel": "conv3x3_tc4_kernel<128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)", "bound": "tensor",
                              "achieved": conv_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_tf / tf_burst,
-                             "traffic": conv_traffic, "algorithmic_bytes": 2.0 * chunk * R * R * 128 * 2, "peak_source": f"{src} bf16 burst", "launch_ms": conv_ms,
+                             "traffic": conv_traffic, "algorithmic_bytes": 2.0 * chunk * R * R * 128 * 2,
+                             "peak_source": f"{src} bf16 burst (fp16 runs at the same tcgen05 kind::f16 rate)",
+                             "launch_ms": conv_ms, "clocks": roof_clk,
                              "how": f"kernel alone at the sampler's launch shape ({chunk}x{R}x{R}x128), CUDA events "
                                     "around each launch on the launching stream, L2 flushed between launches, taken "
-                                    "before the long timed region (board not yet power-capped)"},
-                "roofline_update": {"kernel": "superpose_update_kernel<2>", "bound": "hbm", "achieved": upd_gbs,
+                                    "before the long timed region; clocks sampled during the roofline legs"},
+                "roofline_update": {"kernel": "superpose_update_kernel<2> (the whole update step: one launch)",
+                                    "bound": "hbm", "achieved": upd_gbs,
                                     "peak": hbm, "unit": "GB/s", "frac": upd_gbs / hbm, "traffic": upd_traffic,
                                     "bytes_per_element": 16, "launch_ms": upd_ms, "peak_source": f"{src} copy",
                                     "noise_tensor_variant": {"bytes_per_element": 20, "achieved": upd_gbs_n,
                                                              "frac": upd_gbs_n / hbm, "launch_ms": upd_ms_n},
-                                    "how": "kernel alone, M=2, in-kernel Philox noise; 200 back-to-back launches "
-                                           "between one CUDA-event pair on the launching stream, each launch on the "
-                                           "next of several buffer sets totalling >= 512 MB (inputs larger than L2, "
-                                           "code stays warm)"},
+                                    "how": "the step's single launch (HBM pass + per-sample finalize + step-counter "
+                                           "bump), M=2, in-kernel Philox noise; 400 back-to-back launches between one "
+                                           "CUDA-event pair on the launching stream, each launch on the next of "
+                                           "several buffer sets totalling >= 512 MB (inputs larger than L2, code "
+                                           "stays warm)"},
                 }
         if e2e:
             line["e2e"] = e2e
+            line["e2e_philox"] = e2e_philox
         if world == 1 and not args.no_cpu_baseline:
-            t0 = time.perf_counter()
-            v, secs = cpu_reference_run(R, T, M, 4, 8)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            v, secs, kind = cpu_reference_run(R, T, M, 4, 8)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
                                     "sample": f"B=4, 8 of {T} diffusion steps after 1 warm-up step "
-                                              f"({secs:.1f} s of CPU work), extrapolated linearly in T"}
+                                              f"({secs:.1f} s of CPU work), extrapolated linearly in T; UNet / DDPM = "
+                                              + ("the reference's own modules (baseline/_ref)" if kind == "reference"
+                                                 else "oracle restatement")
+                                              + ", superposition step = oracle (no reference code exists)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

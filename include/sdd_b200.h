@@ -55,19 +55,27 @@ int sdd_device_check(void);
 
 /* ---- UNet (unet.py:37-65; default architecture only: in=out=1, time_emb_dim=256, base=64) ---- */
 
-/* Build device-resident kernel-layout weights (bf16 conv operands, fp32 everything else) from the
+/* Build device-resident kernel-layout weights (fp16 conv operands, fp32 everything else) from the
  * 54 fp32 state-dict tensors (device pointers, contiguous, reference shapes).  The inputs are only
  * read during the call (stream-ordered); the handle owns its own copies. */
 int sdd_unet_create(sdd_unet_t** out, const float* const* tensors, int num_tensors, void* stream);
 int sdd_unet_destroy(sdd_unet_t* u);
+/* Cap the number of samples one pass of the forward processes at a time (0 = automatic: up to 1.5 GB per ping-pong
+ * activation buffer).  Chunking changes no result bit; it bounds the workspace.  Takes effect at the next call. */
+int sdd_unet_set_max_chunk(sdd_unet_t* u, int max_samples);
 
 /* eps_out[B,1,H,W] = UNet(x[B,1,H,W], t[B]); fp32 in/out, t is int64 as in unet.py:57.
  * H % 16 == 0 and W % 8 == 0 are required (SDD_EINVAL otherwise).  Workspace is owned by the
  * handle and grown on demand (so the first call at a new shape is not graph-capturable). */
 int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps_out,
                      int B, int H, int W, void* stream);
+/* Same, with the first layer's GroupNorm(1,1) statistics of x supplied by the caller: xstats[B,2] = (mean, rstd) per
+ * sample, e.g. the xstats_out of the sdd_superpose_update call that produced x (NULL: computed here).  A step-by-step
+ * loop driven through the operator entry points then reproduces sdd_sampler_run bit for bit. */
+int sdd_unet_forward_xstats(sdd_unet_t* u, const float* x, const float* xstats, const int64_t* t, float* eps_out,
+                            int B, int H, int W, void* stream);
 
-/* ---- Fused superposition update (A7): one HBM pass per step ----
+/* ---- Fused superposition update (A7): ONE kernel launch and one HBM pass per step ----
  * kappa = softmax_m(temperature * logq[b,:] + bias);  eps_bar = sum_m kappa_m eps[m,b,:]
  * x_out = alpha^-1/2 (x_in - (1-alpha)/sqrt(1-alpha_bar) eps_bar) + sqrt(beta) z        (ddpm.py:42-44)
  * logq[b,m] += <s_m, x_out-x_in> - beta D/2 - beta/2 <x_in, s_m> - beta/2 |s_m|^2,  s_m = -eps_m/sqrt(1-alpha_bar)
@@ -75,7 +83,9 @@ int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps
  * if draw_index >= 0; else zero (the t == 0 step, ddpm.py:36).
  * x_out may alias x_in.  kappa_out[B,M] / logq_out[B,M] / xstats_out[B,2] (mean, rstd of x_out for the
  * next GroupNorm(1,1)) may be NULL; logq_out may alias logq.  M <= 4.  D % 4 == 0.
- * workspace: sdd_superpose_update_workspace(B, D, M) bytes, zero-initialised once by the caller. */
+ * workspace: sdd_superpose_update_workspace(B, D, M) bytes, zero-initialised once by the caller (it holds the
+ * per-segment partial sums and the arrival counters that elect each sample's finalising CTA; the kernel leaves the
+ * counters at zero again). */
 size_t sdd_superpose_update_workspace(int B, int D, int M);
 int sdd_superpose_update(const float* x_in, float* x_out, const float* eps, const float* noise,
                          const float* logq, float* logq_out, float* kappa_out, float* xstats_out,
@@ -140,7 +150,9 @@ typedef struct {
   float* x_out;             /* device [B,D] */
   float* kappa_traj;        /* device [T,B,M] or NULL */
   float* logq_traj;         /* device [T+1,B,M] or NULL */
-  int use_graph;            /* 1: replay one captured step graph T times */
+  float* x_traj;            /* device [T+1,B,D] or NULL: row 0 = x_T, row k+1 = state after loop iteration k (the
+                               reverse-diffusion strip of utils/visualization.py:6-28; per-step parity tests) */
+  int use_graph;            /* 1: replay one captured step graph T-1 times (step 0 runs eagerly) */
   int mode;                 /* 0 = SuperDiff OR (kappa = softmax of the running log q); 1 = AND (kappa solved per
                                sample and step so that all models' log-density increments are equal; 8(f) N3) */
 } sdd_sample_args;
@@ -154,38 +166,33 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
 int sdd_sampler_destroy(sdd_sampler_t* s);
 /* Kernel launches one sdd_sampler_run issues (for bench.py's gpu_launches). */
 int64_t sdd_sampler_launches_per_run(const sdd_sampler_t* s);
+/* How many times this sampler captured + instantiated its step graph so far.  Seed, shard offset, noise stack,
+ * temperature, bias and trajectory buffers live in device memory the graph points at, so this stays 1 across calls
+ * (a change of `mode` or a re-allocated UNet workspace re-captures). */
+int64_t sdd_sampler_graph_instantiations(const sdd_sampler_t* s);
 
 /* ---- Operator-level entry points (used by the parity tests and the roofline bench) ---- */
 
-/* out[B,H,W,Cout] (bf16 NHWC) = conv3x3(act[B,H,W,Cin] bf16 NHWC, pad 1) + bias[b*bias_batch_stride + c].
- * w: fp32 [Cout,Cin,3,3] (reference layout; converted internally).  Cin, Cout in {64,128}.
- * impl 0 = tcgen05/TMA kernel, 1 = plain CUDA-core kernel (bring-up cross-check only).
- * gn_meanrstd[B,4,2] (may be NULL) receives GroupNorm(4,Cout) mean / rstd of the output. */
-int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t bias_batch_stride,
-                     void* out, float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, int impl,
-                     void* stream);
-
-/* The product kernel: GroupNorm(4,Cin)+SiLU of the RAW input (statistics in_meanrstd[B,4,2], affine in_gamma/in_beta[Cin])
- * fused with the 3x3 conv, bias add and the OUTPUT's GroupNorm(4,Cout) statistics (unet.py:21-28 in one launch).
- * in_meanrstd == NULL: the input is used as is.  2-CTA tcgen05 kernel with resident weights. */
+/* The product conv kernel as an operator: GroupNorm(4,Cin)+SiLU of the RAW input (statistics in_meanrstd[B,4,2], affine
+ * in_gamma/in_beta[Cin]) fused with the 3x3 conv (pad 1), bias add (bias[b*bias_batch_stride + c]) and the OUTPUT's
+ * GroupNorm(4,Cout) statistics gn_meanrstd[B,4,2] (may be NULL) -- unet.py:21-28 in one launch.
+ * act_raw / out: fp16 NHWC [B,H,W,Cin] / [B,H,W,Cout]; w: fp32 [Cout,Cin,3,3] (reference layout; rounded to fp16
+ * internally).  Cin, Cout in {64,128}.  in_meanrstd == NULL: the input is used as is.  2-CTA tcgen05 kernel with
+ * resident weights. */
 int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const float* in_gamma, const float* in_beta,
                            const float* w, const float* bias, int64_t bias_batch_stride, void* out,
                            float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, void* stream);
 
-/* In place on bf16 NHWC act[B,H,W,C]: silu((v - mean[b,g]) * rstd[b,g] * gamma[c] + beta[c]), G = 4. */
-int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta,
-                      int B, int H, int W, int C, void* stream);
-
 /* Kernel-only timing for the roofline numbers (bench.py): `iters` launches, each bracketed by CUDA events
  * on the launching stream; `flush` (may be NULL) is rewritten before every launch to evict L2.
  * *ms_host receives the mean kernel duration in milliseconds. */
-/* impl: 0 = bring-up kernel (cta_group::1, streamed weights, pre-activated input), 1 = product kernel without the fused
- * GroupNorm, 2 = product kernel with the fused GroupNorm+SiLU (identity statistics). */
+/* impl: 1 = product kernel without the fused GroupNorm, 2 = product kernel with the fused GroupNorm+SiLU (identity
+ * statistics); act / out fp16 NHWC. */
 int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W,
                         int Cin, int Cout, int impl, int iters, void* flush, size_t flush_bytes, float* ms_host,
                         void* stream);
-/* Times the one-pass update kernel ALONE (the event pair brackets superpose_update_kernel; the tiny per-sample finalize
- * kernel that follows it is launched after the second event). */
+/* Times the whole update step (one launch: HBM pass + per-sample finalize + step-counter bump), one event pair per
+ * launch, `flush` rewritten before each. */
 int sdd_superpose_update_profile(float* x, const float* eps, const float* noise, float* logq, int B, int D,
                                  int M, int iters, void* flush, size_t flush_bytes, float* ms_host,
                                  void* stream);

@@ -17,7 +17,8 @@ def lib_path():
 class SampleArgs(ctypes.Structure):
     _fields_ = [("noise_stack", ctypes.c_void_p), ("seed", ctypes.c_uint64), ("sample_offset", ctypes.c_int64),
                 ("temperature", ctypes.c_float), ("bias", ctypes.c_void_p), ("x_out", ctypes.c_void_p),
-                ("kappa_traj", ctypes.c_void_p), ("logq_traj", ctypes.c_void_p), ("use_graph", ctypes.c_int), ("mode", ctypes.c_int)]
+                ("kappa_traj", ctypes.c_void_p), ("logq_traj", ctypes.c_void_p), ("x_traj", ctypes.c_void_p),
+                ("use_graph", ctypes.c_int), ("mode", ctypes.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/sdd_b200.h declares.
@@ -29,7 +30,9 @@ SYMBOLS = {
     "sdd_device_check": (_i, []),
     "sdd_unet_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _vp]),
     "sdd_unet_destroy": (_i, [_vp]),
+    "sdd_unet_set_max_chunk": (_i, [_vp, _i]),
     "sdd_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sdd_unet_forward_xstats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "sdd_superpose_update_workspace": (_sz, [_i, _i, _i]),
     "sdd_superpose_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _u64,
                                   _i64, _i, _vp, _sz, _vp]),
@@ -46,9 +49,8 @@ SYMBOLS = {
     "sdd_sampler_run": (_i, [_vp, ctypes.POINTER(SampleArgs), _vp]),
     "sdd_sampler_destroy": (_i, [_vp]),
     "sdd_sampler_launches_per_run": (_i64, [_vp]),
-    "sdd_conv3x3_nhwc": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "sdd_sampler_graph_instantiations": (_i64, [_vp]),
     "sdd_conv3x3_fused_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
-    "sdd_gn_silu_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "sdd_conv3x3_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, ctypes.POINTER(_f), _vp]),
     "sdd_superpose_update_profile_rotating": (_i, [_i, _i, _i, _i, _i, _sz, ctypes.POINTER(_f), _vp]),
     "sdd_superpose_update_profile": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _sz, ctypes.POINTER(_f), _vp]),

@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdd_b200.so")
 SOURCES = ["sdd_api.cu"]
-HEADERS = ["common.cuh", "conv_tc.cuh", "cluster.cuh", "conv_tc3.cuh", "conv_tc4.cuh", "unet_kernels.cuh", "update.cuh", "train_eval.cuh", "attention.cuh", "attention_block.cuh", os.path.join("..", "..", "include", "sdd_b200.h")]
+HEADERS = ["common.cuh", "conv_common.cuh", "conv_tc4.cuh", "unet_kernels.cuh", "update.cuh", "train_eval.cuh", "attention.cuh",
+           "attention_block.cuh", os.path.join("..", "..", "include", "sdd_b200.h")]
 
 
 def _stale():

@@ -18,8 +18,7 @@
 // warps 2..5 = softmax / epilogue (TMEM lane quadrant = warp % 4, thread = query row).
 #pragma once
 #include "common.cuh"
-#include "cluster.cuh"
-#include "conv_tc3.cuh"
+#include "conv_common.cuh"
 
 namespace sdd {
 

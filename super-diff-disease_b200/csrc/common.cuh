@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -140,6 +141,7 @@ __device__ __forceinline__ void gn_publish_and_finalize_warp(
 // fixed-point integers in units of 2^-20 with fire-and-forget RED.ADDs.  Integer addition is associative, so the
 // totals are bit-reproducible whatever the arrival order or batch sharding, and no fence / counter / last-CTA
 // protocol is needed; consumers (the next kernel) derive (mean, rstd) themselves.  Range: |sum| < 8.8e12.
+constexpr float kGnEps = 1e-5f;  // GroupNorm eps of the reference (nn.GroupNorm default, unet.py:22,25)
 constexpr float kGnFixScale = 1048576.0f;
 constexpr double kGnFixInv = 1.0 / 1048576.0;
 __device__ __forceinline__ void gn_red_add(long long* dst, float v) {
@@ -332,6 +334,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same with fp16 x fp16 operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // One lane of a converged warp; ptxas then knows the guarded region runs single-threaded and feeds
 // tcgen05 / TMA descriptors through uniform registers without a per-instruction waterfall loop.
 __device__ __forceinline__ bool elect_one_sync() {
@@ -351,6 +358,29 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 16-bit type of the 64/128-channel layers (inter-layer activations in HBM, both MMA operands): IEEE fp16, fp32
+// accumulate.  Measured error budget of the forward against the fp32 reference (tools/error_budget.py):
+// bf16 weights / bf16 storage / bf16 activated operand each cost 6-8e-3 rel-L2 of eps-hat (1.1-1.3e-2 together, the
+// round-1 figure); the same three roundings in fp16 cost 7-9e-4 each (1.6-1.9e-3 together) at the same tcgen05
+// kind::f16 rate.  Range: every conv input is a GroupNorm+SiLU output (bounded), so |conv output| <= |w|_1 * max|act|;
+// conversions saturate at +-65504 instead of producing inf.
+typedef __half act_t;
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ void unpack_act2(uint32_t u, float& lo, float& hi) {
+  asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}"
+      : "=f"(lo), "=f"(hi)
+      : "r"(u));
+}
+__device__ __forceinline__ float act_to_float(act_t v) { return __half2float(v); }
+__device__ __forceinline__ act_t float_to_act(float v) {
+  return __ushort_as_half((unsigned short)(pack_act2(v, 0.f) & 0xffffu));
 }
 
 }  // namespace sdd

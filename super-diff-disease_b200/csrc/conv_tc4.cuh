@@ -1,17 +1,23 @@
-// Product tensor-core 3x3 conv, generation 4 = generation 3 (conv_tc3.cuh: same contract, same MMA / epilogue / barriers)
-// with the loader warps split into TWO groups that work on alternating 64-channel items (see the loader section).
+// Product tensor-core 3x3 conv: GroupNorm+SiLU -> conv3x3 -> (+bias, next GroupNorm's sums), one kernel.
+//
+//   out[n,h,w,co] = bias[n,co] + sum_{ky,kx,ci} f(raw[n,h+ky-1,w+kx-1,ci]) * wt[kx][ky][co][ci]
+//   f(v) = silu((v - mean[n,g]) * rstd[n,g] * gamma[ci] + beta[ci])  inside the image, 0 in the padding
+//   (reference: GroupNorm -> SiLU -> Conv2d of ResidualBlock, /root/reference/src/models/unet.py:21-28)
+//
+// CTA pair (cluster of 2, tcgen05 cta_group::2), UMMA M = 256 = two 16x8-pixel tiles, N = Cout, K = 9*Cin, fp16 x fp16
+// -> fp32 in TMEM (double-buffered accumulators); this CTA's half of the weights resident in shared memory for the whole
+// persistent kernel; the nine taps are descriptor VIEWS of one (18 x 10)-pixel halo box (start row ky*10+kx, 1280-byte
+// group stride under SWIZZLE_128B).  Shared memory, not the tensor pipe, is the scarce resource (an SS-mode
+// M256xN128xK16 UMMA reads 6 KB per CTA in 64 cycles), so the operand tile is touched ONCE: loader warps read the raw
+// activations into registers, apply GroupNorm+SiLU there and store the activated tile straight into the UMMA swizzle.
+// The output's GroupNorm sums leave the epilogue as fire-and-forget 64-bit fixed-point RED.ADDs (common.cuh).
+// Barriers (arrival count): ready[s] loaders->MMA (8, on the leader) | empty[s] MMA->loaders (1, multicast commit)
+// | tfull[a] MMA->epilogue (1, multicast commit) | tempty[a] epilogue->MMA (16, on the leader) | wbar weights (1+tx).
+// The loader warps form TWO groups that work on alternating 64-channel items (see the loader section).
 #pragma once
-#include "conv_tc3.cuh"
+#include "conv_common.cuh"
 
 namespace sdd {
-
-// stamps exist only in the kTrace instantiation (timing experiments, tools/conv_exp.py); the product kernel has none
-#define SDD_TRACE4(role, iter, ev)                                                                    \
-  do {                                                                                                \
-    if constexpr (kTrace) {                                                                           \
-      if (a.trace && blockIdx.x < 2 && (iter) < kTraceIters) s_trace[role][iter][ev] = clock64();     \
-    }                                                                                                 \
-  } while (0)
 
 // kRaw (generation 5, layers whose resident weights leave >= 3 spare 23 KB slots: every layer but 128->128): the
 // halo boxes are not fetched by the loader threads' own global loads but by TMA into a ring of RAW shared-memory slots,
@@ -23,7 +29,7 @@ namespace sdd {
 // conflict-free LDS.128 from the same swizzled offsets they write to (the TMA box lands in the UMMA layout), no thread
 // has a global load outstanding at the fence, and address arithmetic leaves the loaders entirely.  Cost: one more
 // shared-memory write + read per byte (23 KB + 23 KB per item), affordable where the MMA leaves bandwidth.
-template <int COUT, bool kTrace = false, bool kRaw = false>
+template <int COUT, bool kRaw = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
 conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ConvTc3Args a) {
@@ -46,11 +52,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t tmem_slot = bar_base + 8u * (2 * kC3MaxStages + 5);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-  __shared__ long long s_trace[kTrace ? 5 : 1][kTrace ? kTraceIters : 1][4];
-  if constexpr (kTrace) {
-    if (a.trace && blockIdx.x < 2)
-      for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) (&s_trace[0][0][0])[i] = 0;
-  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -118,19 +119,16 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) ===
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, COUT);
+      constexpr uint32_t idesc = umma_idesc_f16(256, COUT);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      int it = 0;
-      for (int pair = pair0; pair < pair_end; pair += pair_step(), ++it) {
+      for (int pair = pair0; pair < pair_end; pair += pair_step()) {
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        if (lane == 0) SDD_TRACE4(1, it, 0);
         const uint32_t d_tmem = SDD_TMEM_BASE() + (uint32_t)(acc * COUT);
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait_cluster(ready_bar(stage), phase);
           tc_fence_after();
-          if (lane == 0) SDD_TRACE4(1, it, 1 + kc);
           const uint32_t sa = a_base + stage * kHaloBytes;
           if (elect_one_sync()) {
 #pragma unroll
@@ -139,10 +137,9 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int ky = 0; ky < 3; ++ky) {
                 const uint64_t adesc = umma_desc_sw128(sa + (ky * kHaloW + kx) * 128, kHaloW * 128);
                 const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)((kx * 3 + ky) * kchunks + kc) * kWSlot);
-                if (a.dbg & 4) continue;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)  // 4 x UMMA_K (16 bf16 = 32 B) inside the 128-byte swizzle row
-                  umma_bf16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                for (int k = 0; k < 4; ++k)  // 4 x UMMA_K (16 fp16 = 32 B) inside the 128-byte swizzle row
+                  umma_f16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
                                  (kc | kx | ky | k) ? 1u : 0u);
               }
             umma_commit_2cta(empty_bar(stage));                         // frees the stage in both CTAs
@@ -151,7 +148,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        if (lane == 0) SDD_TRACE4(1, it, 3);
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
@@ -186,7 +182,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     __shared__ __align__(16) float s_bias[8][64];
     int bias_cur = -1;
     int acc = 0; uint32_t acc_phase = 0;
-    int it = 0;
     // division-free tile cursor (the two runtime-divisor divisions per tile were ~55 of the epilogue's ~450 instructions
     // per warp and tile): (n, th, tw) of this CTA's tile advance by a constant tile step with carries
     int n, th, tw;
@@ -201,13 +196,13 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int tstep = 2 * pair_step();
     const int e_dn = tstep / a.tiles_per_sample, e_dr = tstep - e_dn * a.tiles_per_sample;
     const int e_dth = e_dr / a.tiles_w, e_dtw = e_dr - e_dth * a.tiles_w;
-    for (int pair = pair0; pair < pair_end; pair += pair_step(), ++it) {
+    for (int pair = pair0; pair < pair_end; pair += pair_step()) {
       const bool valid = 2 * pair + (int)rank < a.num_tiles;  // false: the dummy tile of an odd count (coordinates stay
                                                              // at the previous, valid tile; nothing is stored)
       const int h = th * kTileH + (m >> 3), w = tw * kTileW + (m & 7);
       const float* bp = bias_row + (int64_t)n * a.bias.batch_stride;
-      __nv_bfloat16* orow = a.out + (((size_t)n * a.H + h) * a.W + w) * COUT + col0;
-      const bool do_store = valid && !(a.dbg & 2);  // dbg 2: no stores (statistics stay), dbg 8: no statistics
+      act_t* orow = a.out + (((size_t)n * a.H + h) * a.W + w) * COUT + col0;
+      const bool do_store = valid;
       // This warp's COLS bias values live in shared memory and are refreshed only when the sample changes (never, when
       // all samples share one row).  As per-tile global loads they were the first use behind the accumulator wait and
       // cost 10 % of the epilogue's stall samples: with 213 KB of shared memory there is almost no L1 left to hit in.
@@ -220,11 +215,10 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      if (e == 0 && lane == 0) SDD_TRACE4(3, it, 0);
       const uint32_t taddr = SDD_TMEM_BASE() + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + col0);
       float sg[2] = {0.f, 0.f}, ssg[2] = {0.f, 0.f};
       uint32_t v[2][16];
-      uint32_t pk[G][8];  // this lane's pixel: G chunks of 16 channels (32 B each), packed bf16
+      uint32_t pk[G][8];  // this lane's pixel: G chunks of 16 channels (32 B each), packed fp16
       tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
       for (int st = 0; st < G; ++st) {
@@ -264,7 +258,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int j = 0; j < 8; ++j) {
           float lo, hi;
           unpack_f32x2(f2[j], lo, hi);
-          pk[st][j] = pack_bf16x2(lo, hi);
+          pk[st][j] = pack_act2(lo, hi);
         }
       }
       tc_fence_before();
@@ -284,7 +278,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         val += __shfl_xor_sync(0xffffffffu, val, 4);
         val += __shfl_xor_sync(0xffffffffu, val, 2);
         val += __shfl_xor_sync(0xffffffffu, val, 1);
-        if ((lane & 7) == 0 && valid && !(a.dbg & 8) && a.out_sums)
+        if ((lane & 7) == 0 && valid && a.out_sums)
           gn_red_add(a.out_sums + ((size_t)n * 4 + hcol * 2 + (lane >> 4)) * 2 + ((lane >> 3) & 1), val);
       }
       if (do_store) {
@@ -307,13 +301,11 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
         // pk[i] now holds chunk (lane % G) of pixel (lane - lane % G + i)
-        __nv_bfloat16* obase = orow - (size_t)(lane & (G - 1)) * COUT + (lane & (G - 1)) * 16;
+        act_t* obase = orow - (size_t)(lane & (G - 1)) * COUT + (lane & (G - 1)) * 16;
 #pragma unroll
         for (int i = 0; i < G; ++i) st_global_v8(obase + (size_t)i * COUT, pk[i]);
       }
-      if (e == 0 && lane == 0) SDD_TRACE4(3, it, 1);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      if (e == 0 && lane == 0) SDD_TRACE4(3, it, 2);
       if (2 * (pair + pair_step()) + (int)rank < a.num_tiles) {  // advance to this CTA's next tile
         tw += e_dtw; th += e_dth; n += e_dn;
         if (tw >= a.tiles_w) { tw -= a.tiles_w; ++th; }
@@ -333,8 +325,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int tt = threadIdx.x - 384;        // 0..255
     const int grp = tt >> 7, tg = tt & 127;  // group, thread in group
     const int piece = tg & 7, col = tg >> 3; // col 0..15
-    __shared__ __align__(16) float s_ga[2][128], s_gb[2][128];
-    const bool fuse = (a.in_sums != nullptr) || (a.in_meanrstd != nullptr) || (a.in_ab != nullptr);
+    const bool fuse = a.in_ab != nullptr;
     const uint8_t* in_bytes = reinterpret_cast<const uint8_t*>(a.in);
     const int tiles_h = a.H / kTileH;
     // vector i <-> halo row r = col + 16 i (pixel (r / 10, r % 10) of the 18 x 10 box); r & 7 == col & 7 for every i
@@ -408,22 +399,25 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (item < my_items) { tile_src(c, base, ok_c); if constexpr (!kRaw) issue_loads(base, ok_c); }
     int stage = grp % a.stages; uint32_t phase = (uint32_t)((grp / a.stages) & 1);
     int cur_n = -1;
-    uint64_t ga2[4], gb2[4];
+    uint64_t ga2[4] = {0ull, 0ull, 0ull, 0ull}, gb2[4] = {0ull, 0ull, 0ull, 0ull};
     mbar_wait(w_bar, 0);  // this CTA's weights have landed (the MMA warp relies on the loaders for this)
 
+    // silu(gn(v)) of one fp16 pair: 2 cvt + FFMA2 + 2 MUFU.TANH + FFMA2 + 1 cvt.f16x2
     auto xform_pair = [&](uint32_t u, int j) -> uint32_t {
-      const uint64_t h = fma_f32x2(pack_f32x2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)), ga2[j], gb2[j]);
+      float vl, vh;
+      unpack_act2(u, vl, vh);
+      const uint64_t h = fma_f32x2(pack_f32x2(vl, vh), ga2[j], gb2[j]);
       float hl, hh;
       unpack_f32x2(h, hl, hh);
       const uint64_t q2 = fma_f32x2(h, pack_f32x2(tanh_approx(hl), tanh_approx(hh)), h);
       float rl, rh;
       unpack_f32x2(q2, rl, rh);
-      return pack_bf16x2(rl, rh);
+      return pack_act2(rl, rh);
     };
 
     while (item < my_items) {
       // ---- GroupNorm scale / shift: this group's chunk is fixed, so the registers only change with the sample
-      if (fuse && c.n != cur_n && a.in_ab) {
+      if (fuse && c.n != cur_n) {
         // precomputed by gn_scale_shift_kernel: this thread's eight channels, four 16-byte loads, no barrier
         const float* pa = a.in_ab + ((size_t)c.n * a.Cin + kc * 64 + piece * 8);
         const float* pb = pa + (size_t)a.B * a.Cin;
@@ -431,31 +425,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int j = 0; j < 4; j += 2) {
           const float4 x = __ldg(reinterpret_cast<const float4*>(pa + 2 * j));
           const float4 y = __ldg(reinterpret_cast<const float4*>(pb + 2 * j));
-          ga2[j] = pack_f32x2(x.x, x.y); ga2[j + 1] = pack_f32x2(x.z, x.w);
-          gb2[j] = pack_f32x2(y.x, y.y); gb2[j + 1] = pack_f32x2(y.z, y.w);
-        }
-        cur_n = c.n;
-      }
-      // (no precomputed table -- A/B and bring-up only: rebuild them in the group)
-      if (fuse && c.n != cur_n) {
-        named_bar_sync(2 + grp, 128);  // previous readers of this group's s_ga/s_gb are done
-        if (tg < 64) {
-          const int ch = kc * 64 + tg;
-          const int g = ch / (a.Cin / 4);
-          float mean, rstd;
-          if (a.in_sums)
-            gn_mean_rstd_from_sums(a.in_sums + ((size_t)c.n * 4 + g) * 2, (double)a.H * (double)a.W * (double)(a.Cin / 4),
-                                   kGnEps, mean, rstd);
-          else { mean = a.in_meanrstd[(c.n * 4 + g) * 2]; rstd = a.in_meanrstd[(c.n * 4 + g) * 2 + 1]; }
-          const float sc = rstd * a.in_gamma[ch];
-          s_ga[grp][tg] = 0.5f * sc;                       // pre-halved: silu(v) = h + h tanh(h), h = v / 2
-          s_gb[grp][tg] = 0.5f * (a.in_beta[ch] - mean * sc);
-        }
-        named_bar_sync(2 + grp, 128);
-#pragma unroll
-        for (int j = 0; j < 4; j += 2) {
-          const float4 x = *reinterpret_cast<const float4*>(&s_ga[grp][piece * 8 + 2 * j]);
-          const float4 y = *reinterpret_cast<const float4*>(&s_gb[grp][piece * 8 + 2 * j]);
           ga2[j] = pack_f32x2(x.x, x.y); ga2[j + 1] = pack_f32x2(x.z, x.w);
           gb2[j] = pack_f32x2(y.x, y.y); gb2[j + 1] = pack_f32x2(y.z, y.w);
         }
@@ -472,9 +441,8 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (i < nvec) r[i] = lds_v4(src + (uint32_t)i * 2048u);
       }
       mbar_wait(empty_bar(stage), phase ^ 1u);
-      if (tg == 0) SDD_TRACE4(2, item / kchunks, grp);
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes + soff;
-      if (fuse && ok_c == (1u << nvec) - 1u && !(a.dbg & 64)) {
+      if (fuse && ok_c == (1u << nvec) - 1u) {
         // interior tile: straight-line code, the vectors' chains interleave freely.  (Three of a group's four warps own
         // eleven vectors, not twelve -- rows >= 180 do not exist -- and used to fall into the masked path below on every
         // item: 78 % of all loader executions, ~1.7x the instructions.)
@@ -490,7 +458,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int i = 0; i < kVecs; ++i) {
           uint4 v = r[i];
-          if (fuse && ((ok_c >> i) & 1u) && !(a.dbg & 64))
+          if (fuse && ((ok_c >> i) & 1u))
             v = make_uint4(xform_pair(v.x, 0), xform_pair(v.y, 1), xform_pair(v.z, 2), xform_pair(v.w, 3));
           if (i < nvec) sts_v4(dst + (uint32_t)i * 2048u, v);  // padding pixels hold the zeros they were "loaded" as
         }
@@ -503,7 +471,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if constexpr (kRaw) {  // every lane's LDS results were consumed by the stores above: the raw slot is free
         if (lane == 0) mbar_arrive(raw_empty_bar(item % a.raw_slots));
       }
-      if (tg == 0) SDD_TRACE4(2, item / kchunks, 2 + grp);
       // ---- this group's next item: coordinates, then its loads (nothing of this thread is in flight at a MEMBAR)
       item += 2;
       stage += 2; if (stage >= a.stages) { stage -= a.stages; phase ^= 1u; }
@@ -525,13 +492,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (kTrace) {
-    if (a.trace && blockIdx.x < 2)
-      for (int i = threadIdx.x; i < 5 * kTraceIters * 4; i += kC3Threads) {
-        const int role = i / (kTraceIters * 4), rem = i % (kTraceIters * 4);
-        a.trace[(((size_t)blockIdx.x * 6 + role) * 64 + rem / 4) * 4 + (rem & 3)] = (&s_trace[0][0][0])[i];
-      }
-  }
   cluster_sync_all();  // the peer may still be reading our smem / arriving on our barriers
   if (warp == 2) {
     tc_fence_after();

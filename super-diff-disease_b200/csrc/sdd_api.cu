@@ -7,9 +7,7 @@
 #include <vector>
 
 #include "common.cuh"
-#include "conv_tc.cuh"
-#include "cluster.cuh"
-#include "conv_tc3.cuh"
+#include "conv_common.cuh"
 #include "conv_tc4.cuh"
 #include "unet_kernels.cuh"
 #include "update.cuh"
@@ -29,8 +27,18 @@ static thread_local int64_t g_launches = 0;  // kernels launched by this thread 
     SDD_CUDA(cudaGetLastError());          \
   } while (0)
 
-// ------------------------------------------------------------------------------- device check
-static int device_check() {
+// ------------------------------------------------------------------------------- per-device state
+// Function attributes (the opt-in to > 48 KB of dynamic shared memory) and the SM count are properties of a DEVICE, not
+// of the process: they are set / queried once per device ordinal, so models on cuda:0 and cuda:1 of one process both work.
+struct DeviceCtx {
+  bool known = false;   // compute capability queried
+  bool attrs = false;   // cudaFuncSetAttribute done on this device
+  int major = 0, minor = 0, sms = 0;
+};
+static DeviceCtx g_dev[64];
+static std::mutex g_dev_mu;
+
+static int device_ctx(DeviceCtx** out) {
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) {
@@ -38,36 +46,31 @@ static int device_check() {
     cudaGetLastError();
     return SDD_ENODEV;
   }
-  // compute capability, cached per device ordinal (cudaGetDeviceProperties costs ~1 ms per call)
-  static int major_of[64], minor_of[64];
-  static bool known[64];
-  int major = 0, minor = 0;
-  if (dev >= 0 && dev < 64 && known[dev]) {
-    major = major_of[dev]; minor = minor_of[dev];
-  } else {
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
-      set_error("cudaDeviceGetAttribute(compute capability) failed");
+  if (dev < 0 || dev >= 64) { set_error("device ordinal out of range"); return SDD_ENODEV; }
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  DeviceCtx& c = g_dev[dev];
+  if (!c.known) {
+    if (cudaDeviceGetAttribute(&c.major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&c.minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+      set_error("cudaDeviceGetAttribute failed");
       cudaGetLastError();
       return SDD_ENODEV;
     }
-    if (dev >= 0 && dev < 64) { major_of[dev] = major; minor_of[dev] = minor; known[dev] = true; }
+    c.known = true;
   }
-  if (major != 10) {
-    set_error("device is sm_" + std::to_string(major) + std::to_string(minor) +
+  if (c.major != 10) {
+    set_error("device is sm_" + std::to_string(c.major) + std::to_string(c.minor) +
               "; this library contains sm_100a code only (no fallback)");
     return SDD_ENODEV;
   }
+  if (out) *out = &c;
   return SDD_OK;
 }
+static int device_check() { return device_ctx(nullptr); }
 static int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
+  DeviceCtx* c = nullptr;
+  return device_ctx(&c) == SDD_OK ? c->sms : 1;
 }
 
 // ------------------------------------------------------------------------------- tensor maps
@@ -86,15 +89,15 @@ static EncodeTiledFn get_encode() {
   });
   return fn;
 }
-// act bf16 [N][H][W][C]  ->  box (64 c, 8 w, 18 h, 1 n), 128-byte swizzle, zero fill out of bounds
-static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, bool halo = false) {
+// act fp16 [N][H][W][C]  ->  halo box (64 c, 10 w, 18 h, 1 n), 128-byte swizzle, zero fill out of bounds
+static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int C) {
   EncodeTiledFn enc = get_encode();
   SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)(halo ? kHaloW : kTileW), (cuuint32_t)(kTileH + 2), 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)kHaloW, (cuuint32_t)(kTileH + 2), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -103,37 +106,19 @@ static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, i
   }
   return SDD_OK;
 }
-// wt bf16 [9 = kx*3+ky][Cout][Cin]  ->  box (64 ci, Cout, 3 taps)
+// wt fp16 [9 = kx*3+ky][Cout][Cin] -> box (64 ci, Cout/2 rows, 1 tap): each CTA of a pair keeps its N half resident
 static int make_wt_map(CUtensorMap* m, const void* base, int Cout, int Cin) {
-  EncodeTiledFn enc = get_encode();
-  SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
-  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
-  cuuint32_t box[3] = {64, (cuuint32_t)Cout, 3};
-  cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(wt) failed: " + std::to_string((int)r));
-    return SDD_ECUDA;
-  }
-  return SDD_OK;
-}
-
-// v2: wt bf16 [9][Cout][Cin] -> box (64 ci, Cout/2 rows, 1 tap): each CTA of a pair keeps its N half resident
-static int make_wt_map2(CUtensorMap* m, const void* base, int Cout, int Cin) {
   EncodeTiledFn enc = get_encode();
   SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, 9};
   cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)(Cout / 2), 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(wt2) failed: " + std::to_string((int)r));
+    set_error("cuTensorMapEncodeTiled(wt) failed: " + std::to_string((int)r));
     return SDD_ECUDA;
   }
   return SDD_OK;
@@ -157,51 +142,19 @@ static int make_attn_map(CUtensorMap* m, const void* base, int BH, int rows, int
   return SDD_OK;
 }
 
-// ------------------------------------------------------------------------------- conv launchers
-struct GnScratch {
-  float* partials;
-  int* counters;
-  float* meanrstd;
-};
-
-static int conv_tc_init() {
-  static bool done = false;
-  if (done) return SDD_OK;
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ConvCfg<64>::kSmemBytes));
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ConvCfg<128>::kSmemBytes));
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ConvCfg<64, true>::kSmemBytes));
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                ConvCfg<128, true>::kSmemBytes));
-  done = true;
-  return SDD_OK;
-}
-
-static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, __nv_bfloat16* out, BiasRef bias,
-                          GnScratch gn, int B, int H, int W, int Cin, int Cout, cudaStream_t st, bool halo = false) {
-  SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
-  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
-  ConvTcArgs a;
-  a.out = out; a.bias = bias;
-  a.partials = gn.partials; a.counters = gn.counters; a.meanrstd = gn.meanrstd;
-  a.B = B; a.H = H; a.W = W; a.Cin = Cin;
-  a.tiles_w = W / kTileW;
-  a.tiles_per_sample = (H / kTileH) * a.tiles_w;
-  a.num_tiles = B * a.tiles_per_sample;
-  int grid = std::min(a.num_tiles, num_sms());
-  SDD_TRY(conv_tc_init());
-  if (halo) {
-    if (Cout == 64)
-      conv3x3_tc_kernel<64, true><<<grid, kConvThreads, ConvCfg<64, true>::kSmemBytes, st>>>(tmA, tmB, a);
-    else
-      conv3x3_tc_kernel<128, true><<<grid, kConvThreads, ConvCfg<128, true>::kSmemBytes, st>>>(tmA, tmB, a);
-  } else if (Cout == 64)
-    conv3x3_tc_kernel<64><<<grid, kConvThreads, ConvCfg<64>::kSmemBytes, st>>>(tmA, tmB, a);
-  else
-    conv3x3_tc_kernel<128><<<grid, kConvThreads, ConvCfg<128>::kSmemBytes, st>>>(tmA, tmB, a);
-  SDD_LAUNCH_CHECK();
+// ------------------------------------------------------------------------------- conv launcher
+static int ensure_func_attrs() {
+  DeviceCtx* c = nullptr;
+  SDD_TRY(device_ctx(&c));
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  if (c->attrs) return SDD_OK;
+  const int reg_smem = conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, reg_smem));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, reg_smem));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
+  SDD_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+  c->attrs = true;
   return SDD_OK;
 }
 
@@ -210,33 +163,25 @@ struct GnInput3 {  // GroupNorm(4, Cin) + SiLU of the conv's input: fixed-point 
   const float* meanrstd;
   const float* gamma;
   const float* beta;
-  float* ab = nullptr;  // scratch [2][B][Cin] for gn_scale_shift_kernel (generation 4+); null: the kernel rebuilds the values
+  float* ab = nullptr;  // scratch [2][B][Cin] for gn_scale_shift_kernel
 };
 
-static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2, const __nv_bfloat16* in,
-                           __nv_bfloat16* out, BiasRef bias, GnInput3 gi, long long* out_sums, int B, int H, int W,
-                           int Cin, int Cout, cudaStream_t st, int dbg = 0, long long* trace = nullptr) {
+// Launch policy, from same-box A/B runs:
+//  * generation 5 (kRaw: TMA-filled raw ring behind 3 operand stages) for the two Cin != Cout layers (64->128 314 -> 287,
+//    128->64 369 -> 348 us per 32 x 256^2 chunk); 64->64 is slower with it (227 -> 244) and 128->128 has no room;
+//  * contiguous tile ranges for 64->64 only (382 -> 373 us per 64-sample chunk; 64->128 508 -> 515);
+//  * TMA L2 prefetch of a loader group's item after next on the register path (+3..6 %).
+static int launch_conv(const CUtensorMap& tmA_halo, const CUtensorMap& tmB, const act_t* in, act_t* out, BiasRef bias,
+                       GnInput3 gi, long long* out_sums, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "tcgen05 conv needs H % 16 == 0 and W % 8 == 0");
   SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "tcgen05 conv supports 64/128 channels");
   SDD_CHECK((size_t)B * H * W * Cin * 2 < ((size_t)1 << 32), "input tensor of one launch must be < 4 GB (32-bit offsets)");
-  static bool attr = false;
-  if (!attr) {
-    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
-    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
-    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
-    SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc3_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
-    attr = true;
-  }
+  SDD_TRY(ensure_func_attrs());
   ConvTc3Args a;
   a.in = in; a.out = out; a.bias = bias;
-  a.in_sums = gi.sums; a.in_meanrstd = gi.meanrstd; a.in_gamma = gi.gamma; a.in_beta = gi.beta;
   a.in_ab = nullptr;
-  static const bool no_ab = getenv("SDD_CONV_NO_AB") != nullptr;  // A/B: in-kernel scale / shift
-  if (gi.ab && (gi.sums || gi.meanrstd) && !no_ab && getenv("SDD_CONV_V3") == nullptr) {
+  if (gi.sums || gi.meanrstd) {
+    SDD_CHECK(gi.ab && gi.gamma && gi.beta, "fused GroupNorm needs gamma, beta and the scale/shift scratch");
     gn_scale_shift_kernel<<<B, Cin, 0, st>>>(gi.sums, gi.meanrstd, gi.gamma, gi.beta,
                                              (double)H * (double)W * (double)(Cin / 4), kGnEps, gi.ab, B, Cin);
     SDD_LAUNCH_CHECK();
@@ -250,81 +195,22 @@ static int launch_conv_tc3(const CUtensorMap& tmA_halo, const CUtensorMap& tmB2,
   a.num_pairs = (a.num_tiles + 1) / 2;
   a.stages = conv_tc3_stages(Cout, Cin);
   a.raw_slots = 0;
-  // contiguous tile ranges: before the scale / shift table they paid off for both Cin = 64 layers (64->64 399 -> 363 us,
-  // 64->128 545 -> 528 us per 64-sample chunk: the per-sample rebuild nearly vanished) and cost the Cin = 128 layers
-  // (128->128 899 -> 905); with the table (same-box A/B): 64->64 382 -> 373, 64->128 508 -> 515.  So: 64->64 only.
-  // (SDD_CONV_CONTIG = 0 / 1 forces it off / on everywhere for A/B)
-  static const int contig_env = getenv("SDD_CONV_CONTIG") ? atoi(getenv("SDD_CONV_CONTIG")) : -1;
-  a.contig = contig_env >= 0 ? contig_env : ((Cin == 64 && Cout == 64) ? 1 : 0);
-  static const int prefetch = getenv("SDD_CONV_PREFETCH") ? atoi(getenv("SDD_CONV_PREFETCH")) : 1;  // v4: TMA L2 prefetch of a loader group's item after next; measured +3..6 % (v3's paced prefetch warp: no effect)
-  a.prefetch = prefetch;
-  a.dbg = dbg;
-  a.trace = trace;
-  // generation 5 (kRaw): TMA-filled raw ring behind 3 operand stages.  Measured (32 x 256^2 chunk, us, v4 -> raw):
-  // 64->128 314 -> 287, 128->64 369 -> 348, 64->64 227 -> 244 (slower: one item per tile, the per-tile epilogue and
-  // hand-offs bind there, not the loads), 128->128 has no room for the ring.  So: the two Cin != Cout layers only.
-  // SDD_CONV_RAW=0 selects the register-path loader everywhere, =2 forces the ring wherever it fits (A/B).
-  static const int raw_env = getenv("SDD_CONV_RAW") ? atoi(getenv("SDD_CONV_RAW")) : 1;
-  static const int raw_stages = getenv("SDD_CONV_RAW_STAGES") ? atoi(getenv("SDD_CONV_RAW_STAGES")) : 3;
-  static const int raw_max = getenv("SDD_CONV_RAW_SLOTS") ? atoi(getenv("SDD_CONV_RAW_SLOTS")) : 4;
+  a.contig = (Cin == 64 && Cout == 64) ? 1 : 0;
+  a.prefetch = 1;
   bool use_raw = false;
-  if (raw_env && (raw_env == 2 || Cin != Cout) && !trace && getenv("SDD_CONV_V3") == nullptr) {
-    int slots = raw_max;
-    while (slots > 0 && conv_tc3_smem_bytes(Cout, Cin, raw_stages + slots) > kC2SmemLimit - 4096) --slots;
-    if (slots >= 3) { use_raw = true; a.stages = raw_stages; a.raw_slots = slots; }
+  if (Cin != Cout) {
+    constexpr int kRawStages = 3, kRawMaxSlots = 4;
+    int slots = kRawMaxSlots;
+    while (slots > 0 && conv_tc3_smem_bytes(Cout, Cin, kRawStages + slots) > kC2SmemLimit - 4096) --slots;
+    if (slots >= 3) { use_raw = true; a.stages = kRawStages; a.raw_slots = slots; }
   }
   const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages + a.raw_slots);
   const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
   if (use_raw) {
-    static bool attr5 = false;
-    if (!attr5) {
-      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kC2SmemLimit - 4096));
-      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kC2SmemLimit - 4096));
-      attr5 = true;
-    }
-    if (Cout == 64) conv3x3_tc4_kernel<64, false, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-    else conv3x3_tc4_kernel<128, false, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-    SDD_LAUNCH_CHECK();
-    return SDD_OK;
-  }
-  static const bool v4 = getenv("SDD_CONV_V3") == nullptr;  // product: two loader groups on alternating items (v4); SDD_CONV_V3=1 selects the single-group loader for A/B
-  if (v4) {
-    static bool attr4 = false;
-    if (!attr4) {
-      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
-      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
-      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    conv_tc3_smem_bytes(64, 128, conv_tc3_stages(64, 128))));
-      SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128))));
-      attr4 = true;
-    }
-    if (trace) {
-      if (Cout == 64) conv3x3_tc4_kernel<64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-      else conv3x3_tc4_kernel<128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-    } else if (Cout == 64) conv3x3_tc4_kernel<64><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-    else conv3x3_tc4_kernel<128><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-  } else if (trace) {  // timing-experiment instantiation with clock64 stamps
-    if (Cout == 64) conv3x3_tc3_kernel<64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-    else conv3x3_tc3_kernel<128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-  } else if (Cout == 64)
-    conv3x3_tc3_kernel<64><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-  else
-    conv3x3_tc3_kernel<128><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB2, a);
-  SDD_LAUNCH_CHECK();
-  return SDD_OK;
-}
-
-static int launch_apply(__nv_bfloat16* act, const float* meanrstd, const float* gamma, const float* beta, int B,
-                        int H, int W, int C, cudaStream_t st) {
-  size_t nvec = (size_t)H * W * C / 8;
-  int blocks = (int)std::min<size_t>((nvec + 256 * 8 - 1) / (256 * 8), 4096);
-  if (blocks < 1) blocks = 1;
-  gn_silu_apply_kernel<<<dim3(blocks, B), 256, 0, st>>>(act, meanrstd, gamma, beta, H * W, C);
+    if (Cout == 64) conv3x3_tc4_kernel<64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
+    else conv3x3_tc4_kernel<128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
+  } else if (Cout == 64) conv3x3_tc4_kernel<64><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
+  else conv3x3_tc4_kernel<128><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
   SDD_LAUNCH_CHECK();
   return SDD_OK;
 }
@@ -339,9 +225,8 @@ namespace {
 struct BlockParams {
   int cin, cout;
   const float *gn1_w, *gn1_b, *conv1_w, *conv1_b, *gn2_w, *gn2_b, *conv2_w, *conv2_b, *temb_w, *temb_b;
-  __nv_bfloat16 *conv1_wt, *conv2_wt;  // bf16 [kx][ky][Cout][Cin] (tensor-core convs only)
-  CUtensorMap tm_w1, tm_w2;      // v1 kernel: box (64, Cout, 3 taps)
-  CUtensorMap tm_w1h, tm_w2h;    // v2 kernel: box (64, Cout/2, 1 tap)
+  act_t *conv1_wt, *conv2_wt;    // fp16 [kx][ky][Cout][Cin] (tensor-core convs only)
+  CUtensorMap tm_w1h, tm_w2h;    // box (64 ci, Cout/2 rows, 1 tap)
 };
 
 constexpr int kBiasRow = 388;  // 64+128+128+64+1 = 385 per-block (conv2 bias + time_emb) values, padded to 16 B
@@ -354,15 +239,14 @@ constexpr int kGnLayers = 9;  // GroupNorms fed by a conv output: downs.0 gn2 ..
 struct Workspace {
   int cap_b = 0, H = 0, W = 0;  // chunk capacity and image size the buffers were built for
   int64_t generation = 0;       // bumped on every (re)allocation; captured graphs check it
-  __nv_bfloat16* act[2] = {nullptr, nullptr};
+  act_t* act[2] = {nullptr, nullptr};
   float* e1 = nullptr;
-  float* partials = nullptr;
+  float* partials = nullptr;  // stats_x_kernel only
   int* counters = nullptr;
   long long* gnsums = nullptr;  // 9 x [cap_b][4][2] fixed-point GroupNorm sums, one slab per GroupNorm layer (common.cuh)
   float* xstats = nullptr;    // [cap_b][2] (used when the caller has no stats of x)
   float* gn_ab = nullptr;     // [2][cap_b][128] fused GroupNorm+SiLU scale / shift of the layer being launched
-  CUtensorMap tm_act[2][2];   // [buffer][Cin == 128], v1 box (64, 8, 18)
-  CUtensorMap tm_halo[2][2];  // v2 halo box (64, 10, 18)
+  CUtensorMap tm_halo[2][2];  // [buffer][Cin == 128], halo box (64, 10, 18)
   void release() {
     cudaFree(act[0]); cudaFree(act[1]); cudaFree(e1); cudaFree(partials); cudaFree(counters);
     cudaFree(gnsums); cudaFree(xstats); cudaFree(gn_ab);
@@ -376,8 +260,9 @@ struct Workspace {
 
 struct sdd_unet {
   float* params = nullptr;  // one arena holding all 54 fp32 tensors
-  __nv_bfloat16* wt = nullptr;
+  act_t* wt = nullptr;
   float* freq = nullptr;    // [128]
+  int max_chunk = 0;        // sdd_unet_set_max_chunk: 0 = automatic
   const float *time_w1, *time_b1, *time_w2, *time_b2;
   BlockParams blk[5];
   Workspace ws;
@@ -388,11 +273,8 @@ struct sdd_unet {
 
 namespace {
 
-int chunk_for(int B, int H, int W) {
-  if (const char* e = getenv("SDD_CHUNK")) {
-    int c = atoi(e);
-    if (c > 0) return std::min(c, B);
-  }
+int chunk_for(const sdd_unet* u, int B, int H, int W) {
+  if (u->max_chunk > 0) return std::min(u->max_chunk, B);
   // Measured (tools/conv_chunk.py): the conv kernels are far from HBM-bound (<= 1.5 TB/s of traffic), while every
   // launch pays a fixed prologue (resident-weight load, TMEM alloc) and a partially filled last wave, so large
   // chunks win: 128->128 goes from 0.53 of peak at 3 samples to 0.65 at >= 16.  Cap a ping-pong buffer at 1.5 GB.
@@ -402,11 +284,11 @@ int chunk_for(int B, int H, int W) {
 }
 
 int ensure_workspace(sdd_unet* u, int B, int H, int W) {
-  int need = chunk_for(B, H, W);
+  int need = chunk_for(u, B, H, W);
   Workspace& ws = u->ws;
-  if (ws.cap_b >= need && ws.H == H && ws.W == W) return SDD_OK;
+  if (ws.cap_b >= need && ws.H == H && ws.W == W && (u->max_chunk == 0 || ws.cap_b == need)) return SDD_OK;
   ws.release();
-  size_t act_bytes = (size_t)need * H * W * 128 * sizeof(__nv_bfloat16);
+  size_t act_bytes = (size_t)need * H * W * 128 * sizeof(act_t);
   SDD_CUDA(cudaMalloc(&ws.act[0], act_bytes));
   SDD_CUDA(cudaMalloc(&ws.act[1], act_bytes));
   SDD_CUDA(cudaMalloc(&ws.e1, (size_t)need * H * W * sizeof(float)));
@@ -417,10 +299,8 @@ int ensure_workspace(sdd_unet* u, int B, int H, int W) {
   SDD_CUDA(cudaMalloc(&ws.gn_ab, (size_t)2 * need * 128 * sizeof(float)));
   SDD_CUDA(cudaMalloc(&ws.xstats, (size_t)need * 2 * sizeof(float)));
   for (int bi = 0; bi < 2; ++bi) {
-    SDD_TRY(make_act_map(&ws.tm_act[bi][0], ws.act[bi], need, H, W, 64));
-    SDD_TRY(make_act_map(&ws.tm_act[bi][1], ws.act[bi], need, H, W, 128));
-    SDD_TRY(make_act_map(&ws.tm_halo[bi][0], ws.act[bi], need, H, W, 64, true));
-    SDD_TRY(make_act_map(&ws.tm_halo[bi][1], ws.act[bi], need, H, W, 128, true));
+    SDD_TRY(make_act_map(&ws.tm_halo[bi][0], ws.act[bi], need, H, W, 64));
+    SDD_TRY(make_act_map(&ws.tm_halo[bi][1], ws.act[bi], need, H, W, 128));
   }
   ws.cap_b = need; ws.H = H; ws.W = W;
   ++ws.generation;
@@ -481,29 +361,23 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     dim3 eg = egrid; eg.z = nb;
     // downs.0: GN(1,1)+SiLU fused into the 1->64 conv; raw result in act[0], its GroupNorm(4,64) sums -> sums(0)
     const BlockParams& d0 = u->blk[0];
-    static const bool conv_in_simt = getenv("SDD_CONV_IN_SIMT") != nullptr;  // A/B: fp32 CUDA-core version
-    if (conv_in_simt)
-      conv_in_kernel<<<eg, 256, 0, st>>>(xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0],
-                                         sums(0), H, W);
-    else
     {
       const int in_tiles = (int)(eg.x * eg.y * eg.z);
-      static const int in_cps = getenv("SDD_CIN_CPS") ? atoi(getenv("SDD_CIN_CPS")) : 2;  // persistent CTAs per SM
-      conv_in_mma_kernel<<<std::min(in_tiles, in_cps * num_sms()), 256, 0, st>>>(
+      conv_in_mma_kernel<<<std::min(in_tiles, 2 * num_sms()), 256, 0, st>>>(  // two persistent CTAs per SM
           xc, xs, d0.gn1_w, d0.gn1_b, d0.conv1_w, bias_const(d0.conv1_b), ws.act[0], sums(0), H, W, (int)eg.x, (int)eg.y,
           in_tiles);
     }
     SDD_LAUNCH_CHECK();
     // every tensor-core conv normalises + activates its own input (GroupNorm+SiLU fused on the operand path)
-    SDD_TRY(launch_conv_tc3(ws.tm_halo[0][0], d0.tm_w2h, ws.act[0], ws.act[1], bias_time(0),
+    SDD_TRY(launch_conv(ws.tm_halo[0][0], d0.tm_w2h, ws.act[0], ws.act[1], bias_time(0),
                             GnInput3{sums(0), nullptr, d0.gn2_w, d0.gn2_b, ws.gn_ab}, sums(1), nb, H, W, 64, 64, st));
     int cur = 1, gi = 1;
     for (int bi = 1; bi <= 3; ++bi) {
       const BlockParams& p = u->blk[bi];
-      SDD_TRY(launch_conv_tc3(ws.tm_halo[cur][p.cin == 128], p.tm_w1h, ws.act[cur], ws.act[cur ^ 1], bias_const(p.conv1_b),
+      SDD_TRY(launch_conv(ws.tm_halo[cur][p.cin == 128], p.tm_w1h, ws.act[cur], ws.act[cur ^ 1], bias_const(p.conv1_b),
                               GnInput3{sums(gi), nullptr, p.gn1_w, p.gn1_b, ws.gn_ab}, sums(gi + 1), nb, H, W, p.cin, p.cout, st));
       cur ^= 1; ++gi;
-      SDD_TRY(launch_conv_tc3(ws.tm_halo[cur][p.cout == 128], p.tm_w2h, ws.act[cur], ws.act[cur ^ 1], bias_time(bi),
+      SDD_TRY(launch_conv(ws.tm_halo[cur][p.cout == 128], p.tm_w2h, ws.act[cur], ws.act[cur ^ 1], bias_time(bi),
                               GnInput3{sums(gi), nullptr, p.gn2_w, p.gn2_b, ws.gn_ab}, sums(gi + 1), nb, H, W, p.cout, p.cout, st));
       cur ^= 1; ++gi;
     }
@@ -571,22 +445,21 @@ int sdd_unet_create(sdd_unet_t** out, const float* const* tensors, int num_tenso
     if (b.cin >= 64 && b.cout >= 64) wt_elems += (size_t)9 * b.cin * b.cout;
     if (b.cout >= 64) wt_elems += (size_t)9 * b.cout * b.cout;
   }
-  if (cudaMalloc(&u->wt, wt_elems * sizeof(__nv_bfloat16)) != cudaSuccess) { set_error("cudaMalloc(wt) failed"); return fail(SDD_ENOMEM); }
-  __nv_bfloat16* wp = u->wt;
+  if (cudaMalloc(&u->wt, wt_elems * sizeof(act_t)) != cudaSuccess) { set_error("cudaMalloc(wt) failed"); return fail(SDD_ENOMEM); }
+  act_t* wp = u->wt;
   for (int i = 0; i < 5; ++i) {
     BlockParams& b = u->blk[i];
-    auto conv = [&](const float* w, int cout, int cin, __nv_bfloat16** dst, CUtensorMap* tm, CUtensorMap* tmh) -> int {
+    auto conv = [&](const float* w, int cout, int cin, act_t** dst, CUtensorMap* tmh) -> int {
       int total_w = 9 * cout * cin;
-      conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wp, cout, cin);
+      conv_weight_to_act_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wp, cout, cin);
       SDD_LAUNCH_CHECK();
       *dst = wp;
-      SDD_TRY(make_wt_map(tm, wp, cout, cin));
-      SDD_TRY(make_wt_map2(tmh, wp, cout, cin));
+      SDD_TRY(make_wt_map(tmh, wp, cout, cin));
       wp += total_w;
       return SDD_OK;
     };
-    if (b.cin >= 64 && b.cout >= 64) { int r = conv(b.conv1_w, b.cout, b.cin, &b.conv1_wt, &b.tm_w1, &b.tm_w1h); if (r) return fail(r); }
-    if (b.cout >= 64) { int r = conv(b.conv2_w, b.cout, b.cout, &b.conv2_wt, &b.tm_w2, &b.tm_w2h); if (r) return fail(r); }
+    if (b.cin >= 64 && b.cout >= 64) { int r = conv(b.conv1_w, b.cout, b.cin, &b.conv1_wt, &b.tm_w1h); if (r) return fail(r); }
+    if (b.cout >= 64) { int r = conv(b.conv2_w, b.cout, b.cout, &b.conv2_wt, &b.tm_w2h); if (r) return fail(r); }
   }
   // sinusoid frequencies exactly as unet.py:14 evaluates them in fp32
   float hf[kTimeDim / 2];
@@ -608,8 +481,19 @@ int sdd_unet_destroy(sdd_unet_t* u) {
   return SDD_OK;
 }
 
+int sdd_unet_set_max_chunk(sdd_unet_t* u, int max_samples) {
+  SDD_CHECK(u && max_samples >= 0, "bad argument");
+  u->max_chunk = max_samples;
+  return SDD_OK;
+}
+
 int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps_out, int B, int H, int W,
                      void* stream) {
+  return sdd_unet_forward_xstats(u, x, nullptr, t, eps_out, B, H, W, stream);
+}
+
+int sdd_unet_forward_xstats(sdd_unet_t* u, const float* x, const float* xstats, const int64_t* t, float* eps_out, int B,
+                            int H, int W, void* stream) {
   SDD_CHECK(u && x && t && eps_out, "null argument");
   SDD_CHECK(B >= 1 && H >= 16 && W >= 8, "bad shape");
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
@@ -626,7 +510,7 @@ int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps
   }
   SDD_TRY(time_bias_rows(u, t, B, u->t_emb0, u->t_h1, u->t_emb, u->t_bias, st));
   BiasRef tb{u->t_bias, nullptr, 0, kBiasRow};
-  return unet_forward_impl(u, x, nullptr, tb, eps_out, B, H, W, st);
+  return unet_forward_impl(u, x, xstats, tb, eps_out, B, H, W, st);
 }
 
 // ------------------------------------------------------------------------------- fused update
@@ -635,53 +519,36 @@ size_t sdd_superpose_update_workspace(int B, int D, int M) { return update_works
 }  // extern "C"
 
 namespace sdd {
-template <int STEPS>
-static void launch_update_kernel(const UpdateArgs& a, dim3 grid, cudaStream_t st) {
-  switch (a.M) {
-    case 1: superpose_update_kernel<1, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
-    case 2: superpose_update_kernel<2, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
-    case 3: superpose_update_kernel<3, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
-    default: superpose_update_kernel<4, STEPS><<<grid, kUpdThreads, 0, st>>>(a); break;
-  }
-}
 
-int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st, cudaEvent_t after_update = nullptr,
-                            bool finalize = true) {
+int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st) {
   SDD_CHECK(a.M >= 1 && a.M <= kMaxModels, "1 <= M <= 4");
   SDD_CHECK(a.D % 4 == 0 && a.D > 0 && a.B > 0, "D must be a positive multiple of 4");
-  a.partials = reinterpret_cast<float*>(workspace);
-  a.and_partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + update_ws_part_bytes(a.B, a.D));
-  a.kappa_in = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + update_ws_part_bytes(a.B, a.D) +
-                                        update_ws_and_bytes(a.B, a.D));
   SDD_CHECK(a.mode == 0 || a.mode == 1, "mode must be 0 (OR) or 1 (AND)");
-  {
-    // sub-steps per segment: a build-time constant (or an experiment override), never a function of B
-    static const int steps = getenv("SDD_UPD_STEPS") ? atoi(getenv("SDD_UPD_STEPS")) : kSegSteps;
-    SDD_CHECK(steps == 1 || steps == 2 || steps == 4, "SDD_UPD_STEPS must be 1, 2 or 4");
-    a.nblk = update_blocks_per_sample(a.D, steps);
-    dim3 grid(a.nblk, a.B);
-    if (a.mode == 1) {  // AND: Gram pass + per-sample solve write kappa_in before the update pass reads it
-      switch (a.M) {
-        case 1: superpose_and_gram_kernel<1><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<1><<<a.B, 256, 0, st>>>(a); break;
-        case 2: superpose_and_gram_kernel<2><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<2><<<a.B, 256, 0, st>>>(a); break;
-        case 3: superpose_and_gram_kernel<3><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<3><<<a.B, 256, 0, st>>>(a); break;
-        default: superpose_and_gram_kernel<4><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<4><<<a.B, 256, 0, st>>>(a); break;
-      }
-      ++g_launches;
-      SDD_LAUNCH_CHECK();
+  char* w = reinterpret_cast<char*>(workspace);
+  a.partials = reinterpret_cast<float*>(w);
+  w += update_ws_part_bytes(a.B, a.D);
+  a.and_partials = reinterpret_cast<float*>(w);
+  w += update_ws_and_bytes(a.B, a.D);
+  a.kappa_in = reinterpret_cast<float*>(w);
+  w += update_ws_kappa_bytes(a.B);
+  a.counters = reinterpret_cast<int*>(w);
+  a.nblk = update_blocks_per_sample(a.D, kSegSteps);  // a function of D only, never of B (shard-invariant reduction tree)
+  dim3 grid(a.nblk, a.B);
+  if (a.mode == 1) {  // AND: Gram pass + per-sample solve write kappa_in before the update pass reads it
+    switch (a.M) {
+      case 1: superpose_and_gram_kernel<1><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<1><<<a.B, 256, 0, st>>>(a); break;
+      case 2: superpose_and_gram_kernel<2><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<2><<<a.B, 256, 0, st>>>(a); break;
+      case 3: superpose_and_gram_kernel<3><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<3><<<a.B, 256, 0, st>>>(a); break;
+      default: superpose_and_gram_kernel<4><<<grid, kUpdThreads, 0, st>>>(a); superpose_and_solve_kernel<4><<<a.B, 256, 0, st>>>(a); break;
     }
-    if (steps == 1) launch_update_kernel<1>(a, grid, st);
-    else if (steps == 2) launch_update_kernel<2>(a, grid, st);
-    else launch_update_kernel<4>(a, grid, st);
+    ++g_launches;
+    SDD_LAUNCH_CHECK();
   }
-  SDD_LAUNCH_CHECK();
-  if (after_update) cudaEventRecord(after_update, st);  // roofline timing of the HBM pass alone
-  if (!finalize) return SDD_OK;
   switch (a.M) {
-    case 1: superpose_finalize_kernel<1><<<a.B, 256, 0, st>>>(a); break;
-    case 2: superpose_finalize_kernel<2><<<a.B, 256, 0, st>>>(a); break;
-    case 3: superpose_finalize_kernel<3><<<a.B, 256, 0, st>>>(a); break;
-    default: superpose_finalize_kernel<4><<<a.B, 256, 0, st>>>(a); break;
+    case 1: superpose_update_kernel<1, kSegSteps><<<grid, kUpdThreads, 0, st>>>(a); break;
+    case 2: superpose_update_kernel<2, kSegSteps><<<grid, kUpdThreads, 0, st>>>(a); break;
+    case 3: superpose_update_kernel<3, kSegSteps><<<grid, kUpdThreads, 0, st>>>(a); break;
+    default: superpose_update_kernel<4, kSegSteps><<<grid, kUpdThreads, 0, st>>>(a); break;
   }
   SDD_LAUNCH_CHECK();
   return SDD_OK;
@@ -699,7 +566,33 @@ __global__ void copy_f32_kernel(float* dst, const float* src, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     dst[i] = src[i];
 }
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+// start of a sampler run: this call's parameters into the device block the captured step graph reads, step = 0
+__global__ void begin_run_kernel(RunParams* dst, RunParams v, int* step) {
+  *dst = v;
+  *step = 0;
+}
+
+static int update_op(const float* x_in, float* x_out, const float* eps, const float* noise, const float* logq,
+                     float* logq_out, float* kappa_out, float* xstats_out, int B, int D, int M, float alpha,
+                     float alpha_bar, float beta, float temperature, const float* bias, uint64_t seed,
+                     int64_t sample_offset, int draw_index, int mode, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  SDD_CHECK(x_in && x_out && eps && logq && logq_out && workspace, "null argument");
+  SDD_CHECK(B > 0 && D > 0 && M >= 1 && M <= kMaxModels, "bad shape");
+  SDD_CHECK(workspace_bytes >= update_workspace_bytes(B, D, M), "workspace too small");
+  SDD_TRY(device_check());
+  UpdateArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x_in = x_in; a.x_out = x_out; a.eps = eps;
+  a.logq = logq; a.logq_out = logq_out; a.kappa_out = kappa_out; a.xstats_out = xstats_out;
+  a.sc.alpha = alpha; a.sc.alpha_bar = alpha_bar; a.sc.beta = beta;
+  a.sc.draw_index = noise ? 0 : draw_index;
+  step_scalars_fill(a.sc);
+  a.rv.noise = noise; a.rv.noise_step_stride = 0; a.rv.seed = seed; a.rv.sample_offset = sample_offset;
+  a.rv.temperature = temperature; a.rv.bias = bias;
+  a.B = B; a.D = D; a.M = M; a.mode = mode;
+  return launch_superpose_update(a, workspace, (cudaStream_t)stream);
+}
 }  // namespace sdd
 
 extern "C" {
@@ -709,38 +602,16 @@ int sdd_superpose_update(const float* x_in, float* x_out, const float* eps, cons
                          float alpha_bar, float beta, float temperature, const float* bias, uint64_t seed,
                          int64_t sample_offset, int draw_index, void* workspace, size_t workspace_bytes,
                          void* stream) {
-  SDD_CHECK(x_in && x_out && eps && logq && logq_out && workspace, "null argument");
-  SDD_CHECK(workspace_bytes >= update_workspace_bytes(B, D, M), "workspace too small");
-  SDD_TRY(device_check());
-  UpdateArgs a;
-  memset(&a, 0, sizeof(a));
-  a.x_in = x_in; a.x_out = x_out; a.eps = eps; a.noise = noise; a.noise_step_stride = 0;
-  a.logq = logq; a.logq_out = logq_out; a.kappa_out = kappa_out; a.xstats_out = xstats_out;
-  a.sc.alpha = alpha; a.sc.alpha_bar = alpha_bar; a.sc.beta = beta;
-  a.sc.draw_index = noise ? 0 : draw_index;
-  step_scalars_fill(a.sc);
-  a.temperature = temperature; a.bias = bias; a.seed = seed; a.sample_offset = sample_offset;
-  a.B = B; a.D = D; a.M = M;
-  return launch_superpose_update(a, workspace, (cudaStream_t)stream);
+  return update_op(x_in, x_out, eps, noise, logq, logq_out, kappa_out, xstats_out, B, D, M, alpha, alpha_bar, beta,
+                   temperature, bias, seed, sample_offset, draw_index, 0, workspace, workspace_bytes, stream);
 }
 
 int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, const float* noise, const float* logq,
                              float* logq_out, float* kappa_out, float* xstats_out, int B, int D, int M, float alpha,
                              float alpha_bar, float beta, uint64_t seed, int64_t sample_offset, int draw_index,
                              void* workspace, size_t workspace_bytes, void* stream) {
-  SDD_CHECK(x_in && x_out && eps && logq && logq_out && workspace, "null argument");
-  SDD_CHECK(workspace_bytes >= update_workspace_bytes(B, D, M), "workspace too small");
-  SDD_TRY(device_check());
-  UpdateArgs a;
-  memset(&a, 0, sizeof(a));
-  a.x_in = x_in; a.x_out = x_out; a.eps = eps; a.noise = noise; a.noise_step_stride = 0;
-  a.logq = logq; a.logq_out = logq_out; a.kappa_out = kappa_out; a.xstats_out = xstats_out;
-  a.sc.alpha = alpha; a.sc.alpha_bar = alpha_bar; a.sc.beta = beta;
-  a.sc.draw_index = noise ? 0 : draw_index;
-  step_scalars_fill(a.sc);
-  a.temperature = 1.0f; a.seed = seed; a.sample_offset = sample_offset;
-  a.B = B; a.D = D; a.M = M; a.mode = 1;
-  return launch_superpose_update(a, workspace, (cudaStream_t)stream);
+  return update_op(x_in, x_out, eps, noise, logq, logq_out, kappa_out, xstats_out, B, D, M, alpha, alpha_bar, beta, 1.0f,
+                   nullptr, seed, sample_offset, draw_index, 1, workspace, workspace_bytes, stream);
 }
 
 int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
@@ -754,11 +625,7 @@ int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, i
   SDD_TRY(make_attn_map(&tmQ, q, BH, S, kAttnD, kAttnBM));
   SDD_TRY(make_attn_map(&tmK, k, BH, S, kAttnD, kAttnBN));
   SDD_TRY(make_attn_map(&tmVt, vt, BH, kAttnD, S, kAttnD));
-  static bool attr = false;
-  if (!attr) {
-    SDD_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
-    attr = true;
-  }
+  SDD_TRY(ensure_func_attrs());
   AttnArgs a;
   a.out = reinterpret_cast<__nv_bfloat16*>(out); a.S = S; a.BH = BH;
   a.scale_log2e = scale * 1.4426950408889634f;
@@ -875,20 +742,21 @@ struct sdd_sampler {
   float* tables[kMaxModels] = {nullptr, nullptr, nullptr, nullptr};  // [T][385], row = loop iteration
   StepScalars* sched = nullptr;  // [T], row = loop iteration (t = T-1-row)
   int* step = nullptr;
+  RunParams* rp = nullptr;       // per-call parameters, rewritten by begin_run_kernel
   float *x = nullptr, *eps = nullptr, *logq = nullptr, *xstats = nullptr;
   void* upd_ws = nullptr;
   float* stat_partials = nullptr; int* stat_counters = nullptr;
   cudaStream_t work = nullptr;   // private stream: graph capture is illegal on the legacy default stream
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t exec = nullptr;
-  sdd_sample_args captured;  // arguments baked into `exec`
+  int captured_mode = -1;        // the only per-call argument that changes the graph's topology
   int64_t captured_gen[kMaxModels] = {0, 0, 0, 0};
-  int64_t launches_per_step = 0, launches_fixed = 0;
+  int64_t launches_per_step = 0, launches_fixed = 0, graph_instantiations = 0;
 };
 
 namespace {
 
-int enqueue_step(sdd_sampler* s, const sdd_sample_args& ar, cudaStream_t st) {
+int enqueue_step(sdd_sampler* s, int mode, cudaStream_t st) {
   for (int m = 0; m < s->M; ++m) {
     BiasRef tb{s->tables[m], s->step, kBiasRow, 0};
     SDD_TRY(unet_forward_impl(s->models[m], s->x, s->xstats, tb, s->eps + (size_t)m * s->B * s->D, s->B, s->H, s->W,
@@ -897,22 +765,11 @@ int enqueue_step(sdd_sampler* s, const sdd_sample_args& ar, cudaStream_t st) {
   UpdateArgs a;
   memset(&a, 0, sizeof(a));
   a.x_in = s->x; a.x_out = s->x; a.eps = s->eps;
-  a.noise = ar.noise_stack; a.noise_step_stride = (int64_t)s->B * s->D;
   a.logq = s->logq; a.logq_out = s->logq; a.kappa_out = nullptr; a.xstats_out = s->xstats;
-  a.kappa_traj = ar.kappa_traj; a.logq_traj = ar.logq_traj;
-  a.table = s->sched; a.step_ptr = s->step;
-  a.temperature = ar.temperature; a.bias = ar.bias; a.seed = ar.seed; a.sample_offset = ar.sample_offset;
-  a.B = s->B; a.D = s->D; a.M = s->M; a.mode = ar.mode;
-  SDD_TRY(launch_superpose_update(a, s->upd_ws, st));
-  advance_step_kernel<<<1, 1, 0, st>>>(s->step);
-  SDD_LAUNCH_CHECK();
-  return SDD_OK;
-}
-
-bool same_args(const sdd_sample_args& a, const sdd_sample_args& b) {
-  return a.noise_stack == b.noise_stack && a.seed == b.seed && a.sample_offset == b.sample_offset &&
-         a.temperature == b.temperature && a.bias == b.bias && a.kappa_traj == b.kappa_traj &&
-         a.logq_traj == b.logq_traj && a.mode == b.mode;
+  a.table = s->sched; a.step_ptr = s->step; a.advance_step = 1;
+  a.rp = s->rp;
+  a.B = s->B; a.D = s->D; a.M = s->M; a.mode = mode;
+  return launch_superpose_update(a, s->upd_ws, st);
 }
 
 }  // namespace
@@ -941,6 +798,7 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
   S_CUDA(cudaMalloc(&s->logq, (size_t)B * M * sizeof(float)));
   S_CUDA(cudaMalloc(&s->xstats, (size_t)B * 2 * sizeof(float)));
   S_CUDA(cudaMalloc(&s->step, sizeof(int)));
+  S_CUDA(cudaMalloc(&s->rp, sizeof(RunParams)));
   size_t uw = update_workspace_bytes(B, s->D, M);
   S_CUDA(cudaMalloc(&s->upd_ws, uw));
   S_CUDA(cudaMemsetAsync(s->upd_ws, 0, uw, st));
@@ -986,14 +844,22 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
 
 int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream) {
   SDD_CHECK(s && args && args->x_out, "null argument");
+  SDD_CHECK(args->mode == 0 || args->mode == 1, "mode must be 0 (OR) or 1 (AND)");
   cudaStream_t user = (cudaStream_t)stream;
   cudaStream_t st = s->work;  // everything runs here, ordered after / before the caller's stream by events
   SDD_CUDA(cudaEventRecord(s->ev_in, user));
   SDD_CUDA(cudaStreamWaitEvent(st, s->ev_in, 0));
   const size_t BD = (size_t)s->B * s->D;
   const int64_t l0 = g_launches;
-  // --- x_T, logq = 0, step = 0, GN(1,1) stats of x_T
-  SDD_CUDA(cudaMemsetAsync(s->step, 0, sizeof(int), st));
+  // --- this call's parameters -> device block read by the (possibly already instantiated) step graph; step = 0
+  RunParams rv;
+  memset(&rv, 0, sizeof(rv));
+  rv.noise = args->noise_stack; rv.noise_step_stride = (int64_t)BD;
+  rv.seed = args->seed; rv.sample_offset = args->sample_offset; rv.temperature = args->temperature;
+  rv.bias = args->bias; rv.kappa_traj = args->kappa_traj; rv.logq_traj = args->logq_traj; rv.x_traj = args->x_traj;
+  begin_run_kernel<<<1, 1, 0, st>>>(s->rp, rv, s->step);
+  SDD_LAUNCH_CHECK();
+  // --- x_T, logq = 0, GN(1,1) stats of x_T
   SDD_CUDA(cudaMemsetAsync(s->logq, 0, (size_t)s->B * s->M * sizeof(float), st));
   if (args->logq_traj) SDD_CUDA(cudaMemsetAsync(args->logq_traj, 0, (size_t)s->B * s->M * sizeof(float), st));
   if (args->noise_stack) {
@@ -1006,34 +872,40 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
   }
   stats_x_kernel<<<dim3(kStatsBlocks, s->B), 256, 0, st>>>(s->x, s->D, s->stat_partials, s->stat_counters, s->xstats);
   SDD_LAUNCH_CHECK();
+  if (args->x_traj) SDD_CUDA(cudaMemcpyAsync(args->x_traj, s->x, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const int64_t l1 = g_launches;
   for (int m = 0; m < s->M; ++m) SDD_TRY(ensure_workspace(s->models[m], s->B, s->H, s->W));
   // --- T steps.  Step 0 always runs eagerly (so every kernel is loaded before a capture begins).
   {
     const int64_t lk = g_launches;
-    SDD_TRY(enqueue_step(s, *args, st));
+    SDD_TRY(enqueue_step(s, args->mode, st));
     s->launches_per_step = g_launches - lk;
   }
   if (args->use_graph && s->T > 1) {
-    bool stale = !s->exec || !same_args(s->captured, *args);
+    // The graph holds only pointers to sampler-owned device state (x, eps, logq, step counter, RunParams block, bias
+    // tables): seed, shard offset, noise stack, temperature, bias and trajectory buffers change WITHOUT a re-capture.
+    bool stale = !s->exec || s->captured_mode != args->mode;
     for (int m = 0; m < s->M; ++m) stale = stale || s->captured_gen[m] != s->models[m]->ws.generation;
     if (stale) {
       if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
       cudaGraph_t graph = nullptr;
+      const int64_t lk = g_launches;
       SDD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_step(s, *args, st);
+      int rc = enqueue_step(s, args->mode, st);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);  // always leave capture mode, even on error
+      g_launches = lk;                                    // captured, not launched
       if (rc != SDD_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
       SDD_CUDA(ce);
       ce = cudaGraphInstantiate(&s->exec, graph, 0);
       cudaGraphDestroy(graph);
       SDD_CUDA(ce);
-      s->captured = *args;
+      s->captured_mode = args->mode;
+      ++s->graph_instantiations;
       for (int m = 0; m < s->M; ++m) s->captured_gen[m] = s->models[m]->ws.generation;
     }
     for (int k = 1; k < s->T; ++k) SDD_CUDA(cudaGraphLaunch(s->exec, st));
   } else {
-    for (int k = 1; k < s->T; ++k) SDD_TRY(enqueue_step(s, *args, st));
+    for (int k = 1; k < s->T; ++k) SDD_TRY(enqueue_step(s, args->mode, st));
   }
   s->launches_fixed = (l1 - l0) + 1;
   int blocks = (int)std::min<size_t>((BD + 255) / 256, 2048);
@@ -1048,6 +920,8 @@ int64_t sdd_sampler_launches_per_run(const sdd_sampler_t* s) {
   return s ? s->launches_fixed + (int64_t)s->T * s->launches_per_step : 0;
 }
 
+int64_t sdd_sampler_graph_instantiations(const sdd_sampler_t* s) { return s ? s->graph_instantiations : 0; }
+
 int sdd_sampler_destroy(sdd_sampler_t* s) {
   if (!s) return SDD_OK;
   if (s->work) cudaStreamSynchronize(s->work);
@@ -1056,115 +930,56 @@ int sdd_sampler_destroy(sdd_sampler_t* s) {
   if (s->ev_out) cudaEventDestroy(s->ev_out);
   if (s->work) cudaStreamDestroy(s->work);
   for (int m = 0; m < kMaxModels; ++m) cudaFree(s->tables[m]);
-  cudaFree(s->sched); cudaFree(s->step); cudaFree(s->x); cudaFree(s->eps); cudaFree(s->logq); cudaFree(s->xstats);
-  cudaFree(s->upd_ws); cudaFree(s->stat_partials); cudaFree(s->stat_counters);
+  cudaFree(s->sched); cudaFree(s->step); cudaFree(s->rp); cudaFree(s->x); cudaFree(s->eps); cudaFree(s->logq);
+  cudaFree(s->xstats); cudaFree(s->upd_ws); cudaFree(s->stat_partials); cudaFree(s->stat_counters);
   delete s;
   return SDD_OK;
 }
 
 // ------------------------------------------------------------------------------- operator entry points
-int sdd_conv3x3_nhwc(const void* act, const float* w, const float* bias, int64_t bias_batch_stride, void* out,
-                     float* gn_meanrstd, int B, int H, int W, int Cin, int Cout, int impl, void* stream) {
-  SDD_CHECK(act && w && bias && out, "null argument");
-  SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "Cin, Cout must be 64 or 128");
-  SDD_TRY(device_check());
-  cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* wt = nullptr;
-  float* partials = nullptr; int* counters = nullptr; float* mr = nullptr;
-  const int total_w = 9 * Cout * Cin;
-  SDD_CUDA(cudaMalloc(&wt, (size_t)total_w * sizeof(__nv_bfloat16)));
-  conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
-  ++g_launches;
-  BiasRef br{bias, nullptr, 0, bias_batch_stride};
-  int rc = SDD_OK;
-  if (impl == 0 || impl == 2) {
-    const int tiles_ps = (H / kTileH) * (W / kTileW);
-    CUtensorMap tmA, tmB;
-    rc = (H % kTileH == 0 && W % kTileW == 0) ? SDD_OK : SDD_EINVAL;
-    if (rc != SDD_OK) set_error("H must be a multiple of 16 and W a multiple of 8");
-    if (rc == SDD_OK && cudaMalloc(&partials, (size_t)B * tiles_ps * 8 * sizeof(float)) != cudaSuccess) rc = SDD_ENOMEM;
-    if (rc == SDD_OK && cudaMalloc(&counters, (size_t)B * sizeof(int)) != cudaSuccess) rc = SDD_ENOMEM;
-    if (rc == SDD_OK && cudaMalloc(&mr, (size_t)B * 8 * sizeof(float)) != cudaSuccess) rc = SDD_ENOMEM;
-    if (rc == SDD_OK) cudaMemsetAsync(counters, 0, (size_t)B * sizeof(int), st);
-    if (rc == SDD_OK) rc = make_act_map(&tmA, act, B, H, W, Cin, impl == 2);
-    if (rc == SDD_OK) rc = make_wt_map(&tmB, wt, Cout, Cin);
-    if (rc == SDD_OK)
-      rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st,
-                          impl == 2);
-    if (rc == SDD_OK && gn_meanrstd)
-      cudaMemcpyAsync(gn_meanrstd, mr, (size_t)B * 8 * sizeof(float), cudaMemcpyDeviceToDevice, st);
-  } else {
-    size_t total = (size_t)B * H * W * Cout;
-    conv3x3_simt_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)act, wt, br,
-                                                                        (__nv_bfloat16*)out, B, H, W, Cin, Cout);
-    ++g_launches;
-    if (gn_meanrstd) {
-      gn_stats_nhwc_kernel<<<B * 4, 256, 0, st>>>((const __nv_bfloat16*)out, gn_meanrstd, H * W, Cout);
-      ++g_launches;
-    }
-  }
-  cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr);
-  if (rc != SDD_OK) return rc;
-  if (e != cudaSuccess) { set_error(std::string("conv3x3: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
-  e = cudaGetLastError();
-  if (e != cudaSuccess) { set_error(std::string("conv3x3 launch: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
-  return SDD_OK;
-}
-
-// Kernel-only timing for the roofline: `iters` launches of the tcgen05 conv at one shape, each bracketed by
-// CUDA events on the launching stream, with `flush_bytes` of `flush` rewritten before every launch (L2 flush).
+// Kernel-only timing for the roofline: `iters` launches of the product conv at one shape, each bracketed by CUDA events
+// on the launching stream, with `flush_bytes` of `flush` rewritten before every launch (L2 flush).
 int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,
                         int Cout, int impl, int iters, void* flush, size_t flush_bytes, float* ms_host, void* stream) {
   SDD_CHECK(act && w && bias && out && ms_host && iters > 0, "bad argument");
+  SDD_CHECK(impl == 1 || impl == 2, "impl: 1 = conv alone, 2 = with the fused GroupNorm+SiLU");
   SDD_CHECK((Cin == 64 || Cin == 128) && (Cout == 64 || Cout == 128), "Cin, Cout must be 64 or 128");
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
   SDD_TRY(device_check());
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* wt = nullptr; float* partials = nullptr; int* counters = nullptr; float* mr = nullptr;
+  act_t* wt = nullptr;
   float* gin = nullptr;  // identity GroupNorm input: mean 0, rstd 1 | gamma 1 | beta 0
+  long long* osums = nullptr;
+  float* gn_ab = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  const int total_w = 9 * Cout * Cin, tiles_ps = (H / kTileH) * (W / kTileW);
+  const int total_w = 9 * Cout * Cin;
   int rc = SDD_OK;
   CUtensorMap tmA, tmB;
-  if (cudaMalloc(&wt, (size_t)total_w * 2) != cudaSuccess || cudaMalloc(&partials, (size_t)B * tiles_ps * 32) != cudaSuccess ||
-      cudaMalloc(&counters, (size_t)B * 4) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 32) != cudaSuccess ||
-      cudaMalloc(&gin, ((size_t)B * 8 + 256) * 4) != cudaSuccess) rc = SDD_ENOMEM;
+  if (cudaMalloc(&wt, (size_t)total_w * 2) != cudaSuccess || cudaMalloc(&gin, ((size_t)B * 8 + 256) * 4) != cudaSuccess ||
+      cudaMalloc(&osums, (size_t)B * 8 * sizeof(long long)) != cudaSuccess ||
+      cudaMalloc(&gn_ab, (size_t)2 * B * Cin * sizeof(float)) != cudaSuccess) {
+    set_error("cudaMalloc failed"); rc = SDD_ENOMEM;
+  }
   if (rc == SDD_OK) {
     std::vector<float> h((size_t)B * 8 + 256, 0.f);
     for (int i = 0; i < B * 4; ++i) h[2 * i + 1] = 1.f;
     for (int i = 0; i < 128; ++i) h[(size_t)B * 8 + i] = 1.f;
     cudaMemcpyAsync(gin, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st);
     cudaStreamSynchronize(st);
-    cudaMemsetAsync(counters, 0, (size_t)B * 4, st);
-    conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
-    rc = make_act_map(&tmA, act, B, H, W, Cin, (impl & 15) != 0);
+    conv_weight_to_act_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
+    rc = make_act_map(&tmA, act, B, H, W, Cin);
   }
-  if (rc == SDD_OK) rc = (impl & 15) == 0 ? make_wt_map(&tmB, wt, Cout, Cin) : make_wt_map2(&tmB, wt, Cout, Cin);
-  GnInput3 gi{nullptr, nullptr, nullptr, nullptr};
-  const int dbg = impl >> 4;
-  impl &= 15;
-  long long* trace = nullptr;
-  long long* osums = nullptr;
-  const char* trace_path = getenv("SDD_CONV_TRACE");
-  if (trace_path && impl != 0) { cudaMalloc(&trace, 2 * 6 * 64 * 4 * sizeof(long long)); }
-  if (rc == SDD_OK && cudaMalloc(&osums, (size_t)B * 8 * sizeof(long long)) != cudaSuccess) rc = SDD_ENOMEM;
-  float* gn_ab = nullptr;
-  if (impl == 2 && rc == SDD_OK && cudaMalloc(&gn_ab, (size_t)2 * B * Cin * sizeof(float)) != cudaSuccess) rc = SDD_ENOMEM;
+  if (rc == SDD_OK) rc = make_wt_map(&tmB, wt, Cout, Cin);
+  GnInput3 gi{nullptr, nullptr, nullptr, nullptr, nullptr};
   if (impl == 2) gi = GnInput3{nullptr, gin, gin + (size_t)B * 8, gin + (size_t)B * 8 + 128, gn_ab};
   if (rc == SDD_OK && (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess)) rc = SDD_ECUDA;
   BiasRef br{bias, nullptr, 0, 0};
   double total = 0.0;
   for (int i = 0; rc == SDD_OK && i < iters + 2; ++i) {
     if (flush && flush_bytes) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
-    if (trace) cudaMemsetAsync(trace, 0, 2 * 6 * 64 * 4 * sizeof(long long), st);
     cudaMemsetAsync(osums, 0, (size_t)B * 8 * sizeof(long long), st);
     cudaEventRecord(e0, st);
-    if (impl == 0)
-      rc = launch_conv_tc(tmA, tmB, (__nv_bfloat16*)out, br, GnScratch{partials, counters, mr}, B, H, W, Cin, Cout, st);
-    else
-      rc = launch_conv_tc3(tmA, tmB, (const __nv_bfloat16*)act, (__nv_bfloat16*)out, br, gi, osums, B, H, W, Cin, Cout,
-                           st, dbg, trace);
+    rc = launch_conv(tmA, tmB, (const act_t*)act, (act_t*)out, br, gi, osums, B, H, W, Cin, Cout, st);
     cudaEventRecord(e1, st);
     if (cudaEventSynchronize(e1) != cudaSuccess) { set_error("conv profile: kernel failed"); rc = SDD_ECUDA; break; }
     float ms = 0.f;
@@ -1174,27 +989,13 @@ int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void
   cudaStreamSynchronize(st);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
-  if (trace) {
-    std::vector<long long> h(2 * 6 * 64 * 4);
-    cudaMemcpy(h.data(), trace, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-    if (FILE* f = fopen(trace_path, "w")) {
-      for (int c = 0; c < 2; ++c)
-        for (int r = 0; r < 6; ++r)
-          for (int i = 0; i < 64; ++i) {
-            const long long* p = &h[(((size_t)c * 6 + r) * 64 + i) * 4];
-            if (p[0] | p[1] | p[2] | p[3]) fprintf(f, "%d %d %d %lld %lld %lld %lld\n", c, r, i, p[0], p[1], p[2], p[3]);
-          }
-      fclose(f);
-    }
-    cudaFree(trace);
-  }
-  cudaFree(osums);
-  cudaFree(wt); cudaFree(partials); cudaFree(counters); cudaFree(mr); cudaFree(gin); cudaFree(gn_ab);
+  cudaFree(osums); cudaFree(wt); cudaFree(gin); cudaFree(gn_ab);
   if (rc == SDD_OK) *ms_host = (float)(total / iters);
   return rc;
 }
 
-// Same for the fused update kernel (M models, fp32 eps; noise == NULL => in-kernel Philox).
+// The fused update step (ONE launch: HBM pass + per-sample finalize by the last-arriving CTA), M models, fp32 eps;
+// noise == NULL => in-kernel Philox.  One event pair per launch, `flush` rewritten before each (also evicts the code).
 int sdd_superpose_update_profile(float* x, const float* eps, const float* noise, float* logq, int B, int D, int M,
                                  int iters, void* flush, size_t flush_bytes, float* ms_host, void* stream) {
   SDD_CHECK(x && eps && logq && ms_host && iters > 0, "bad argument");
@@ -1208,8 +1009,9 @@ int sdd_superpose_update_profile(float* x, const float* eps, const float* noise,
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   UpdateArgs a;
   memset(&a, 0, sizeof(a));
-  a.x_in = x; a.x_out = x; a.eps = eps; a.noise = noise; a.logq = logq; a.logq_out = logq;
-  a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f; a.temperature = 1.0f; a.seed = 1234;
+  a.x_in = x; a.x_out = x; a.eps = eps; a.logq = logq; a.logq_out = logq;
+  a.rv.noise = noise; a.rv.temperature = 1.0f; a.rv.seed = 1234;
+  a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f;
   step_scalars_fill(a.sc);
   a.B = B; a.D = D; a.M = M;
   int rc = SDD_OK;
@@ -1218,7 +1020,8 @@ int sdd_superpose_update_profile(float* x, const float* eps, const float* noise,
     if (flush && flush_bytes) cudaMemsetAsync(flush, i & 0xff, flush_bytes, st);
     a.sc.draw_index = noise ? 0 : i;
     cudaEventRecord(e0, st);
-    rc = launch_superpose_update(a, ws, st, e1);  // e1 is recorded between the update and the finalize kernel
+    rc = launch_superpose_update(a, ws, st);
+    cudaEventRecord(e1, st);
     if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("update profile: kernel failed"); rc = SDD_ECUDA; break; }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, e0, e1);
@@ -1239,11 +1042,11 @@ int sdd_superpose_update_profile_rotating(int B, int D, int M, int use_noise, in
   const size_t set_floats = BD * (size_t)(1 + M + (use_noise ? 1 : 0));
   int nsets = (int)((rot_bytes + set_floats * 4 - 1) / (set_floats * 4));
   nsets = nsets < 2 ? 2 : (nsets > 512 ? 512 : nsets);
-  float* pool = nullptr; float* logq = nullptr; void* ws = nullptr;
+  float* pool = nullptr; float* logq = nullptr; void* ws = nullptr; float* xstats = nullptr;
   const size_t wb = update_workspace_bytes(B, D, M);
   if (cudaMalloc(&pool, set_floats * 4 * nsets) != cudaSuccess || cudaMalloc(&logq, (size_t)B * M * 4) != cudaSuccess ||
-      cudaMalloc(&ws, wb) != cudaSuccess) {
-    cudaFree(pool); cudaFree(logq); cudaFree(ws);
+      cudaMalloc(&ws, wb) != cudaSuccess || cudaMalloc(&xstats, (size_t)B * 8) != cudaSuccess) {
+    cudaFree(pool); cudaFree(logq); cudaFree(ws); cudaFree(xstats);
     set_error("cudaMalloc failed"); return SDD_ENOMEM;
   }
   cudaMemsetAsync(ws, 0, wb, st);
@@ -1258,17 +1061,18 @@ int sdd_superpose_update_profile_rotating(int B, int D, int M, int use_noise, in
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   UpdateArgs a;
   memset(&a, 0, sizeof(a));
-  a.logq = logq; a.logq_out = logq;
-  a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f; a.temperature = 1.0f; a.seed = 1234;
+  a.logq = logq; a.logq_out = logq; a.xstats_out = xstats;  // the whole step, as the sampler launches it
+  a.rv.temperature = 1.0f; a.rv.seed = 1234;
+  a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f;
   step_scalars_fill(a.sc);
   a.B = B; a.D = D; a.M = M;
   int rc = SDD_OK;
   auto run = [&](int n, int first) {
     for (int i = 0; rc == SDD_OK && i < n; ++i) {
       float* set = pool + (size_t)((first + i) % nsets) * set_floats;
-      a.x_in = set; a.x_out = set; a.eps = set + BD; a.noise = use_noise ? set + BD * (1 + M) : nullptr;
+      a.x_in = set; a.x_out = set; a.eps = set + BD; a.rv.noise = use_noise ? set + BD * (1 + M) : nullptr;
       a.sc.draw_index = use_noise ? 0 : first + i;
-      rc = launch_superpose_update(a, ws, st, nullptr, /*finalize=*/false);
+      rc = launch_superpose_update(a, ws, st);
     }
   };
   run(nsets, 0);  // warm-up: code, constants, TLBs; every set touched once
@@ -1278,7 +1082,7 @@ int sdd_superpose_update_profile_rotating(int B, int D, int M, int use_noise, in
   if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("update profile: kernel failed"); rc = SDD_ECUDA; }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws); cudaFree(logq); cudaFree(pool);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws); cudaFree(logq); cudaFree(pool); cudaFree(xstats);
   if (rc == SDD_OK) *ms_host = ms / iters;
   return rc;
 }
@@ -1292,7 +1096,7 @@ int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const 
   SDD_CHECK(!in_meanrstd || (in_gamma && in_beta), "in_gamma / in_beta required with in_meanrstd");
   SDD_TRY(device_check());
   cudaStream_t st = (cudaStream_t)stream;
-  __nv_bfloat16* wt = nullptr; long long* osums = nullptr;
+  act_t* wt = nullptr; long long* osums = nullptr;
   const int total_w = 9 * Cout * Cin;
   int rc = SDD_OK;
   CUtensorMap tmA, tmB;
@@ -1301,19 +1105,18 @@ int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const 
   }
   if (rc == SDD_OK) {
     cudaMemsetAsync(osums, 0, (size_t)B * 8 * sizeof(long long), st);
-    conv_weight_to_bf16_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
+    conv_weight_to_act_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wt, Cout, Cin);
     ++g_launches;
-    rc = make_act_map(&tmA, act_raw, B, H, W, Cin, true);
+    rc = make_act_map(&tmA, act_raw, B, H, W, Cin);
   }
-  if (rc == SDD_OK) rc = make_wt_map2(&tmB, wt, Cout, Cin);
+  if (rc == SDD_OK) rc = make_wt_map(&tmB, wt, Cout, Cin);
   float* gn_ab = nullptr;
   if (rc == SDD_OK && in_meanrstd && cudaMalloc(&gn_ab, (size_t)2 * B * Cin * sizeof(float)) != cudaSuccess) {
     set_error("cudaMalloc failed"); rc = SDD_ENOMEM;
   }
   if (rc == SDD_OK)
-    rc = launch_conv_tc3(tmA, tmB, (const __nv_bfloat16*)act_raw, (__nv_bfloat16*)out,
-                         BiasRef{bias, nullptr, 0, bias_batch_stride},
-                         GnInput3{nullptr, in_meanrstd, in_gamma, in_beta, gn_ab}, osums, B, H, W, Cin, Cout, st);
+    rc = launch_conv(tmA, tmB, (const act_t*)act_raw, (act_t*)out, BiasRef{bias, nullptr, 0, bias_batch_stride},
+                     GnInput3{nullptr, in_meanrstd, in_gamma, in_beta, gn_ab}, osums, B, H, W, Cin, Cout, st);
   if (rc == SDD_OK && gn_meanrstd) {
     gn_sums_to_meanrstd_kernel<<<(B * 4 + 127) / 128, 128, 0, st>>>(osums, gn_meanrstd, B * 4,
                                                                    (double)H * (double)W * (double)(Cout / 4), kGnEps);
@@ -1324,14 +1127,6 @@ int sdd_conv3x3_fused_nhwc(const void* act_raw, const float* in_meanrstd, const 
   if (rc != SDD_OK) return rc;
   if (e != cudaSuccess) { set_error(std::string("conv3x3_fused: ") + cudaGetErrorString(e)); return SDD_ECUDA; }
   return SDD_OK;
-}
-
-int sdd_gn_silu_apply(void* act, const float* meanrstd, const float* gamma, const float* beta, int B, int H, int W,
-                      int C, void* stream) {
-  SDD_CHECK(act && meanrstd && gamma && beta, "null argument");
-  SDD_CHECK(C == 64 || C == 128, "C must be 64 or 128");
-  SDD_TRY(device_check());
-  return launch_apply((__nv_bfloat16*)act, meanrstd, gamma, beta, B, H, W, C, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,13 +1,10 @@
-// CUDA-core kernels of the UNet forward (everything except the 64/128-channel 3x3 convs):
-// time-embedding MLP, GroupNorm statistics / apply, the 1->64, 64->1 and 1->1 edge convs,
-// weight re-layout, and a plain CUDA-core 3x3 conv used only to cross-check the tcgen05 kernel.
+// Kernels of the UNet forward other than the 64/128-channel 3x3 convs: time-embedding MLP, GroupNorm(1,1) statistics,
+// the 1->64 (TF32 mma.sync), 64->1 (fp16 mma.sync) and 1->1 edge convs, weight re-layout.
 // Reference semantics: /root/reference/src/models/unet.py:11-16, :21-34, :40-45, :57-65.
 #pragma once
 #include "common.cuh"
 
 namespace sdd {
-
-constexpr float kGnEps = 1e-5f;
 
 // ------------------------------------------------------------------ time embedding (unet.py:11-16,40-45)
 // emb[i][k] = sin(t_i * f_k), emb[i][k+half] = cos(t_i * f_k); t_i = t[i] or i when t == nullptr.
@@ -44,9 +41,8 @@ __global__ void linear_kernel(const float* __restrict__ x, const float* __restri
 }
 
 // ------------------------------------------------------------------ weight re-layout
-// fp32 [Cout][Cin][3][3] -> bf16 [kx][ky][Cout][Cin] (K-major rows for the UMMA B operand).
-__global__ void conv_weight_to_bf16_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout,
-                                           int Cin) {
+// fp32 [Cout][Cin][3][3] -> fp16 [kx][ky][Cout][Cin] (K-major rows for the UMMA B operand).
+__global__ void conv_weight_to_act_kernel(const float* __restrict__ w, act_t* __restrict__ o, int Cout, int Cin) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   int total = 9 * Cout * Cin;
   if (idx >= total) return;
@@ -54,7 +50,7 @@ __global__ void conv_weight_to_bf16_kernel(const float* __restrict__ w, __nv_bfl
   int co = (idx / Cin) % Cout;
   int tap = idx / (Cin * Cout);  // kx*3 + ky
   int kx = tap / 3, ky = tap % 3;
-  o[idx] = __float2bfloat16_rn(w[(((size_t)co * Cin + ci) * 3 + ky) * 3 + kx]);
+  o[idx] = float_to_act(w[(((size_t)co * Cin + ci) * 3 + ky) * 3 + kx]);
 }
 
 // ------------------------------------------------------------------ GroupNorm(1,1) statistics of x
@@ -89,81 +85,10 @@ __global__ void __launch_bounds__(256) stats_x_kernel(const float* __restrict__ 
   }
 }
 
-// ------------------------------------------------------------------ conv 1 -> 64 (first conv of downs.0)
-// x fp32 [B,H,W] --GN(1,1)+SiLU on load--> 3x3 conv -> raw bf16 NHWC [B,H,W,64] + bias, + GN(4,64) stats.
-// 8 threads per pixel (8 channels each) so each pixel's 128-byte NHWC row is one coalesced store.
+// ------------------------------------------------------------------ conv 1 -> 64 on tensor cores
+// x fp32 [B,H,W] --GN(1,1)+SiLU on load--> 3x3 conv -> raw fp16 NHWC [B,H,W,64] + bias, + GN(4,64) statistics.
 constexpr int kCinTH = 8, kCinTW = 32;
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ xstats,
-                                                      const float* __restrict__ gn_w, const float* __restrict__ gn_b,
-                                                      const float* __restrict__ w /*[64][9]*/, BiasRef bias,
-                                                      __nv_bfloat16* __restrict__ out, long long* out_sums /*[B][4][2]*/,
-                                                      int H, int W) {
-  const int b = blockIdx.z;
-  const int h0 = blockIdx.y * kCinTH, w0 = blockIdx.x * kCinTW;
-  const int tid = threadIdx.x;
-  __shared__ float tile[kCinTH + 2][kCinTW + 2];
-  const float mean = xstats[b * 2], rstd = xstats[b * 2 + 1];
-  const float ga = rstd * gn_w[0], gb = gn_b[0] - mean * rstd * gn_w[0];
-  for (int i = tid; i < (kCinTH + 2) * (kCinTW + 2); i += 256) {
-    int r = i / (kCinTW + 2), c = i % (kCinTW + 2);
-    int h = h0 + r - 1, ww = w0 + c - 1;
-    float v = 0.f;
-    if (h >= 0 && h < H && ww >= 0 && ww < W) v = silu_f(fmaf(x[((size_t)b * H + h) * W + ww], ga, gb));
-    tile[r][c] = v;
-  }
-  const int cg = tid & 7;
-  float wr[9][8], br[8];
-  const float* bp = bias_ptr(bias, b);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    br[j] = bp[cg * 8 + j];
-#pragma unroll
-    for (int t = 0; t < 9; ++t) wr[t][j] = w[(cg * 8 + j) * 9 + t];
-  }
-  __syncthreads();
-  float s = 0.f, ss = 0.f;
-#pragma unroll 1
-  for (int pass = 0; pass < 8; ++pass) {
-    const int p = pass * 32 + (tid >> 3);
-    const int r = p / kCinTW, c = p % kCinTW;
-    const int h = h0 + r, ww = w0 + c;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = br[j];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const float v = tile[r + ky][c + kx];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, wr[ky * 3 + kx][j], acc[j]);
-      }
-    if (h < H && ww < W) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s += acc[j]; ss = fmaf(acc[j], acc[j], ss); }
-      uint4 pk;
-      pk.x = pack_bf16x2(acc[0], acc[1]); pk.y = pack_bf16x2(acc[2], acc[3]);
-      pk.z = pack_bf16x2(acc[4], acc[5]); pk.w = pack_bf16x2(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(out + (((size_t)b * H + h) * W + ww) * 64 + cg * 8) = pk;
-    }
-  }
-  // group of this thread = cg / 2; reduce over lane bits 0, 3, 4 then across the 8 warps
-  s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 8);  ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-  s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-  __shared__ float red[8][4][2];
-  const int lane = tid & 31, warp = tid >> 5;
-  if (lane < 8 && (lane & 1) == 0) { red[warp][lane >> 1][0] = s; red[warp][lane >> 1][1] = ss; }
-  __syncthreads();
-  if (tid < 8) {  // tid = group*2 + {sum, sumsq}: fixed-order sum over the 8 warps, one fixed-point RED per value
-    float a = 0.f;
-    for (int wq = 0; wq < 8; ++wq) a += red[wq][tid >> 1][tid & 1];
-    gn_red_add(out_sums + (size_t)b * 8 + tid, a);
-  }
-}
-
-// ------------------------------------------------------------------ conv 1 -> 64 on tensor cores (product path)
-// Same contract as conv_in_kernel.  A 576-MAC/pixel layer is FMA-bound on the CUDA cores at about the rate HBM can
+// A 576-MAC/pixel layer is FMA-bound on the CUDA cores at about the rate HBM can
 // absorb its 128 B/pixel of output, so the multiply goes to mma.sync instead: per 16-pixel m-tile,
 //   D[16 px x 64 co] = A[16 px x 16 taps (9 used)] * B[16 taps x 64 co],  m16n8k8 TF32 (fp32 accumulate),
 // TF32 (10-bit mantissa, round-to-nearest) rather than bf16 keeps this first layer close to the fp32 reference.
@@ -190,7 +115,7 @@ constexpr int kCinTS = 40;  // tile row stride in floats: the four tap groups of
 __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __restrict__ x, const float* __restrict__ xstats,
                                                           const float* __restrict__ gn_w, const float* __restrict__ gn_b,
                                                           const float* __restrict__ w /*[64][9]*/, BiasRef bias,
-                                                          __nv_bfloat16* __restrict__ out, long long* out_sums /*[B][4][2]*/,
+                                                          act_t* __restrict__ out, long long* out_sums /*[B][4][2]*/,
                                                           int H, int W, int tiles_x, int tiles_y, int num_tiles) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = lane & 3, g = lane >> 2;
@@ -293,7 +218,7 @@ __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __rest
             const float v0 = d[j][2 * rh], v1 = d[j][2 * rh + 1];
             s += v0 + v1;
             ss = fmaf(v0, v0, ss); ss = fmaf(v1, v1, ss);
-            pk[j] = pack_bf16x2(v0, v1);
+            pk[j] = pack_act2(v0, v1);
           }
           st_global_v8(out + (((size_t)b * H + h) * W + ww) * 64 + t * 16, pk);
         }
@@ -314,44 +239,10 @@ __global__ void __launch_bounds__(256, 2) conv_in_mma_kernel(const float* __rest
   }
 }
 
-// ------------------------------------------------------------------ GroupNorm(4,C)+SiLU apply, in place
-// act bf16 NHWC [B,H,W,C]; each thread handles 8 consecutive channels (16 bytes).
-__global__ void __launch_bounds__(256) gn_silu_apply_kernel(__nv_bfloat16* act, const float* __restrict__ meanrstd,
-                                                            const float* __restrict__ gamma,
-                                                            const float* __restrict__ beta, int HW, int C) {
-  const int b = blockIdx.y;
-  __shared__ float sa[128], sb[128];
-  for (int c = threadIdx.x; c < C; c += 256) {
-    int g = c / (C / 4);
-    float mean = meanrstd[(b * 4 + g) * 2], rstd = meanrstd[(b * 4 + g) * 2 + 1];
-    float a = rstd * gamma[c];
-    sa[c] = a;
-    sb[c] = beta[c] - mean * a;
-  }
-  __syncthreads();
-  const size_t nvec = (size_t)HW * C / 8;
-  uint4* p = reinterpret_cast<uint4*>(act + (size_t)b * HW * C);
-  const int cvec = C / 8;
-  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
-    uint4 v = p[i];
-    const int c0 = (int)(i % cvec) * 8;
-    uint32_t u[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      __nv_bfloat162 h = *reinterpret_cast<__nv_bfloat162*>(&u[j]);
-      float lo = __low2float(h), hi = __high2float(h);
-      lo = silu_f(fmaf(lo, sa[c0 + 2 * j], sb[c0 + 2 * j]));
-      hi = silu_f(fmaf(hi, sa[c0 + 2 * j + 1], sb[c0 + 2 * j + 1]));
-      u[j] = pack_bf16x2(lo, hi);
-    }
-    p[i] = make_uint4(u[0], u[1], u[2], u[3]);
-  }
-}
-
 // ------------------------------------------------------------------ GN(4,64)+SiLU + conv 64 -> 1, tensor cores
-// raw bf16 NHWC [B,H,W,64] --GroupNorm(4,64)+SiLU in registers--> 3x3 conv to ONE channel -> raw fp32 [B,H,W] + bias,
+// raw fp16 NHWC [B,H,W,64] --GroupNorm(4,64)+SiLU in registers--> 3x3 conv to ONE channel -> raw fp32 [B,H,W] + bias,
 // + GN(1,1) statistics.  Written as out[p] = sum_tap T[p + off_tap][tap] with T[q][tap] = <act'[q,:], w[tap,:]>:
-// T is a [halo pixels x 64] x [64 x 16] GEMM (9 taps padded to 16) done with mma.sync m16n8k16 (bf16, fp32 accumulate;
+// T is a [halo pixels x 64] x [64 x 16] GEMM (9 taps padded to 16) done with mma.sync m16n8k16 (fp16, fp32 accumulate;
 // a 576-MAC/pixel layer is far too small to justify a tcgen05 pipeline), then a 9-tap gather from shared memory.
 // The K order is permuted so that each lane's 16 channels are 32 contiguous bytes of the pixel row (coalesced 16-byte
 // loads, no shuffles): lane t = lane%4 owns channels [16t, 16t+16), register ks*2+h holds channels 16t + 4ks + 2h + {0,1}.
@@ -367,6 +258,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 // PERSISTENT: a CTA walks a CONTIGUOUS range of tiles (tile = (sample, 8 x 32 pixel block); a range rarely crosses a
 // sample, so the per-sample scale/shift is rebuilt about once per CTA).  The weight
@@ -375,7 +272,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 // longer contains a global-load latency.  Measured per 16 samples at 256^2: 84.8 us with one CTA per tile (the ~70 parameter
 // loads of the prologue and three exposed load latencies per 340-pixel tile dominated) -> 63.0 us (2.1 TB/s of input).
 template <int CPS>
-__global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bfloat16* __restrict__ raw,
+__global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const act_t* __restrict__ raw,
                                                             const long long* __restrict__ in_sums /*[B][4][2]*/,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             const float* __restrict__ w /*[1][64][3][3]*/,
@@ -397,7 +294,7 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bflo
       for (int h = 0; h < 2; ++h) {
         const int tap = nt * 8 + j, c = t * 16 + ks * 4 + h * 2;
         const float w0v = tap < kO1Taps ? w[c * 9 + tap] : 0.f, w1v = tap < kO1Taps ? w[(c + 1) * 9 + tap] : 0.f;
-        bw[nt][ks][h] = pack_bf16x2(w0v, w1v);
+        bw[nt][ks][h] = pack_act2(w0v, w1v);
       }
   const float bias0 = bias[0];
 
@@ -408,7 +305,7 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bflo
     const int ty = r / tiles_x;
     h0 = ty * kO1TH; w0 = (r - ty * tiles_x) * kO1TW;
   };
-  auto load_mt = [&](const __nv_bfloat16* img, int h0, int w0, int mt, uint4 (&v)[2][2], bool (&ok)[2]) {
+  auto load_mt = [&](const act_t* img, int h0, int w0, int mt, uint4 (&v)[2][2], bool (&ok)[2]) {
 #pragma unroll
     for (int rh = 0; rh < 2; ++rh) {
       const int p = mt * 16 + j + 8 * rh;
@@ -430,7 +327,7 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bflo
   if (tile >= tile_end) return;
   int b, h0, w0;
   tile_coords(tile, b, h0, w0);
-  const __nv_bfloat16* img = raw + (size_t)b * H * W * 64 + t * 16;
+  const act_t* img = raw + (size_t)b * H * W * 64 + t * 16;
   uint4 vc[2][2], vn[2][2];
   bool okc[2], okn[2] = {false, false};
   load_mt(img, h0, w0, warp, vc, okc);
@@ -453,7 +350,7 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bflo
     const int ntile = tile + 1;
     int nb = b, nh0 = h0, nw0 = w0;
     if (ntile < tile_end) tile_coords(ntile, nb, nh0, nw0);
-    const __nv_bfloat16* nimg = raw + (size_t)nb * H * W * 64 + t * 16;
+    const act_t* nimg = raw + (size_t)nb * H * W * 64 + t * 16;
 
     for (int mt = warp; mt < kO1MT; mt += 8) {
       if (mt + 8 < kO1MT) load_mt(img, h0, w0, mt + 8, vn, okn);
@@ -465,10 +362,11 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bflo
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (okc[rh]) {
-            __nv_bfloat162 hv = *reinterpret_cast<__nv_bfloat162*>(&u[i]);
-            const float lo = silu_tanh(fmaf(__low2float(hv), ga[2 * i], gb[2 * i]));
-            const float hi = silu_tanh(fmaf(__high2float(hv), ga[2 * i + 1], gb[2 * i + 1]));
-            u[i] = pack_bf16x2(lo, hi);
+            float vl, vh;
+            unpack_act2(u[i], vl, vh);
+            const float lo = silu_tanh(fmaf(vl, ga[2 * i], gb[2 * i]));
+            const float hi = silu_tanh(fmaf(vh, ga[2 * i + 1], gb[2 * i + 1]));
+            u[i] = pack_act2(lo, hi);
           }
           a[rh][i] = u[i];
         }
@@ -477,8 +375,8 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const __nv_bflo
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint32_t af[4] = {a[0][ks * 2], a[1][ks * 2], a[0][ks * 2 + 1], a[1][ks * 2 + 1]};
-        mma_bf16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
-        mma_bf16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
+        mma_f16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
+        mma_f16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
       }
       // d0: taps 2t, 2t+1 of rows j and j+8; d1: taps 8+2t, 9+2t (only tap 8 exists)
       const int r0 = mt * 16 + j;
@@ -548,32 +446,8 @@ __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict_
   }
 }
 
-// ------------------------------------------------------------------ bring-up cross-check conv (CUDA cores)
-// Same contract as the tcgen05 kernel minus the statistics: act bf16 NHWC, w bf16 [kx][ky][Cout][Cin].
-__global__ void conv3x3_simt_kernel(const __nv_bfloat16* __restrict__ act, const __nv_bfloat16* __restrict__ w,
-                                    BiasRef bias, __nv_bfloat16* __restrict__ out, int B, int H, int W, int Cin,
-                                    int Cout) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t total = (size_t)B * H * W * Cout;
-  if (idx >= total) return;
-  int co = idx % Cout;
-  size_t p = idx / Cout;
-  int ww = p % W;
-  int h = (p / W) % H;
-  int b = p / ((size_t)W * H);
-  float acc = bias_ptr(bias, b)[co];
-  for (int kx = 0; kx < 3; ++kx)
-    for (int ky = 0; ky < 3; ++ky) {
-      int hh = h + ky - 1, wx = ww + kx - 1;
-      if (hh < 0 || hh >= H || wx < 0 || wx >= W) continue;
-      const __nv_bfloat16* a = act + (((size_t)b * H + hh) * W + wx) * Cin;
-      const __nv_bfloat16* wr = w + ((size_t)(kx * 3 + ky) * Cout + co) * Cin;
-      for (int ci = 0; ci < Cin; ++ci) acc = fmaf(__bfloat162float(a[ci]), __bfloat162float(wr[ci]), acc);
-    }
-  out[idx] = __float2bfloat16_rn(acc);
-}
-
-// GroupNorm(4,C) statistics straight from a bf16 NHWC tensor (cross-check path only).
+// ------------------------------------------------------------------ GroupNorm(4,C) statistics of a bf16 NHWC tensor
+// (attention block only: the conv layers get their statistics from the producer's epilogue)
 __global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const __nv_bfloat16* __restrict__ act, float* meanrstd,
                                                             int HW, int C) {
   const int b = blockIdx.x / 4, g = blockIdx.x % 4;

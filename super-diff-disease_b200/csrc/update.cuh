@@ -1,7 +1,8 @@
-// Fused superposition update: one coalesced, vectorised HBM pass per step.
+// Fused superposition update: ONE launch per step, one coalesced, vectorised HBM pass.
 //   reads  x[B,D], eps[M,B,D], (noise[B,D] | Philox)      writes x'[B,D]
-//   per-sample reductions <eps_m,dx>, <x,eps_m>, |eps_m|^2, sum x', sum x'^2 via warp shuffles,
-//   fixed-order cross-CTA reduce by the last CTA of each sample -> logq', kappa, GN(1,1) stats of x'.
+//   per-sample reductions <eps_m,dx>, <x,eps_m>, |eps_m|^2, sum x', sum x'^2 via warp shuffles -> per-segment partials;
+//   the LAST-ARRIVING CTA of each sample reduces them in a fixed order (independent of which CTA that is) -> logq',
+//   kappa, GN(1,1) statistics of x'; the CTA that finalises the last sample advances the device-side step counter.
 // Algorithmic bytes / element: 4 + 4M + (4 if noise tensor) + 4.
 #pragma once
 #include "common.cuh"
@@ -30,58 +31,90 @@ inline void step_scalars_fill(StepScalars& s) {
   s.pad = 0.f;
 }
 
+// Per-CALL values.  The sampler keeps one copy in device memory and rewrites it at the start of every run, so the
+// captured step graph (which only holds the pointer) survives a new seed / shard offset / trajectory buffer; the
+// operator API passes the struct by value.
+struct RunParams {
+  const float* noise;        // [B,D] slice (operator API), noise stack [T,B,D] (sampler; draw_index selects) or nullptr
+  int64_t noise_step_stride; // elements between consecutive draw indices of a noise stack (0 = single slice)
+  uint64_t seed;             // Philox key when noise == nullptr
+  int64_t sample_offset;     // global index of local sample 0
+  float temperature;
+  int pad;
+  const float* bias;         // [M] or nullptr
+  float* kappa_traj;         // [T,B,M] or nullptr (row = step)
+  float* logq_traj;          // [T+1,B,M] or nullptr (row = step+1)
+  float* x_traj;             // [T+1,B,D] or nullptr (row = step+1 receives x'; row 0 = x_T is written by the sampler)
+};
+
 struct UpdateArgs {
   const float* x_in;
   float* x_out;
   const float* eps;          // [M,B,D]
-  const float* noise;        // [B,D] slice base or nullptr
-  int64_t noise_step_stride; // elements between consecutive draw indices in a noise stack (0 = single slice)
   const float* logq;         // [B,M]
   float* logq_out;           // [B,M]
   float* kappa_out;          // [B,M] or nullptr
   float* xstats_out;         // [B,2] (mean, rstd) or nullptr
-  float* kappa_traj;         // [T,B,M] or nullptr (row = step)
-  float* logq_traj;          // [T+1,B,M] or nullptr (row = step+1)
   const StepScalars* table;  // device table or nullptr
-  const int* step_ptr;       // device step counter or nullptr
+  int* step_ptr;             // device step counter or nullptr; advanced by the kernel when `advance_step`
   StepScalars sc;            // used when table == nullptr
-  float temperature;
-  const float* bias;         // [M] or nullptr
-  uint64_t seed;
-  int64_t sample_offset;
+  const RunParams* rp;       // device copy (sampler) or nullptr
+  RunParams rv;              // used when rp == nullptr
   float* partials;           // [B][nblk][kPartialsPerBlock]
+  int* counters;             // [B + 1]: per-sample arrivals, then finalised samples; zero between launches
   // "AND" mode: kappa solved per sample from a first reduction pass instead of the softmax
   float* and_partials;       // [B][nblk][kAndPartialsPerBlock] or nullptr
-  float* kappa_in;           // [B][M]: written by superpose_and_solve_kernel, read by the update / finalize kernels
+  float* kappa_in;           // [B][M]: written by superpose_and_solve_kernel, read by the update kernel
   int mode;                  // 0 = OR (softmax of log q), 1 = AND (equal log-density increments)
+  int advance_step;
   int B, D, M, nblk;
 };
 
 constexpr int kPartialsPerBlock = 3 * kMaxModels + 2;
 constexpr int kAndPartialsPerBlock = kMaxModels * (kMaxModels + 1) / 2 + 2 * kMaxModels;  // G_ij (i <= j), <eps,x>, <eps,z>
 
+__device__ __forceinline__ RunParams load_run_params(const UpdateArgs& a) {
+  if (a.rp) return *a.rp;
+  return a.rv;
+}
+
 // ------------------------------------------------------------------------------------- Philox
+// Philox4x32-10 (Salmon et al., SC'11).  mul.wide gives hi:lo of a round's product in one IMAD.WIDE.
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    const uint64_t p0 = (uint64_t)0xD2511F53u * (uint64_t)c.x;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * (uint64_t)c.z;
+    c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k.x, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k.y, (uint32_t)p0);
     k.x += 0x9E3779B9u;
     k.y += 0xBB67AE85u;
   }
   return c;
 }
 __device__ __forceinline__ float u01(uint32_t r) { return (float)r * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }
+// -2 ln(u) for u in (0, 1].  MUFU.LG2 (absolute error 2^-22 on [0.5, 2), relative elsewhere) is accurate enough except
+// next to u = 1, where ln u -> 0 and the radius sqrt(-2 ln u) is ill-conditioned: there (u > 0.998, 0.2 % of the
+// draws, warp-divergent but rare) a three-term series in t = 1 - u (exact in fp32) is used instead.  The radius then
+// agrees with the float64 oracle to < 3e-6 absolute everywhere (the accurate logf this replaces cost ~40 of the ~180
+// instructions of a four-normal draw).
+__device__ __forceinline__ float neg2_log(float u) {
+  float l2;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u));
+  float v = -1.3862943611198906f * l2;
+  if (u > 0.998f) {
+    const float t = 1.0f - u;
+    v = 2.0f * t * fmaf(t, fmaf(t, 0.3333333333f, 0.5f), 1.0f);
+  }
+  return v;
+}
 // 4 standard normals for elements 4q..4q+3 of (global sample, draw); definition in oracle.philox_normal.
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint32_t q, uint32_t gsample, uint32_t draw) {
   uint4 r = philox4x32_10(make_uint4(q, gsample, draw, 0x5D1FFu), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   float4 o;
-  // accurate logf (the radius is ill-conditioned near u = 1); fast sqrt and sin/cos (angle in (-pi, pi], where the
-  // MUFU approximations are good to ~4e-7 absolute).  Normals agree with the float64 oracle to < 5e-6.
+  // fast sqrt and sin / cos (angle in (-pi, pi], where the MUFU approximations are good to ~5e-7 absolute)
   float rad0, rad1;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(rad0) : "f"(-2.0f * logf(u01(r.x))));
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(rad1) : "f"(-2.0f * logf(u01(r.z))));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad0) : "f"(neg2_log(u01(r.x))));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad1) : "f"(neg2_log(u01(r.z))));
   float s0, c0, s1, c1;
   __sincosf(3.14159265358979f * (2.0f * u01(r.y) - 1.0f), &s0, &c0);
   __sincosf(3.14159265358979f * (2.0f * u01(r.w) - 1.0f), &s1, &c1);
@@ -95,31 +128,33 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-// x' for one element, with the reference's expression tree and no FMA contraction (ddpm.py:42-44):
-//   (1/sqrt(alpha)) * (x - ((1-alpha)/sqrt(1-alpha_bar)) * eps_bar) + sqrt(beta) * z
-__device__ __forceinline__ float ddpm_x_update(float x, float eb, float z, float c1, float c2, float c3) {
-  return __fadd_rn(__fmul_rn(c1, __fsub_rn(x, __fmul_rn(c2, eb))), __fmul_rn(c3, z));
+// packed fp32 pairs without contraction: the reference's expression tree (ddpm.py:42-44) is mul, mul, sub, mul, add
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // One CTA = one segment of one sample = STEPS sub-steps of kSegVecPerThread float4 per thread and array (STEPS = 2:
 // 4096 elements).  Per sub-step all loads are issued before any use; the per-thread sums are carried across the
-// sub-steps, so the ~320 instructions of per-thread prologue + reduction are paid once per 32 elements (they were 43 %
-// of all issued instructions at 8 elements per thread).  The first sub-step's x / eps loads are issued BEFORE the
-// dependent chain step counter -> schedule row -> log q -> kappa is walked (two L2 round trips).  Segment boundaries
-// and every reduction order are fixed functions of D alone, so logq / statistics are bit-identical for any batch
-// sharding.  No atomics, no fences: per-segment partial sums go to a small buffer and superpose_finalize_kernel (one
-// CTA per sample) reduces them in a fixed order.
-// Measured (B200, rotating buffers, D = 65536, M = 2; us per launch Philox / noise tensor): STEPS 1: B=64 18.8 / 16.5,
-// B=256 59.5 / 51.9; STEPS 2: 18.4 / 17.4, 53.0 / 53.3; STEPS 4: 18.5 / 17.5, 52.4 / 53.6 (B=16: 8.2, 8.2, 10.3).
-// Tried and rejected: persistent CTAs (2-3 per SM) fed by a cp.async.bulk + mbarrier shared-memory ring -- 22.3 / 19.1
-// at B=64 and 65.4 / 58.0 at B=256: the Philox variant is issue-bound and wants the 32 warps per SM this version has.
+// sub-steps.  The first sub-step's x / eps loads are issued BEFORE the dependent chain step counter -> schedule row ->
+// log q -> kappa is walked (two L2 round trips).  Segment boundaries and every reduction order are fixed functions of
+// D alone, so logq / statistics are bit-identical for any batch sharding.  No floating-point atomics: per-segment
+// partial sums go to a small buffer, an integer arrival counter per sample elects the last CTA, and that CTA reduces
+// the partials in a fixed order.  The arithmetic of an element runs on packed fp32 pairs (FMUL2 / FADD2 / FFMA2): two
+// elements per instruction with the scalar code's per-element rounding (mul, mul, sub, mul, add -- no contraction).
 constexpr int kSegVecPerThread = 2;
 constexpr int kSegSteps = 2;
 constexpr int kSubVec = kUpdThreads * kSegVecPerThread;  // float4 per sub-step
 constexpr int kSegVec = kSubVec * kSegSteps;             // float4 per segment
 
 template <int M>
-__device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, int b, float (&kap)[M]) {
+__device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, const RunParams& rp, int b, float (&kap)[M]) {
   if (a.mode == 1) {  // AND: solved by superpose_and_solve_kernel earlier on the stream
 #pragma unroll
     for (int m = 0; m < M; ++m) kap[m] = a.kappa_in[b * M + m];
@@ -128,16 +163,66 @@ __device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, int b, float 
   float lg[M], mx = -INFINITY;
 #pragma unroll
   for (int m = 0; m < M; ++m) {
-    lg[m] = a.temperature * a.logq[b * M + m] + (a.bias ? a.bias[m] : 0.0f);
+    lg[m] = rp.temperature * a.logq[b * M + m] + (rp.bias ? rp.bias[m] : 0.0f);
     mx = fmaxf(mx, lg[m]);
   }
   // fast exp / divide (relative error ~2^-21, far inside the 2e-6 kappa tolerance; exp(0) = 1 and 1/2 stay exact, so
-  // self-superposition still yields kappa == 0.5 bit-for-bit).  The update and the finalize kernel share this function.
+  // self-superposition still yields kappa == 0.5 bit-for-bit).
   float den = 0.0f;
 #pragma unroll
   for (int m = 0; m < M; ++m) { kap[m] = __expf(lg[m] - mx); den += kap[m]; }
 #pragma unroll
   for (int m = 0; m < M; ++m) kap[m] = __fdividef(kap[m], den);
+}
+
+// Fixed-order reduce of one sample's segment partials by the 256 threads of its last-arriving CTA (16 strided lanes per
+// value, then the 16 lanes in order), Ito log-density increment in double, kappa / log q trajectory rows, GroupNorm(1,1)
+// statistics of x'.  `kap` is the kappa this step used (every CTA of the sample computed the same values).
+template <int M>
+__device__ __forceinline__ void finalize_sample(const UpdateArgs& a, const RunParams& rp, const StepScalars& sc, int step,
+                                                int b, const float (&kap)[M]) {
+  const int tid = threadIdx.x;
+  __shared__ float fin[16][16];
+  __shared__ double tot[3 * M + 2];
+  {
+    const int j = tid & 15, g = tid >> 4;
+    float v = 0.0f;
+    if (j < 3 * M + 2) {
+      const float* src = a.partials + (size_t)b * a.nblk * kPartialsPerBlock + j;
+      for (int p = g; p < a.nblk; p += 16) v += __ldcg(src + (size_t)p * kPartialsPerBlock);
+    }
+    fin[g][j] = v;
+  }
+  __syncthreads();
+  if (tid < 3 * M + 2) {
+    double v = 0.0;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) v += (double)fin[g][tid];
+    tot[tid] = v;
+  }
+  __syncthreads();
+  if (tid < M) {
+    const double beta = (double)sc.beta;
+    const double inv_sig = 1.0 / sqrt(1.0 - (double)sc.alpha_bar);
+    const double A = tot[3 * tid], Bx = tot[3 * tid + 1], C = tot[3 * tid + 2];
+    // s = -eps * inv_sig:  <s,dx> - beta D/2 - beta/2 <x,s> - beta/2 |s|^2
+    const double inc = -inv_sig * A - 0.5 * beta * (double)a.D + 0.5 * beta * inv_sig * Bx - 0.5 * beta * inv_sig * inv_sig * C;
+    const float lq_new = (float)((double)a.logq[b * M + tid] + inc);
+    float kv = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) if (m == tid) kv = kap[m];
+    a.logq_out[b * M + tid] = lq_new;  // in place is fine: every CTA of this sample read logq before it arrived
+    if (a.kappa_out) a.kappa_out[b * M + tid] = kv;
+    if (rp.kappa_traj) rp.kappa_traj[((size_t)step * a.B + b) * M + tid] = kv;
+    if (rp.logq_traj) rp.logq_traj[((size_t)(step + 1) * a.B + b) * M + tid] = lq_new;
+  }
+  if (tid == 32 && a.xstats_out) {
+    const double mean = tot[3 * M] / (double)a.D;
+    double var = tot[3 * M + 1] / (double)a.D - mean * mean;
+    if (var < 0.0) var = 0.0;
+    a.xstats_out[b * 2 + 0] = (float)mean;
+    a.xstats_out[b * 2 + 1] = (float)(1.0 / sqrt(var + (double)kGnEps));
+  }
 }
 
 template <int M, int STEPS>
@@ -166,17 +251,23 @@ __global__ void __launch_bounds__(kUpdThreads, STEPS == 1 ? 5 : 4) superpose_upd
 
   const int step = a.step_ptr ? *a.step_ptr : 0;
   const StepScalars sc = a.table ? a.table[step] : a.sc;
+  const RunParams rp = load_run_params(a);
   const bool have_noise = sc.draw_index >= 0;
-  const bool noise_tensor = a.noise != nullptr && have_noise;
-  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(a.noise + (size_t)sc.draw_index * a.noise_step_stride + (size_t)b * a.D) : nullptr;
+  const bool noise_tensor = rp.noise != nullptr && have_noise;
+  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(rp.noise + (size_t)sc.draw_index * rp.noise_step_stride + (size_t)b * a.D) : nullptr;
   float kap[M];
-  softmax_kappa<M>(a, b, kap);
-  const float c1 = sc.c1, c2 = sc.c2, c3 = sc.c3;
-  const uint32_t gsample = (uint32_t)(a.sample_offset + b);
-
-  float accA[M], accB[M], accC[M], sx = 0.0f, sxx = 0.0f;
+  softmax_kappa<M>(a, rp, b, kap);
+  const uint64_t c1 = pack_f32x2(sc.c1, sc.c1), c2 = pack_f32x2(sc.c2, sc.c2), c3 = pack_f32x2(sc.c3, sc.c3);
+  uint64_t kap2[M];
 #pragma unroll
-  for (int m = 0; m < M; ++m) accA[m] = accB[m] = accC[m] = 0.0f;
+  for (int m = 0; m < M; ++m) kap2[m] = pack_f32x2(kap[m], kap[m]);
+  const uint32_t gsample = (uint32_t)(rp.sample_offset + b);
+  float4* xt4 = rp.x_traj ? reinterpret_cast<float4*>(rp.x_traj + ((size_t)(step + 1) * a.B + b) * (size_t)a.D) : nullptr;
+
+  // packed (even element, odd element) accumulators
+  uint64_t accA[M], accB[M], accC[M], sx = 0ull, sxx = 0ull;
+#pragma unroll
+  for (int m = 0; m < M; ++m) accA[m] = accB[m] = accC[m] = 0ull;
 
 #pragma unroll 1
   for (int s = 0; s < STEPS; ++s) {
@@ -191,52 +282,78 @@ __global__ void __launch_bounds__(kUpdThreads, STEPS == 1 ? 5 : 4) superpose_upd
       const int q = q0 + s * kSubVec + i * kUpdThreads;
       if (q >= nq) continue;
       float4 z = zv[i];
-      if (have_noise && !noise_tensor) z = philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
-      const float xs[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
-      const float zs[4] = {z.x, z.y, z.z, z.w};
-      float xn[4];
+      if (have_noise && !noise_tensor) z = philox_normal4(rp.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
+      uint64_t xn2[2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float es[M];
+      for (int h = 0; h < 2; ++h) {  // elements (0,1) then (2,3) of the float4
+        const uint64_t x2 = h ? pack_f32x2(xv[i].z, xv[i].w) : pack_f32x2(xv[i].x, xv[i].y);
+        const uint64_t z2 = h ? pack_f32x2(z.z, z.w) : pack_f32x2(z.x, z.y);
+        uint64_t e2[M];
 #pragma unroll
-        for (int m = 0; m < M; ++m)
-          es[m] = (j == 0 ? ev[m][i].x : j == 1 ? ev[m][i].y : j == 2 ? ev[m][i].z : ev[m][i].w);
-        float eb = __fmul_rn(kap[0], es[0]);
+        for (int m = 0; m < M; ++m) e2[m] = h ? pack_f32x2(ev[m][i].z, ev[m][i].w) : pack_f32x2(ev[m][i].x, ev[m][i].y);
+        uint64_t eb = mul_f32x2(kap2[0], e2[0]);
 #pragma unroll
-        for (int m = 1; m < M; ++m) eb = __fadd_rn(eb, __fmul_rn(kap[m], es[m]));
-        xn[j] = ddpm_x_update(xs[j], eb, zs[j], c1, c2, c3);
-        const float dx = xn[j] - xs[j];
+        for (int m = 1; m < M; ++m) eb = add_f32x2(eb, mul_f32x2(kap2[m], e2[m]));
+        // (1/sqrt(alpha)) * (x - ((1-alpha)/sqrt(1-alpha_bar)) * eps_bar) + sqrt(beta) * z, ddpm.py:42-44
+        const uint64_t xn = add_f32x2(mul_f32x2(c1, sub_f32x2(x2, mul_f32x2(c2, eb))), mul_f32x2(c3, z2));
+        const uint64_t dx = sub_f32x2(xn, x2);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-          accA[m] = fmaf(es[m], dx, accA[m]);
-          accB[m] = fmaf(xs[j], es[m], accB[m]);
-          accC[m] = fmaf(es[m], es[m], accC[m]);
+          accA[m] = fma_f32x2(e2[m], dx, accA[m]);
+          accB[m] = fma_f32x2(x2, e2[m], accB[m]);
+          accC[m] = fma_f32x2(e2[m], e2[m], accC[m]);
         }
-        sx += xn[j];
-        sxx = fmaf(xn[j], xn[j], sxx);
+        sx = add_f32x2(sx, xn);
+        sxx = fma_f32x2(xn, xn, sxx);
+        xn2[h] = xn;
       }
-      __stcs(xo4 + q, make_float4(xn[0], xn[1], xn[2], xn[3]));
+      float4 o;
+      unpack_f32x2(xn2[0], o.x, o.y);
+      unpack_f32x2(xn2[1], o.z, o.w);
+      __stcs(xo4 + q, o);
+      if (xt4) __stcs(xt4 + q, o);  // optional trajectory copy (visualisation strips, parity tests)
     }
   }
 
-  // segment reduce: shuffle within warps, fixed-order sum across the 8 warps
+  // segment reduce: (even + odd), shuffle within warps, fixed-order sum across the 8 warps
   __shared__ float red[kUpdThreads / 32][3 * M + 2];
+  auto fold = [](uint64_t v) { float lo, hi; unpack_f32x2(v, lo, hi); return lo + hi; };
+  float rA[M], rB[M], rC[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) {
-    accA[m] = warp_sum(accA[m]); accB[m] = warp_sum(accB[m]); accC[m] = warp_sum(accC[m]);
+    rA[m] = warp_sum(fold(accA[m])); rB[m] = warp_sum(fold(accB[m])); rC[m] = warp_sum(fold(accC[m]));
   }
-  sx = warp_sum(sx); sxx = warp_sum(sxx);
+  const float rsx = warp_sum(fold(sx)), rsxx = warp_sum(fold(sxx));
   if (lane == 0) {
 #pragma unroll
-    for (int m = 0; m < M; ++m) { red[warp][3 * m] = accA[m]; red[warp][3 * m + 1] = accB[m]; red[warp][3 * m + 2] = accC[m]; }
-    red[warp][3 * M] = sx; red[warp][3 * M + 1] = sxx;
+    for (int m = 0; m < M; ++m) { red[warp][3 * m] = rA[m]; red[warp][3 * m + 1] = rB[m]; red[warp][3 * m + 2] = rC[m]; }
+    red[warp][3 * M] = rsx; red[warp][3 * M + 1] = rsxx;
   }
   __syncthreads();
   if (tid < 3 * M + 2) {
     float v = 0.0f;
 #pragma unroll
     for (int w = 0; w < kUpdThreads / 32; ++w) v += red[w][tid];
-    a.partials[((size_t)b * a.nblk + seg) * kPartialsPerBlock + tid] = v;
+    __stcg(a.partials + ((size_t)b * a.nblk + seg) * kPartialsPerBlock + tid, v);
+    __threadfence();  // this thread's partial is visible device-wide before the arrival below
+  }
+  // ---- arrival: the last CTA of this sample finalises it (fixed reduction order: the result does not depend on which
+  // CTA is last); the CTA that finalises the last sample advances the step counter (every CTA of the launch read it
+  // before arriving, so nobody can still observe the old value)
+  __shared__ int s_last;
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&a.counters[b], 1) == a.nblk - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  finalize_sample<M>(a, rp, sc, step, b, kap);
+  if (tid == 0) {
+    a.counters[b] = 0;  // ready for the next launch
+    __threadfence();
+    if (atomicAdd(&a.counters[a.B], 1) == a.B - 1) {
+      a.counters[a.B] = 0;
+      if (a.advance_step && a.step_ptr) *a.step_ptr = step + 1;
+    }
   }
 }
 
@@ -252,13 +369,14 @@ __global__ void __launch_bounds__(kUpdThreads, 4) superpose_and_gram_kernel(cons
   const int nq = a.D >> 2;
   const int step = a.step_ptr ? *a.step_ptr : 0;
   const StepScalars sc = a.table ? a.table[step] : a.sc;
+  const RunParams rp = load_run_params(a);
   const bool have_noise = sc.draw_index >= 0;
-  const bool noise_tensor = a.noise != nullptr && have_noise;
+  const bool noise_tensor = rp.noise != nullptr && have_noise;
   const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
   const float4* e4 = reinterpret_cast<const float4*>(a.eps + (size_t)b * a.D);
   const size_t e_stride = (size_t)a.B * (size_t)nq;
-  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(a.noise + (size_t)sc.draw_index * a.noise_step_stride + (size_t)b * a.D) : nullptr;
-  const uint32_t gsample = (uint32_t)(a.sample_offset + b);
+  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(rp.noise + (size_t)sc.draw_index * rp.noise_step_stride + (size_t)b * a.D) : nullptr;
+  const uint32_t gsample = (uint32_t)(rp.sample_offset + b);
   const int per_seg = nq / a.nblk + ((nq % a.nblk) ? 1 : 0);  // == kSubVec * steps for full segments
   float acc[NVAL];
 #pragma unroll
@@ -272,7 +390,7 @@ __global__ void __launch_bounds__(kUpdThreads, 4) superpose_and_gram_kernel(cons
     for (int m = 0; m < M; ++m) ev[m] = __ldg(e4 + m * e_stride + q);
     float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     if (noise_tensor) z = __ldg(n4 + q);
-    else if (have_noise) z = philox_normal4(a.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
+    else if (have_noise) z = philox_normal4(rp.seed, (uint32_t)q, gsample, (uint32_t)sc.draw_index);
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
     const float zs[4] = {z.x, z.y, z.z, z.w};
 #pragma unroll
@@ -380,59 +498,6 @@ __global__ void __launch_bounds__(256) superpose_and_solve_kernel(const UpdateAr
   }
 }
 
-// One CTA (256 threads) per sample: fixed-order reduce of the segment partials (16 strided lanes per value, then the
-// 16 lanes in order), Ito log-density increment in double, kappa, GroupNorm(1,1) statistics of x'.
-template <int M>
-__global__ void __launch_bounds__(256) superpose_finalize_kernel(const UpdateArgs a) {
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int step = a.step_ptr ? *a.step_ptr : 0;
-  const StepScalars sc = a.table ? a.table[step] : a.sc;
-  __shared__ float fin[16][16];
-  __shared__ double tot[3 * M + 2];
-  {
-    const int j = tid & 15, g = tid >> 4;
-    float v = 0.0f;
-    if (j < 3 * M + 2) {
-      const float* src = a.partials + (size_t)b * a.nblk * kPartialsPerBlock + j;
-      for (int p = g; p < a.nblk; p += 16) v += src[(size_t)p * kPartialsPerBlock];
-    }
-    fin[g][j] = v;
-  }
-  __syncthreads();
-  if (tid < 3 * M + 2) {
-    double v = 0.0;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) v += (double)fin[g][tid];
-    tot[tid] = v;
-  }
-  __syncthreads();
-  if (tid < M) {
-    float kap[M];
-    softmax_kappa<M>(a, b, kap);
-    const double beta = (double)sc.beta;
-    const double inv_sig = 1.0 / sqrt(1.0 - (double)sc.alpha_bar);
-    const double A = tot[3 * tid], Bx = tot[3 * tid + 1], C = tot[3 * tid + 2];
-    // s = -eps * inv_sig:  <s,dx> - beta D/2 - beta/2 <x,s> - beta/2 |s|^2
-    const double inc = -inv_sig * A - 0.5 * beta * (double)a.D + 0.5 * beta * inv_sig * Bx - 0.5 * beta * inv_sig * inv_sig * C;
-    const float lq_new = (float)((double)a.logq[b * M + tid] + inc);
-    float kv = 0.f;
-#pragma unroll
-    for (int m = 0; m < M; ++m) if (m == tid) kv = kap[m];
-    __syncwarp((1u << M) - 1u);  // every lane has read logq[b,:] (for kappa) before any lane overwrites it in place
-    a.logq_out[b * M + tid] = lq_new;
-    if (a.kappa_out) a.kappa_out[b * M + tid] = kv;
-    if (a.kappa_traj) a.kappa_traj[((size_t)step * a.B + b) * M + tid] = kv;
-    if (a.logq_traj) a.logq_traj[((size_t)(step + 1) * a.B + b) * M + tid] = lq_new;
-  }
-  if (tid == 32 && a.xstats_out) {
-    const double mean = tot[3 * M] / (double)a.D;
-    double var = tot[3 * M + 1] / (double)a.D - mean * mean;
-    if (var < 0.0) var = 0.0;
-    a.xstats_out[b * 2 + 0] = (float)mean;
-    a.xstats_out[b * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
-  }
-}
-
 // Segments per sample depend on D only (steps * 2048 elements each).
 inline int update_blocks_per_sample(int D, int steps = kSegSteps) {
   int nq = D / 4;
@@ -440,18 +505,18 @@ inline int update_blocks_per_sample(int D, int steps = kSegSteps) {
   return nb < 1 ? 1 : nb;
 }
 
-// workspace = [update partials | AND partials | AND kappa[B][kMaxModels]], each 256-byte aligned
+// workspace = [update partials | AND partials | AND kappa[B][kMaxModels] | arrival counters[B + 1]], 256-byte aligned
 inline size_t update_ws_part_bytes(int B, int D) {
   return ((size_t)B * update_blocks_per_sample(D, 1) * kPartialsPerBlock * sizeof(float) + 255) & ~(size_t)255;  // any steps
 }
 inline size_t update_ws_and_bytes(int B, int D) {
   return ((size_t)B * update_blocks_per_sample(D, 1) * kAndPartialsPerBlock * sizeof(float) + 255) & ~(size_t)255;
 }
+inline size_t update_ws_kappa_bytes(int B) { return ((size_t)B * kMaxModels * sizeof(float) + 255) & ~(size_t)255; }
 inline size_t update_workspace_bytes(int B, int D, int /*M*/) {
-  return update_ws_part_bytes(B, D) + update_ws_and_bytes(B, D) + (((size_t)B * kMaxModels * sizeof(float) + 255) & ~(size_t)255);
+  return update_ws_part_bytes(B, D) + update_ws_and_bytes(B, D) + update_ws_kappa_bytes(B) +
+         ((((size_t)B + 1) * sizeof(int) + 255) & ~(size_t)255);
 }
-
-int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t stream, cudaEvent_t after_update, bool finalize);
 
 __global__ void philox_normal_kernel(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw);
 __global__ void copy_f32_kernel(float* dst, const float* src, size_t n);

@@ -39,10 +39,16 @@ class DDPM:
                                                out.data_ptr(), B, D, _lib.stream_ptr(dev)))
         return out
 
-    @torch.no_grad()
     def p_losses(self, denoise_model, x_start, t, noise=None):
         """eps-MSE of ddpm.py:20-24, forward only (validation loss): q_sample -> UNet forward on the sampler's
-        kernels -> deterministic MSE reduction.  Returns a 0-dim CUDA tensor.  ``noise=`` pins the draw for parity."""
+        kernels -> deterministic MSE reduction.  Returns a 0-dim CUDA tensor WITHOUT a grad_fn; called from a training
+        loop (gradients enabled on the model's parameters) it raises.  ``noise=`` pins the draw for parity."""
+        if hasattr(denoise_model, "_refuse_training"):
+            denoise_model._refuse_training()
+        with torch.no_grad():
+            return self._p_losses(denoise_model, x_start, t, noise)
+
+    def _p_losses(self, denoise_model, x_start, t, noise=None):
         _lib.require_cuda(x_start, "x_start")
         if noise is None:
             noise = torch.randn_like(x_start)
@@ -58,21 +64,44 @@ class DDPM:
                                  ws.numel(), _lib.stream_ptr(dev)))
         return out
 
-    @torch.no_grad()
     def training_step(self, model, x):
-        """ddpm.py:26-29 (same t draw), forward only: the value of the training loss, not a differentiable graph."""
+        """ddpm.py:26-29 (same t draw), forward only: the value of the training loss, not a differentiable graph
+        (raises when called with gradients enabled on the model's parameters, i.e. from training_logic.py:32)."""
+        if hasattr(model, "_refuse_training"):
+            model._refuse_training()
         bsz = x.size(0)
         t = torch.randint(0, self.T, (bsz,), device=x.device).long()
         return self.p_losses(model, x, t)
 
     def draw_noise_stack(self, image_shape, device):
-        """[T, *image_shape] noise with the reference's draw order and generators (ddpm.py:33,36)."""
+        """[T, *image_shape] noise with the reference's draw order and generators (ddpm.py:33,36).  O(T * B * H * W)
+        memory: tests and small shapes only -- ``sample`` itself draws per step."""
         x = torch.randn(image_shape).to(device)
         stack = torch.empty((self.T,) + tuple(image_shape), dtype=torch.float32, device=device)
         stack[0] = x
         for k in range(1, self.T):
             stack[k] = torch.randn_like(x)
         return stack
+
+    def _sample_torch_rng(self, model, image_shape, device):
+        """The default call: torch's generators, consumed exactly like ddpm.py:33,36 (x_T on the CPU generator, then one
+        device ``randn_like`` per step with t > 0, drawn before the model call), with O(B * H * W) memory like the
+        reference: the loop runs step by step through the operator entry points (UNet forward + fused update)."""
+        x = torch.randn(image_shape).to(device)
+        B = x.shape[0]
+        logq = torch.zeros(B, 1, dtype=torch.float32, device=device)
+        ws = xstats = None
+        for t in reversed(range(self.T)):
+            noise = torch.randn_like(x) if t > 0 else None
+            t_tensor = torch.full((B,), t, dtype=torch.long, device=device)
+            eps = model._forward(x, t_tensor, xstats) if hasattr(model, "_forward") else model(x, t_tensor)
+            if ws is None:
+                nbytes = _lib.lib().sdd_superpose_update_workspace(B, x[0].numel(), 1)
+                ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+            x, logq, _, xstats = sampling.superpose_update(x, eps.unsqueeze(0), logq, self.alphas[t].item(),
+                                                      self.alpha_bars[t].item(), self.betas[t].item(), noise=noise,
+                                                      workspace=ws)
+        return x
 
     @torch.no_grad()
     def sample(self, model, image_shape, device, *, noise=None, seed=None, use_graph=True):
@@ -85,6 +114,6 @@ class DDPM:
             raise _lib.SddError("DDPM.sample runs on a CUDA device only (no CPU fallback); "
                                 "the CPU reference lives in oracle/ for tests")
         if noise is None and seed is None:
-            noise = self.draw_noise_stack(image_shape, device)
+            return self._sample_torch_rng(model, image_shape, device)
         return sampling.superposed_sample([model], self, image_shape, device, noise=noise, seed=seed,
                                           use_graph=use_graph)

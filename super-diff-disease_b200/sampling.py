@@ -38,6 +38,9 @@ class _Sampler:
     def launches(self):
         return int(_lib.lib().sdd_sampler_launches_per_run(self.ptr))
 
+    def graph_instantiations(self):
+        return int(_lib.lib().sdd_sampler_graph_instantiations(self.ptr))
+
     def close(self):
         if self.ptr:
             _lib.lib().sdd_sampler_destroy(self.ptr)
@@ -77,7 +80,8 @@ _MODES = {"or": 0, "and": 1}
 
 @torch.no_grad()
 def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bias=None, noise=None, seed=None,
-                      return_trajectory=False, use_graph=True, sample_offset=0, return_launches=False, mode="or"):
+                      return_trajectory=False, use_graph=True, sample_offset=0, return_launches=False, mode="or",
+                      return_x_trajectory=False):
     """Sample from the superposition of ``models`` (one model == DDPM.sample).
 
     models: sequence of super_diff_disease_b200.UNet on ``device``; ddpm: DDPM (schedule);
@@ -87,7 +91,8 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
     mode: "or" (kappa = softmax(temperature * log q + bias)) or "and" (kappa solved per sample and
     step so that every model's log-density increment is equal; temperature / bias unused).
     Returns x [B,1,H,W]; with return_trajectory also kappas [T,B,M] and logq [T+1,B,M]
-    (row k <-> loop iteration k, t = T-1-k).
+    (row k <-> loop iteration k, t = T-1-k); with return_x_trajectory additionally xs [T+1,B,1,H,W] (xs[0] = x_T,
+    xs[k+1] = the state after iteration k; the strip utils/visualization.py:6-28 plots).
     """
     if mode not in _MODES:
         raise _lib.SddError(f"mode must be 'or' or 'and', got {mode!r}")
@@ -132,12 +137,19 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
         lq = torch.empty((T + 1, B, M), dtype=torch.float32, device=device)
         args.kappa_traj, args.logq_traj = kap.data_ptr(), lq.data_ptr()
         keep += [kap, lq]
+    xs = None
+    if return_x_trajectory:
+        xs = torch.empty((T + 1, B, 1, H, W), dtype=torch.float32, device=device)
+        args.x_traj = xs.data_ptr()
+        keep.append(xs)
     args.use_graph = 1 if use_graph else 0
     args.mode = _MODES[mode]
     with torch.cuda.device(device):
         _lib.check(_lib.lib().sdd_sampler_run(s.ptr, ctypes.byref(args), _lib.stream_ptr(device)))
     s.keep = keep  # the stream may still be reading these
     out = (x, kap, lq) if return_trajectory else x
+    if return_x_trajectory:
+        out = (out + (xs,)) if isinstance(out, tuple) else (out, xs)
     if return_launches:
         return out, s.launches()
     return out

@@ -4,7 +4,9 @@ Same constructor, same module tree (hence the same 54 ``state_dict`` keys, so re
 ``load_state_dict(strict=True)`` unchanged), same ``forward(x, t)`` contract.  The modules below
 only HOLD parameters; ``forward`` hands raw device pointers to the C ABI (sdd_unet_forward), which
 runs the hand-written sm_100a kernels.  Inference only (sampling runs under ``torch.no_grad()``,
-src/train/training_logic.py:54).
+src/train/training_logic.py:54): called in ``train()`` mode with autograd enabled on parameters
+that require grad -- i.e. from the training loop, training_logic.py:28-36 -- ``forward`` raises
+instead of returning a loss that cannot be back-propagated.
 """
 import ctypes
 
@@ -57,6 +59,30 @@ class UNet(nn.Module):
                                   ResidualBlock(c, out_channels, time_emb_dim)])
         self._handle = None
         self._handle_key = None
+        self._max_chunk = 0
+
+    # ---- copies (ema_pytorch deep-copies the model, training_logic.py:16; torch.save(model) pickles it) ----------
+    # The sdd_unet_t* is a process-local device resource: it is never copied or pickled.  A copy starts without a
+    # handle and builds its own lazily, so two modules can never free the same handle.
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handle"] = None
+        state["_handle_key"] = None
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k in ("_handle", "_handle_key") else copy.deepcopy(v, memo)
+        return new
+
+    def set_max_chunk(self, max_samples):
+        """Cap the samples one pass of the forward processes at a time (0 = automatic).  Changes no result bit."""
+        self._max_chunk = int(max_samples)
+        if self._handle is not None:
+            _lib.check(_lib.lib().sdd_unet_set_max_chunk(self._handle, self._max_chunk))
 
     # ---- C-ABI handle management -------------------------------------------------------------
     def _param_key(self):
@@ -79,6 +105,8 @@ class UNet(nn.Module):
             arr = (ctypes.c_void_p * len(flat))(*[v.data_ptr() for v in flat])
             h = ctypes.c_void_p()
             _lib.check(L.sdd_unet_create(ctypes.byref(h), arr, len(flat), _lib.stream_ptr(dev)))
+            if self._max_chunk:
+                _lib.check(L.sdd_unet_set_max_chunk(h, self._max_chunk))
         self._handle, self._handle_key = h, key
         return h
 
@@ -98,9 +126,22 @@ class UNet(nn.Module):
             pass
 
     # ---- forward -----------------------------------------------------------------------------
-    @torch.no_grad()
+    def _refuse_training(self):
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise _lib.SddError(
+                "the B200 UNet is forward-only (no autograd graph): it was called in train() mode with gradients enabled "
+                "on parameters that require grad, so loss.backward() (training_logic.py:33) could not work.  Train with "
+                "the reference modules and build this UNet from the trained / EMA state_dict for sampling; for "
+                "evaluation call .eval() or wrap the call in torch.no_grad().")
+
     def forward(self, x, t):
         """x fp32 [B,1,H,W] (CUDA), t int64 [B] -> predicted noise fp32 [B,1,H,W] (unet.py:57-65)."""
+        self._refuse_training()
+        with torch.no_grad():
+            return self._forward(x, t)
+
+    def _forward(self, x, t, xstats=None):
+        """xstats (internal): fp32 [B,2] (mean, rstd) of each x sample from the update kernel that produced x."""
         _lib.require_cuda(x, "x")
         if x.dim() != 4 or x.shape[1] != 1:
             raise _lib.SddError(f"x must be [B,1,H,W], got {tuple(x.shape)}")
@@ -112,6 +153,7 @@ class UNet(nn.Module):
         out = torch.empty_like(xc)
         h = self.handle()
         with torch.cuda.device(x.device):
-            _lib.check(_lib.lib().sdd_unet_forward(h, xc.data_ptr(), tc.data_ptr(), out.data_ptr(), B, H, W,
-                                                   _lib.stream_ptr(x.device)))
+            _lib.check(_lib.lib().sdd_unet_forward_xstats(h, xc.data_ptr(),
+                                                          None if xstats is None else xstats.data_ptr(), tc.data_ptr(),
+                                                          out.data_ptr(), B, H, W, _lib.stream_ptr(x.device)))
         return out

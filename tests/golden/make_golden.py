@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference):
     python tests/golden/make_golden.py
-Writes tests/golden/unet_forward.npz and tests/golden/ddpm_sample.npz.
+Writes tests/golden/unet_forward.npz, unet_forward_r256.npz, ddpm_sample.npz and train_eval.npz.
 
 Weights come from oracle.init_unet_params(seed) (deterministic CPU generator) and are
 loaded into the reference ``UNet`` with ``load_state_dict(strict=True)``, so the fixtures
@@ -22,7 +22,7 @@ sys.path.insert(0, "/root/reference/src")
 from models.unet import UNet  # noqa: E402  (reference, unmodified)
 from models.ddpm import DDPM  # noqa: E402
 
-from oracle.superdiff_oracle import init_unet_params  # noqa: E402
+from oracle.superdiff_oracle import Schedule, ddpm_sample_replay, init_unet_params  # noqa: E402
 
 
 def param_checksum(p):
@@ -66,6 +66,16 @@ def main():
                     y = m(x, torch.full((B,), t, dtype=torch.long))
                 out[f"fwd_w{wseed}_x{xseed}_B{B}_R{R}_t{t}"] = y.numpy()
     np.savez_compressed(os.path.join(HERE, "unet_forward.npz"), **out)
+    # K1 at the headline resolution (BASELINE configs[2]): R = 256, both weight seeds
+    out = {}
+    for wseed in (0, 1):
+        m, _ = ref_model(wseed)
+        x = seeded_input(104, (1, 1, 256, 256))
+        for t in (0, 125, 249):
+            with torch.no_grad():
+                y = m(x, torch.full((1,), t, dtype=torch.long))
+            out[f"fwd_w{wseed}_x104_B1_R256_t{t}"] = y.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "unet_forward_r256.npz"), **out)
 
     # K2: DDPM.sample (reference RNG) -- replay must reproduce it from the drawn stack
     out = {}
@@ -77,9 +87,10 @@ def main():
             y = DDPM(num_timesteps=T).sample(m, shape, "cpu")
         out[f"sample_{name}"] = y.numpy()
         out[f"sample_{name}_meta"] = np.array([wseed, nseed, T, *shape], dtype=np.int64)
-        # sanity: replaying the drawn stack gives the same bits
+        # K2: replaying the drawn stack through the oracle's loop gives the reference's bits
         st = draw_noise_stack(nseed, shape, T)
-        assert torch.equal(st[0], st[0])
+        _, p = ref_model(wseed)
+        assert torch.equal(ddpm_sample_replay(p, Schedule(T), st), y), name
     d = DDPM(num_timesteps=1000)
     out["sched1000_betas"] = d.betas.numpy()
     out["sched1000_alpha_bars"] = d.alpha_bars.numpy()

@@ -88,6 +88,60 @@ def test_state_dict_contract():
         S.UNet(base_channels=32)
 
 
+def test_unet_copies_never_share_or_pickle_the_c_handle(tmp_path):
+    """ema_pytorch deep-copies the model and torch.save(model) pickles it (training_logic.py:16,47-48,55).  The C handle
+    is a ctypes pointer (unpicklable; a cloned one would be freed twice): copies drop it and rebuild lazily."""
+    import copy
+    import pickle
+    import super_diff_disease_b200 as S
+    m = S.UNet()
+    m._handle, m._handle_key = ctypes.c_void_p(0xDEAD0), ("fake",)  # as if a forward had run
+    c = copy.deepcopy(m)
+    assert c._handle is None and c._handle_key is None and m._handle.value == 0xDEAD0
+    assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    r = pickle.loads(pickle.dumps(m))
+    assert r._handle is None and list(r.state_dict()) == list(m.state_dict())
+    torch.save(m, tmp_path / "m.pt")
+    assert torch.load(tmp_path / "m.pt", weights_only=False)._handle is None
+    m._handle = m._handle_key = None  # nothing real to free
+
+
+def test_training_calls_are_refused_by_name():
+    """the swap applies at sampling / evaluation sites only.  In train() mode with gradients
+    enabled (training_logic.py:28-36) forward / training_step raise a named error rather than return a loss without a
+    grad_fn; the check runs before any device work, so it is testable without a GPU."""
+    import super_diff_disease_b200 as S
+    m = S.UNet().train()
+    x = torch.zeros(2, 1, 16, 16)
+    with pytest.raises(S.SddError, match="forward-only"):
+        m(x, torch.zeros(2, dtype=torch.long))
+    with pytest.raises(S.SddError, match="forward-only"):
+        S.DDPM(4).training_step(m, x)
+    with pytest.raises(S.SddError, match="forward-only"):
+        S.DDPM(4).p_losses(m, x, torch.zeros(2, dtype=torch.long))
+
+
+def test_reference_modules_installed_and_oracle_matches_them():
+    """baseline/_ref (git-ignored copy of the reference's unet.py / ddpm.py, baseline/install_ref.py) loads, and the
+    oracle reproduces the reference module's forward bit for bit on CPU; skipped where neither /root/reference nor an
+    installed baseline/_ref exists."""
+    from baseline import install_ref, ref_loader
+    from oracle import superdiff_oracle as O
+    install_ref.install(verbose=False)
+    ref = ref_loader.load()
+    if ref is None:
+        pytest.skip("no /root/reference and no baseline/_ref here")
+    RefUNet, RefDDPM = ref
+    p = O.init_unet_params(1)
+    net = RefUNet()
+    net.load_state_dict(p, strict=True)
+    x = torch.randn(2, 1, 32, 32, generator=torch.Generator().manual_seed(0))
+    t = torch.tensor([3, 700])
+    with torch.no_grad():
+        assert torch.equal(net.eval()(x, t), O.unet_forward(p, x, t))
+    assert torch.equal(RefDDPM(num_timesteps=100).alpha_bars, O.Schedule(100).alpha_bars)
+
+
 def test_ddpm_schedule_matches_golden(golden_dir):
     import super_diff_disease_b200 as S
     g = np.load(os.path.join(golden_dir, "ddpm_sample.npz"))
@@ -129,7 +183,16 @@ def _gloo_worker(rank, world, port, gb, q):
         return torch.from_numpy(philox_normal(99, np.arange(lo, hi), 0, 64)).reshape(hi - lo, 1, 8, 8)
 
     full = sharded_sample(local_fn, gb, (1, 8, 8), "cpu")
-    q.put((rank, full.numpy()))
+
+    def local_traj(lo, hi):  # x plus kappa [T,b,M] / log q [T+1,b,M] trajectories keyed by global sample id
+        ids = torch.arange(lo, hi, dtype=torch.float32)
+        kap = ids[None, :, None] + torch.arange(3.0)[:, None, None] * 100 + torch.arange(2.0)[None, None, :] * 0.5
+        lq = ids[None, :, None] - torch.arange(4.0)[:, None, None] * 10 + torch.arange(2.0)[None, None, :] * 0.25
+        return local_fn(lo, hi), kap, lq
+
+    x2, kap, lq = sharded_sample(local_traj, gb, (1, 8, 8), "cpu", trajectories=True)
+    assert torch.equal(x2, full)
+    q.put((rank, full.numpy(), kap.numpy(), lq.numpy()))
     dist.destroy_process_group()
 
 
@@ -143,11 +206,18 @@ def test_two_rank_gloo_gather_is_shard_invariant(gb):
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, gb, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=120) for _ in range(2))
+    got = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
         p.join(60)
+    res = {r: x for r, x, _, _ in got}
     single = philox_normal(99, np.arange(gb), 0, 64).reshape(gb, 1, 8, 8)
     assert np.array_equal(res[0], single) and np.array_equal(res[1], single)
+    # kappa [T, B, M] / log q [T+1, B, M] come back whole, in global sample order, on every rank
+    ids = np.arange(gb, dtype=np.float32)
+    kap_want = ids[None, :, None] + np.arange(3, dtype=np.float32)[:, None, None] * 100 + np.arange(2, dtype=np.float32)[None, None, :] * 0.5
+    lq_want = ids[None, :, None] - np.arange(4, dtype=np.float32)[:, None, None] * 10 + np.arange(2, dtype=np.float32)[None, None, :] * 0.25
+    for _, _, kap, lq in got:
+        assert np.array_equal(kap, kap_want) and np.array_equal(lq, lq_want)
 
 
 def test_cli_checkpoint_layout_and_grid(tmp_path):

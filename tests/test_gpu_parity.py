@@ -3,9 +3,11 @@
 Tolerances (stated per quantity):
   * fused update kernel (fp32 in/out): x' max-abs <= 2e-6 * max|x'|, logq rel <= 2e-5, kappa abs <= 2e-6
     (differences only from reduction order / expf ulps);
-  * tcgen05 conv vs fp32 conv of the SAME bf16-rounded operands: <= 1 bf16 ulp of the output (rtol 8e-3);
-  * UNet forward, bf16 operands / fp32 accumulate vs fp32 oracle: rel-L2 <= 2e-2, max-abs <= 5e-2 * max|ref|;
-  * sampling loops: final x rel-L2 <= 5e-2, kappa max-abs <= 5e-2, logq rel-to-max <= 2e-2.
+  * tcgen05 conv vs fp32 conv of the SAME fp16-rounded operands: <= 1 fp16 ulp of the output (rtol 1e-3);
+  * UNet forward, fp16 operands / fp32 accumulate vs the reference's fp32 output: rel-L2 <= 4e-3, max-abs <= 1.5e-2 *
+    max|ref| (error budget: DESIGN.md section 2; the round-1 bf16 pipeline measured 1.1e-2);
+  * short sampling loops: final x rel-L2 <= 1e-2, kappa max-abs <= 2e-2, logq rel-to-max <= 5e-3;
+  * BASELINE-config trajectories (full step counts, teacher-forced and free-running): tests/test_gpu_trajectory.py.
 Measured values are printed and appended to gpurun_out/parity_report.jsonl.
 """
 import json
@@ -51,7 +53,7 @@ def _models(S, dev, seeds):
         m = S.UNet()
         m.load_state_dict(p, strict=True)
         params.append(p)
-        models.append(m.to(dev))
+        models.append(m.to(dev).eval())
     return params, models
 
 
@@ -190,39 +192,11 @@ def test_philox_normals_match_oracle(S, dev):
 
 
 # ------------------------------------------------------------------ tcgen05 conv
-def _conv_ref(act_bf16, w, bias):
-    a = act_bf16.float().permute(0, 3, 1, 2)
-    wr = w.to(torch.bfloat16).float()
+def _conv_ref(act_f16, w, bias):
+    a = act_f16.float().permute(0, 3, 1, 2)
+    wr = w.to(torch.float16).float()
     y = F.conv2d(a, wr, None, padding=1) + bias[:, :, None, None]
     return y.permute(0, 2, 3, 1).contiguous()
-
-
-@pytest.mark.parametrize("impl", [0, 1])
-@pytest.mark.parametrize("Cin,Cout", [(64, 64), (64, 128), (128, 128), (128, 64)])
-@pytest.mark.parametrize("B,H,W", [(1, 16, 8), (2, 32, 24), (3, 48, 64)])
-def test_conv3x3_matches_fp32_conv_of_same_operands(S, dev, impl, Cin, Cout, B, H, W):
-    g = torch.Generator().manual_seed(Cin * 7 + Cout + H)
-    act = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
-    w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
-    bias = torch.randn(B, Cout, generator=g)
-    ref = _conv_ref(act, w, bias)
-    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
-    mr = torch.zeros(B, 4, 2, device=dev)
-    a_d, w_d, b_d = act.to(dev), w.to(dev), bias.to(dev)
-    rc = S.lib().sdd_conv3x3_nhwc(a_d.data_ptr(), w_d.data_ptr(), b_d.data_ptr(), Cout, out.data_ptr(),
-                                  mr.data_ptr(), B, H, W, Cin, Cout, impl, None)
-    assert rc == 0, S.lib().sdd_last_error()
-    torch.cuda.synchronize()
-    o = out.float().cpu()
-    err = (o - ref).abs().max().item()
-    _report(test="conv", impl=impl, Cin=Cin, Cout=Cout, B=B, H=H, W=W, max_abs=err, ref_max=ref.abs().max().item())
-    assert torch.allclose(o, ref, rtol=8e-3, atol=8e-3), err
-    # GroupNorm(4, Cout) statistics of the conv output
-    rg = ref.reshape(B, H * W, 4, Cout // 4).permute(0, 2, 1, 3).reshape(B, 4, -1)
-    mean, var = rg.mean(2), rg.var(2, unbiased=False)
-    m = mr.cpu()
-    assert torch.allclose(m[..., 0], mean, atol=3e-3), (m[..., 0] - mean).abs().max()
-    assert torch.allclose(m[..., 1], 1 / torch.sqrt(var + 1e-5), rtol=5e-3)
 
 
 @pytest.mark.parametrize("fuse", [False, True])
@@ -230,9 +204,9 @@ def test_conv3x3_matches_fp32_conv_of_same_operands(S, dev, impl, Cin, Cout, B, 
 @pytest.mark.parametrize("B,H,W", [(1, 16, 8), (3, 16, 8), (2, 32, 24), (3, 48, 64), (2, 128, 128)])
 def test_conv3x3_fused_2cta_kernel(S, dev, fuse, Cin, Cout, B, H, W):
     """The product conv kernel (2-CTA tcgen05, resident weights, halo views, fused GroupNorm+SiLU on the input)
-    vs an fp32 computation on the same bf16 operands.  Odd tile counts exercise the dummy-tile path."""
+    vs an fp32 computation on the same fp16 operands.  Odd tile counts exercise the dummy-tile path."""
     g = torch.Generator().manual_seed(Cin * 3 + Cout + H + B)
-    raw = (torch.randn(B, H, W, Cin, generator=g) * 1.7 + 0.3).to(torch.bfloat16)
+    raw = (torch.randn(B, H, W, Cin, generator=g) * 1.7 + 0.3).to(torch.float16)
     w = torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)
     bias = torch.randn(B, Cout, generator=g)
     if fuse:
@@ -240,13 +214,13 @@ def test_conv3x3_fused_2cta_kernel(S, dev, fuse, Cin, Cout, B, H, W):
         gamma, beta = torch.rand(Cin, generator=g) + 0.5, torch.randn(Cin, generator=g) * 0.2
         a = raw.float().reshape(B, H * W, 4, Cin // 4)
         a = (a - mr[:, None, :, 0:1]) * mr[:, None, :, 1:2]
-        act = F.silu(a.reshape(B, H, W, Cin) * gamma + beta).to(torch.bfloat16)
+        act = F.silu(a.reshape(B, H, W, Cin) * gamma + beta).to(torch.float16)
         mr_d, g_d, b_d = mr.to(dev), gamma.to(dev), beta.to(dev)
         ptrs = (mr_d.data_ptr(), g_d.data_ptr(), b_d.data_ptr())
     else:
         act, ptrs = raw, (None, None, None)
     ref = _conv_ref(act, w, bias)
-    out = torch.empty(B, H, W, Cout, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=dev)
     omr = torch.zeros(B, 4, 2, device=dev)
     r_d, w_d, bias_d = raw.to(dev), w.to(dev), bias.to(dev)
     rc = S.lib().sdd_conv3x3_fused_nhwc(r_d.data_ptr(), *ptrs, w_d.data_ptr(), bias_d.data_ptr(), Cout, out.data_ptr(),
@@ -256,35 +230,19 @@ def test_conv3x3_fused_2cta_kernel(S, dev, fuse, Cin, Cout, B, H, W):
     o = out.float().cpu()
     err = (o - ref).abs().max().item()
     _report(test="conv_fused", fuse=fuse, Cin=Cin, Cout=Cout, B=B, H=H, W=W, max_abs=err, ref_max=ref.abs().max().item())
-    tol = 3e-2 if fuse else 8e-3  # fused: tanh.approx SiLU may move an activation by one bf16 ulp
+    tol = 4e-3 if fuse else 1e-3  # fused: tanh.approx SiLU (2^-11 relative) may move an activation by one fp16 ulp
     assert torch.allclose(o, ref, rtol=tol, atol=tol), err
     rg = ref.reshape(B, H * W, 4, Cout // 4).permute(0, 2, 1, 3).reshape(B, 4, -1)
     mean, var = rg.mean(2), rg.var(2, unbiased=False)
     m = omr.cpu()
-    assert torch.allclose(m[..., 0], mean, atol=5e-3), (m[..., 0] - mean).abs().max()
-    assert torch.allclose(m[..., 1], 1 / torch.sqrt(var + 1e-5), rtol=1e-2)
-
-
-def test_gn_silu_apply(S, dev):
-    g = torch.Generator().manual_seed(11)
-    B, H, W, C = 2, 16, 8, 128
-    act = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
-    mr = torch.stack([torch.randn(B, 4, generator=g) * 0.1, torch.rand(B, 4, generator=g) + 0.5], -1)
-    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
-    a = act.float().reshape(B, H * W, 4, C // 4)
-    ref = (a - mr[:, None, :, 0:1]) * mr[:, None, :, 1:2]
-    ref = ref.reshape(B, H, W, C) * gamma + beta
-    ref = F.silu(ref)
-    d, mr_d, g_d, b_d = act.to(dev), mr.contiguous().to(dev), gamma.to(dev), beta.to(dev)
-    rc = S.lib().sdd_gn_silu_apply(d.data_ptr(), mr_d.data_ptr(), g_d.data_ptr(), b_d.data_ptr(), B, H, W, C, None)
-    torch.cuda.synchronize()
-    assert rc == 0, S.lib().sdd_last_error()
-    assert torch.allclose(d.float().cpu(), ref, rtol=1e-2, atol=1e-2)
+    assert torch.allclose(m[..., 0], mean, atol=2e-3), (m[..., 0] - mean).abs().max()
+    assert torch.allclose(m[..., 1], 1 / torch.sqrt(var + 1e-5), rtol=3e-3)
 
 
 # ------------------------------------------------------------------ UNet forward (K1)
 @pytest.mark.parametrize("wseed,xseed,B,R,t", [(0, 101, 2, 16, 0), (0, 101, 2, 16, 49), (1, 102, 2, 64, 1),
-                                               (1, 102, 2, 64, 999), (0, 103, 1, 128, 250)])
+                                               (1, 102, 2, 64, 999), (0, 103, 1, 128, 250), (0, 104, 1, 256, 0),
+                                               (1, 104, 1, 256, 125), (0, 104, 1, 256, 249)])
 def test_unet_forward_matches_oracle_and_golden(S, dev, golden_dir, wseed, xseed, B, R, t):
     params, models = _models(S, dev, [wseed])
     g = torch.Generator().manual_seed(xseed)
@@ -293,14 +251,15 @@ def test_unet_forward_matches_oracle_and_golden(S, dev, golden_dir, wseed, xseed
     y = models[0](x.to(dev), tt.to(dev)).cpu()
     with torch.no_grad():
         ref = O.unet_forward(params[0], x, tt)
-    gold = torch.from_numpy(np.load(os.path.join(golden_dir, "unet_forward.npz"))[f"fwd_w{wseed}_x{xseed}_B{B}_R{R}_t{t}"])
+    fixture = "unet_forward_r256.npz" if R == 256 else "unet_forward.npz"
+    gold = torch.from_numpy(np.load(os.path.join(golden_dir, fixture))[f"fwd_w{wseed}_x{xseed}_B{B}_R{R}_t{t}"])
     assert torch.allclose(ref, gold, atol=2e-5)  # the oracle is the reference
     rel, mx = _rel(y, gold), (y - gold).abs().max().item() / gold.abs().max().item()
     _report(test="unet_forward", R=R, t=t, rel_l2=rel, relmax=mx)
-    assert rel <= 2e-2 and mx <= 5e-2
+    assert rel <= 4e-3 and mx <= 1.5e-2
 
 
-def test_unet_forward_per_sample_timesteps_and_chunking(S, dev, monkeypatch):
+def test_unet_forward_per_sample_timesteps_and_chunking(S, dev):
     """t may differ per sample (ddpm.py:28 draws random t); chunked execution must not change results."""
     params, models = _models(S, dev, [1])
     g = torch.Generator().manual_seed(8)
@@ -309,9 +268,9 @@ def test_unet_forward_per_sample_timesteps_and_chunking(S, dev, monkeypatch):
     with torch.no_grad():
         ref = O.unet_forward(params[0], x, tt)
     y = models[0](x.to(dev), tt.to(dev)).cpu()
-    assert _rel(y, ref) <= 2e-2
-    monkeypatch.setenv("SDD_CHUNK", "2")
+    assert _rel(y, ref) <= 4e-3
     p2, m2 = _models(S, dev, [1])
+    m2[0].set_max_chunk(2)  # three passes of 2 + 2 + 1 samples
     y2 = m2[0](x.to(dev), tt.to(dev)).cpu()
     assert torch.equal(y, y2)
 
@@ -341,11 +300,13 @@ def test_ddpm_sample_matches_reference_golden(S, dev, golden_dir, name):
     ref = torch.from_numpy(g[f"sample_{name}"])
     rel, mx = _rel(y, ref), (y - ref).abs().max().item()
     _report(test="ddpm_sample", name=name, T=T, rel_l2=rel, max_abs=mx)
-    assert rel <= 5e-2
+    assert rel <= 5e-3
 
 
 def test_ddpm_sample_default_rng_contract(S, dev):
-    """Default call consumes torch's generators like ddpm.py:33,36: same seed -> same sample."""
+    """Default call consumes torch's generators like ddpm.py:33,36: same seed -> same sample, and the step-by-step
+    default path (operator entry points, O(B*H*W) memory) equals the captured-graph sampler fed the same draws BIT FOR
+    BIT (the same-seed comparison against the reference's own modules is tests/test_gpu_reference.py)."""
     _, models = _models(S, dev, [0])
     d = S.DDPM(5)
     torch.manual_seed(3); torch.cuda.manual_seed_all(3)
@@ -382,7 +343,7 @@ def test_k5_superposed_two_models_matches_oracle(S, dev, T, shape):
     el = ((lq.cpu() - lr).abs().max() / lr.abs().max()).item()
     _report(test="superposed", T=T, shape=list(shape), x_rel_l2=rel, kappa_abs=ek, logq_rel=el,
             kappa_min=kr.min().item(), kappa_max=kr.max().item())
-    assert rel <= 5e-2 and ek <= 5e-2 and el <= 2e-2
+    assert rel <= 1e-2 and ek <= 2e-2 and el <= 5e-3
 
 
 @pytest.mark.parametrize("M,shape,temperature,use_bias", [(3, (1, 1, 32, 24), 1.0, False), (2, (3, 1, 48, 16), 0.5, True),
@@ -403,18 +364,16 @@ def test_superposed_ragged_shapes_models_temperature_bias(S, dev, M, shape, temp
     el = ((lq.cpu() - lr).abs().max() / lr.abs().max()).item()
     _report(test="superposed_ragged", M=M, shape=list(shape), temperature=temperature, bias=use_bias, x_rel_l2=rel,
             kappa_abs=ek, logq_rel=el)
-    assert rel <= 5e-2 and ek <= 5e-2 and el <= 2e-2
+    assert rel <= 1e-2 and ek <= 2e-2 and el <= 5e-3
     assert torch.allclose(kap.sum(-1), torch.ones_like(kap[..., 0]), atol=1e-6)
 
 
 @pytest.mark.parametrize("T,shape", [(4, (2, 1, 256, 256)), (2, (1, 1, 512, 512))])
 def test_superposed_matches_oracle_at_baseline_resolutions(S, dev, T, shape):
     """BASELINE configs[2] / configs[3] resolutions (256^2, 512^2) at a batch and step count the CPU oracle finishes in
-    seconds.  Final x and the FIRST log-density increment (same x_T, kappa = 1/2 on both sides) are compared for every
-    sample.  The later kappa / log q trajectory is only comparable while kappa is saturated: in the transition region
-    softmax turns a 0.3 % error of two O(100) log-densities into a 0.1 change of kappa, after which the two runs mix the
-    models differently (measured with the fp32 oracle itself: a 1 % random perturbation of eps moves kappa by 0.02 and
-    log q by 1 % at 256^2) -- that is the algorithm's conditioning, not the kernels'."""
+    seconds; kappa, log q and x are compared over ALL samples and steps, no mask (round 1 masked kappa to saturated
+    samples and hid a 0.108 miss of the bf16 pipeline).  The runs at the configs' real step counts, with the fp32 oracle
+    on the GPU, are tests/test_gpu_trajectory.py."""
     params, models = _models(S, dev, [0, 1])
     g = torch.Generator().manual_seed(shape[-1] + T)
     stack = torch.randn((T,) + shape, generator=g)
@@ -425,13 +384,11 @@ def test_superposed_matches_oracle_at_baseline_resolutions(S, dev, T, shape):
     # the increment is a sum of cancelling O(beta D / 2) terms: measure its error on that scale
     scale = 0.5 * O.Schedule(T).betas[T - 1].item() * shape[2] * shape[3]
     first = ((lq[1] - lr[1]).abs() / (lr[1].abs() + scale)).max().item()
-    saturated = ((kr[1:] < 1e-3) | (kr[1:] > 1 - 1e-3)).all(dim=2).all(dim=0)  # per sample, over steps >= 1
-    ek = (kap - kr)[:, saturated].abs().max().item() if saturated.any() else 0.0
-    el = ((lq - lr)[:, saturated].abs().max() / lr.abs().max()).item() if saturated.any() else 0.0
-    _report(test="superposed_fullres", T=T, shape=list(shape), x_rel_l2=rel, first_logq_rel=first,
-            saturated_samples=int(saturated.sum()), kappa_abs_saturated=ek, logq_rel_saturated=el,
-            kappa_abs_all=(kap - kr).abs().max().item())
-    assert rel <= 5e-2 and first <= 1e-2 and ek <= 5e-2 and el <= 2e-2
+    ek = (kap - kr).abs().max().item()
+    el = ((lq - lr).abs().max() / lr.abs().max()).item()
+    _report(test="superposed_fullres", T=T, shape=list(shape), x_rel_l2=rel, first_logq_rel=first, kappa_abs_all=ek,
+            logq_rel_all=el, kappa_min=kr.min().item(), kappa_max=kr.max().item())
+    assert rel <= 1e-2 and first <= 2e-3 and ek <= 3e-2 and el <= 5e-3
     assert torch.allclose(kap.sum(-1), torch.ones_like(kap[..., 0]), atol=1e-6)
 
 
@@ -550,7 +507,72 @@ def test_graph_equals_eager_and_philox_shard_invariance(S, dev):
     st = O.philox_noise_stack(42, range(4), 8, (1, 32, 32))
     params = [O.init_unet_params(0), O.init_unet_params(1)]
     xr, _, _ = O.superposed_sample(params, O.Schedule(8), st)
-    assert _rel(a.cpu(), xr) <= 5e-2
+    assert _rel(a.cpu(), xr) <= 1e-2
+
+
+def test_graph_survives_new_seed_offset_and_trajectory_buffers(S, dev):
+    """The step graph holds pointers to sampler-owned device state only: a new seed, shard offset, noise stack,
+    temperature / bias or trajectory buffer must NOT re-capture it, and results must match eager."""
+    from super_diff_disease_b200 import sampling
+    _, models = _models(S, dev, [0, 1])
+    d = S.DDPM(6)
+    shape = (2, 1, 32, 32)
+    sampling.clear_cache()
+    outs = []
+    for seed, off in ((1, 0), (2, 0), (2, 5), (3, 7)):
+        x, kap, lq = S.superposed_sample(models, d, shape, dev, seed=seed, sample_offset=off, return_trajectory=True)
+        xe, kape, lqe = S.superposed_sample(models, d, shape, dev, seed=seed, sample_offset=off, return_trajectory=True,
+                                            use_graph=False)
+        assert torch.equal(x, xe) and torch.equal(kap, kape) and torch.equal(lq, lqe)
+        outs.append(x)
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[1], outs[2])
+    g = torch.Generator().manual_seed(0)
+    stack = torch.randn((6,) + shape, generator=g).to(dev)
+    a = S.superposed_sample(models, d, shape, dev, noise=stack, temperature=0.5, bias=[0.1, -0.1])
+    b = S.superposed_sample(models, d, shape, dev, noise=stack, temperature=0.5, bias=[0.1, -0.1], use_graph=False)
+    assert torch.equal(a, b)
+    (smp,) = sampling._SAMPLERS.values()
+    assert smp.graph_instantiations() == 1
+
+
+def test_bench_shape_tie_to_small_batch(S, dev):
+    """The bench shape (64 x 1 x 256 x 256, in-kernel Philox) is tied to the oracle through a bit-exact identity: sample
+    b of the 64-sample run equals the same global sample id produced by a 2-sample run with sample_offset = b (which
+    the oracle comparison above covers at this resolution).  T = 3 keeps it to seconds."""
+    _, models = _models(S, dev, [0, 1])
+    d = S.DDPM(3)
+    big, kb, lb = S.superposed_sample(models, d, (64, 1, 256, 256), dev, seed=77, return_trajectory=True)
+    for b in (0, 31, 62):
+        small, ks, ls = S.superposed_sample(models, d, (2, 1, 256, 256), dev, seed=77, sample_offset=b,
+                                            return_trajectory=True)
+        assert torch.equal(small, big[b:b + 2]) and torch.equal(ks, kb[:, b:b + 2]) and torch.equal(ls, lb[:, b:b + 2])
+    # and the small run against the oracle fed the same (numpy-restated) Philox stack
+    st = O.philox_noise_stack(77, [31, 32], 3, (1, 256, 256))
+    xr, kr, lr = O.superposed_sample([O.init_unet_params(0), O.init_unet_params(1)], O.Schedule(3), st)
+    assert _rel(big[31:33].cpu(), xr) <= 1e-2
+    assert (kb[:, 31:33].cpu() - kr).abs().max().item() <= 3e-2
+
+
+def test_unet_deepcopy_after_forward_and_two_devices(S, dev):
+    """ema_pytorch deep-copies the model (training_logic.py:16,55): a copy made AFTER a forward (live C handle) must
+    work and own its own handle.  With a second GPU in the process, a model there must launch too (function attributes
+    and SM counts are per device)."""
+    import copy
+    _, models = _models(S, dev, [0])
+    x = torch.randn(1, 1, 32, 32, device=dev)
+    t = torch.zeros(1, dtype=torch.long, device=dev)
+    y = models[0](x, t)
+    m2 = copy.deepcopy(models[0])
+    assert m2._handle is None
+    assert torch.equal(m2(x, t), y)
+    assert m2._handle is not None and m2._handle.value != models[0]._handle.value
+    if torch.cuda.device_count() >= 2:
+        d1 = torch.device("cuda:1")
+        m3 = copy.deepcopy(models[0]).to(d1)
+        y3 = m3(x.to(d1), t.to(d1))
+        assert torch.equal(y3.cpu(), y.cpu())
+        z = S.superposed_sample([m3, m3], S.DDPM(3), (1, 1, 64, 64), d1, seed=3)
+        assert torch.isfinite(z).all()
 
 
 def test_and_mode_philox_shard_invariance_and_three_models(S, dev):

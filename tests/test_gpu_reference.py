@@ -1,0 +1,105 @@
+"""GPU (-m gpu): the B200 path against the REFERENCE'S OWN MODULES running on the same GPU under the same seeds.
+
+``baseline/_ref`` holds /root/reference/src/models/{unet,ddpm}.py byte for byte (baseline/install_ref.py copies them in
+the build container; the directory is git-ignored and travels with the gpurun snapshot).  The reference draws x_T on
+the CPU generator and the per-step noise on the device generator (ddpm.py:33,36); ``DDPM.sample`` here keeps that
+contract, so with identical ``torch.manual_seed`` / ``torch.cuda.manual_seed_all`` both consume identical noise and the
+only difference left is fp16-operand tensor-core arithmetic vs the reference's fp32.
+"""
+import pytest
+import torch
+
+from baseline import ref_loader
+from oracle import superdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import __graft_entry__ as G
+    G.build()
+    import super_diff_disease_b200 as S
+    assert torch.cuda.is_available()
+    return S
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = ref_loader.load()
+    if r is None:
+        pytest.skip("baseline/_ref not installed (run baseline/install_ref.py where /root/reference exists)")
+    return r
+
+
+@pytest.fixture(autouse=True)
+def fp32_reference_on_gpu():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _pair(S, ref, wseed, dev):
+    RefUNet, _ = ref
+    p = O.init_unet_params(wseed)
+    r = RefUNet()
+    r.load_state_dict(p, strict=True)
+    m = S.UNet()
+    m.load_state_dict(r.state_dict(), strict=True)  # the reference's own state_dict drops in unchanged
+    return r.to(dev).eval(), m.to(dev).eval()
+
+
+@pytest.mark.parametrize("wseed,shape,T,seed", [(0, (2, 1, 32, 32), 20, 11), (1, (4, 1, 64, 64), 50, 1234),
+                                                (0, (1, 1, 256, 256), 100, 42)])
+def test_same_seed_ddpm_sample_vs_reference_modules(S, ref, wseed, shape, T, seed):
+    """reference: DDPM(T).sample(ref_unet.cuda(), shape, "cuda") under torch.no_grad (training_logic.py:52-55);
+    here: DDPM(T).sample(unet, shape, "cuda") -- same seeds, same RNG consumption order.  (4,1,64,64) / T = 50 is
+    BASELINE configs[0] moved onto the GPU; (1,1,256,256) is the shape training_logic.py:53 samples at."""
+    _, RefDDPM = ref
+    dev = torch.device("cuda:0")
+    r, m = _pair(S, ref, wseed, dev)
+    torch.manual_seed(seed); torch.cuda.manual_seed_all(seed)
+    with torch.no_grad():
+        y_ref = RefDDPM(num_timesteps=T).sample(r, shape, dev)
+    torch.manual_seed(seed); torch.cuda.manual_seed_all(seed)
+    y = S.DDPM(T).sample(m, shape, dev)
+    rel = ((y - y_ref).norm() / y_ref.norm()).item()
+    mx = ((y - y_ref).abs().max() / y_ref.abs().max()).item()
+    print("SAME-SEED", shape, T, "rel-L2", rel, "max-abs/max", mx)
+    assert y.shape == y_ref.shape and y.device == y_ref.device
+    assert rel <= 5e-3 and mx <= 2e-2
+
+
+def test_unet_forward_vs_reference_module_on_gpu(S, ref):
+    """UNet.forward against the reference's nn.Module evaluated in fp32 on the same GPU, per-sample timesteps."""
+    dev = torch.device("cuda:0")
+    r, m = _pair(S, ref, 1, dev)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((3, 1, 128, 128), generator=g).to(dev)
+    t = torch.tensor([0, 499, 999], device=dev)
+    with torch.no_grad():
+        y_ref = r(x, t)
+    y = m(x, t)
+    rel = ((y - y_ref).norm() / y_ref.norm()).item()
+    assert rel <= 4e-3, rel
+
+
+def test_training_entry_points_refuse_autograd(S, ref):
+    """the swap applies at sampling / evaluation sites only.  Called the way training_logic.py:32-36
+    calls them (gradients enabled, parameters requiring grad) the forward-only entry points raise a named error
+    instead of returning a loss whose backward() fails."""
+    dev = torch.device("cuda:0")
+    _, m = _pair(S, ref, 0, dev)
+    x = torch.randn(2, 1, 32, 32, device=dev)
+    d = S.DDPM(10)
+    m.train()  # training_logic.py:28
+    with pytest.raises(S.SddError, match="forward-only"):
+        d.training_step(m, x)
+    with pytest.raises(S.SddError, match="forward-only"):
+        m(x, torch.zeros(2, dtype=torch.long, device=dev))
+    with torch.no_grad():
+        assert torch.isfinite(d.training_step(m, x)).item()
+    m.eval()  # training_logic.py:52
+    assert torch.isfinite(d.training_step(m, x)).item()

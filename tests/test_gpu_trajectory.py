@@ -1,0 +1,184 @@
+"""GPU (-m gpu): trajectory parity of the superposed sampler at the BASELINE configs' REAL step counts
+(SURVEY.md 8(c) K5 "track growth over T"; /root/reference/src/models/ddpm.py:31-45 is a T-step loop).
+
+The checker is the fp32 oracle (oracle/superdiff_oracle.py: the reference's UNet / DDPM update restated, pinned by the
+goldens; A7 = our spec) RUN ON THE GPU as plain fp32 PyTorch with TF32 disabled, so that T = 100 / 250 / 1000 steps
+cost seconds.  Both sides consume the SAME explicit noise stack.  Two comparisons per config, over ALL samples:
+
+  * free-running: both loops start from x_T and run independently; per step kappa max-abs, log q rel-to-max and
+    x rel-L2 are recorded (this is what a user sees, and it includes the algorithm's own sensitivity: kappa is a
+    softmax of two accumulated O(D) log-densities);
+  * teacher-forced: at every step the oracle evaluates ONE step from the CUDA path's own state (x_k, log q_k) and the
+    results are compared with the CUDA path's (x_{k+1}, log q_{k+1}, kappa_k, eps-hat): this isolates the kernels'
+    per-step error from the trajectory's conditioning.
+For configs[1] the oracle is additionally run against ITSELF with eps-hat perturbed by a relative 2e-3 (the CUDA
+forward's measured error level): the kappa / log q / x deviations of that fp32-vs-fp32 pair are the yardstick for
+what "the same trajectory" can mean.  Curves go to gpurun_out/parity_growth.json (committed copy:
+profiles/r2_parity_growth.json); the bounds asserted here are the per-quantity tolerance table of DESIGN.md section 2.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import superdiff_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def S():
+    import __graft_entry__ as G
+    G.build()
+    import super_diff_disease_b200 as S
+    assert torch.cuda.is_available()
+    return S
+
+
+@pytest.fixture(autouse=True)
+def fp32_oracle_on_gpu():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _save(name, rec):
+    path = os.path.join(ROOT, "gpurun_out", "parity_growth.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    data = json.load(open(path)) if os.path.exists(path) else {}
+    data[name] = rec
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1)
+
+
+def _curves(xs, kap, lq, xs_o, kap_o, lq_o):
+    """Per-step deviations between two trajectories (row k+1 = after iteration k), over all samples."""
+    T = kap.shape[0]
+    out = {"kappa_abs": [], "logq_rel": [], "x_rel_l2": []}
+    for k in range(T):
+        out["kappa_abs"].append((kap[k] - kap_o[k]).abs().max().item())
+        out["logq_rel"].append(((lq[k + 1] - lq_o[k + 1]).abs().max() / lq_o[k + 1].abs().max().clamp_min(1e-30)).item())
+        out["x_rel_l2"].append(((xs[k + 1] - xs_o[k + 1]).norm() / xs_o[k + 1].norm()).item())
+    return out
+
+
+def _summary(c):
+    return {k: {"max": max(v), "final": v[-1]} for k, v in c.items()}
+
+
+def _thin(c, n=100):
+    """Keep the curves small in the committed JSON: every ceil(T/n)-th step plus the last."""
+    out = {}
+    for k, v in c.items():
+        st = max(1, (len(v) + n - 1) // n)
+        out[k] = v[::st] + ([v[-1]] if (len(v) - 1) % st else [])
+    out["stride"] = max(1, (len(next(iter(c.values()))) + n - 1) // n)
+    return out
+
+
+def _run(S, name, B, R, T, tf_stride=1, sensitivity=False):
+    dev = torch.device("cuda:0")
+    params = [O.init_unet_params(0), O.init_unet_params(1)]
+    models = []
+    for p in params:
+        m = S.UNet()
+        m.load_state_dict(p, strict=True)
+        models.append(m.to(dev).eval())
+    pd = [O.params_to(p, dev) for p in params]
+    shape = (B, 1, R, R)
+    g = torch.Generator(device=dev).manual_seed(1234 + R)
+    stack = torch.randn((T,) + shape, generator=g, device=dev)
+    sched = O.Schedule(T)
+    # ---- CUDA path: the captured-graph sampler, all trajectories out
+    x, kap, lq, xs = S.superposed_sample(models, S.DDPM(T), shape, dev, noise=stack, return_trajectory=True,
+                                         return_x_trajectory=True)
+    torch.cuda.synchronize()
+    assert torch.equal(xs[T], x) and torch.equal(xs[0], stack[0])
+    # ---- free-running fp32 oracle on the GPU
+    xs_o = torch.empty_like(xs)
+    x_o, kap_o, lq_o = O.superposed_sample(pd, sched, stack, x_trajectory=xs_o)
+    free = _curves(xs, kap, lq, xs_o, kap_o, lq_o)
+    # ---- teacher-forced: one oracle step from the CUDA path's state at every tf_stride-th step
+    D = R * R
+    tf = {"eps_rel_l2": [], "kappa_abs": [], "x_rel_l2": [], "inc_err_over_betaD2": [], "steps": []}
+    with torch.no_grad():
+        for k in list(range(0, T, tf_stride)) + ([T - 1] if (T - 1) % tf_stride else []):
+            t = T - 1 - k
+            tt = torch.full((B,), t, dtype=torch.long, device=dev)
+            eps_o = [O.unet_forward(p, xs[k], tt) for p in pd]
+            eps_c = [m(xs[k], tt) for m in models]
+            noise = stack[k + 1] if t > 0 else torch.zeros_like(xs[k])
+            x1, lq1, kp = O.superpose_step(xs[k], eps_o, noise, lq[k], sched.alphas[t], sched.alpha_bars[t],
+                                           sched.betas[t])
+            tf["steps"].append(k)
+            tf["eps_rel_l2"].append(max(((c - o).norm() / o.norm()).item() for c, o in zip(eps_c, eps_o)))
+            tf["kappa_abs"].append((kap[k] - kp).abs().max().item())
+            tf["x_rel_l2"].append(((xs[k + 1] - x1).norm() / x1.norm()).item())
+            # the increment is a sum of cancelling O(beta D / 2) terms: its error is measured on that scale
+            scale = 0.5 * sched.betas[t].item() * D
+            tf["inc_err_over_betaD2"].append((((lq[k + 1] - lq[k]) - (lq1 - lq[k])).abs().max() / scale).item())
+    rec = {"config": {"B": B, "R": R, "T": T, "models": 2, "noise": "explicit stack, torch.randn on cuda, seed 1234+R",
+                      "oracle": "fp32 PyTorch on cuda:0, TF32 disabled"},
+           "free_running": {"summary": _summary(free), "curves": _thin(free)},
+           "teacher_forced": {"summary": {k: {"max": max(v), "final": v[-1]} for k, v in tf.items() if k != "steps"},
+                              "stride": tf_stride,
+                              "curves": _thin({k: v for k, v in tf.items() if k != "steps"})},
+           "kappa_range_oracle": [kap_o.min().item(), kap_o.max().item()],
+           "logq_final_abs_max": lq_o[T].abs().max().item()}
+    if sensitivity:
+        # fp32 oracle vs fp32 oracle with eps-hat perturbed at the CUDA forward's error level
+        gen = torch.Generator(device=dev).manual_seed(7)
+
+        def hook(it, eps_list):
+            return [e * (1 + 2e-3 * torch.randn(e.shape, generator=gen, device=dev)) for e in eps_list]
+
+        xs_p = torch.empty_like(xs)
+        _, kap_p, lq_p = O.superposed_sample(pd, sched, stack, x_trajectory=xs_p, eps_hook=hook)
+        sens = _curves(xs_p, kap_p, lq_p, xs_o, kap_o, lq_o)
+        rec["oracle_self_sensitivity_eps_2e-3"] = {"summary": _summary(sens), "curves": _thin(sens)}
+    _save(name, rec)
+    print("TRAJECTORY", name, json.dumps({"free": rec["free_running"]["summary"],
+                                          "teacher_forced": rec["teacher_forced"]["summary"]}))
+    return rec
+
+
+# Tolerance table.  teacher-forced = the kernels' per-step error; free-running = whole trajectory.
+TF_BOUNDS = {"eps_rel_l2": 4e-3, "kappa_abs": 2e-6, "x_rel_l2": 2e-5, "inc_err_over_betaD2": 2e-3}
+
+
+def _check(rec, free_kappa, free_logq, free_x):
+    tf = rec["teacher_forced"]["summary"]
+    for k, b in TF_BOUNDS.items():
+        assert tf[k]["max"] <= b, (k, tf[k])
+    fr = rec["free_running"]["summary"]
+    assert fr["kappa_abs"]["max"] <= free_kappa, fr["kappa_abs"]
+    assert fr["logq_rel"]["max"] <= free_logq, fr["logq_rel"]
+    assert fr["x_rel_l2"]["final"] <= free_x, fr["x_rel_l2"]
+
+
+def test_c2_full_config_trajectory(S):
+    """BASELINE configs[1] in full: 128 x 128, batch 16, 100 steps, two models."""
+    rec = _run(S, "c2_B16_R128_T100", 16, 128, 100, sensitivity=True)
+    _check(rec, free_kappa=5e-2, free_logq=5e-3, free_x=1e-2)
+    # the CUDA path stays inside the fp32 oracle's own sensitivity to a 2e-3 perturbation of eps-hat (x2 margin)
+    sens = rec["oracle_self_sensitivity_eps_2e-3"]["summary"]
+    assert rec["free_running"]["summary"]["kappa_abs"]["max"] <= 2 * sens["kappa_abs"]["max"] + 1e-3
+
+
+def test_c3_trajectory_at_full_step_count(S):
+    """BASELINE configs[2] at its real step count (256 x 256, 250 steps) on 4 of the 64 samples (per-sample path:
+    test_bench_shape_tie_to_small_batch shows a sample's bits do not depend on the batch it runs in)."""
+    rec = _run(S, "c3_B4_R256_T250", 4, 256, 250)
+    _check(rec, free_kappa=5e-2, free_logq=5e-3, free_x=1e-2)
+
+
+def test_c4_shard_trajectory_1000_steps(S):
+    """BASELINE configs[3]: 512 x 512, the full 1000-step schedule, one sample of a GPU's 4-sample shard; teacher-forced
+    at every 10th step."""
+    rec = _run(S, "c4_B1_R512_T1000", 1, 512, 1000, tf_stride=10)
+    _check(rec, free_kappa=5e-2, free_logq=5e-3, free_x=1e-2)
