@@ -11,7 +11,8 @@ class SddError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsdd_b200.so")
+    """The built library; SDD_LIB names an alternative build (same-box A/B of kernel variants, tools/README.md)."""
+    return os.environ.get("SDD_LIB") or os.path.join(_HERE, "libsdd_b200.so")
 
 
 class SampleArgs(ctypes.Structure):

@@ -22,20 +22,21 @@ def _stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, out=None, flags=()):
+    """out / flags: build a VARIANT of the library (extra -D flags) to another path for same-box A/B runs."""
+    if out is None and not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
            "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v" if verbose else "-O3",
-           "-o", LIB] + os.environ.get("SDD_NVCC_FLAGS", "").split() + [os.path.join(CSRC, f) for f in SOURCES]
+           "-o", out or LIB] + list(flags) + [os.path.join(CSRC, f) for f in SOURCES]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("nvcc failed building libsdd_b200.so")
     if verbose:
         sys.stderr.write(r.stdout + r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

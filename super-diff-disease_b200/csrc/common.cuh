@@ -367,6 +367,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 // round-1 figure); the same three roundings in fp16 cost 7-9e-4 each (1.6-1.9e-3 together) at the same tcgen05
 // kind::f16 rate.  Range: every conv input is a GroupNorm+SiLU output (bounded), so |conv output| <= |w|_1 * max|act|;
 // conversions saturate at +-65504 instead of producing inf.
+#ifndef SDD_ACT_BF16
 typedef __half act_t;
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
   uint32_t r;
@@ -378,9 +379,23 @@ __device__ __forceinline__ void unpack_act2(uint32_t u, float& lo, float& hi) {
       : "=f"(lo), "=f"(hi)
       : "r"(u));
 }
-__device__ __forceinline__ float act_to_float(act_t v) { return __half2float(v); }
+#define SDD_ACT_TMAP_TYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define SDD_ACT_IDESC umma_idesc_f16
+#else
+// A/B build only (tools/README.md): the round-1 bf16 pipeline, to measure what the fp16 operands cost or buy on the
+// same box.  Not the product configuration: tests and tolerances assume fp16.
+typedef __nv_bfloat16 act_t;
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) { return pack_bf16x2(lo, hi); }
+__device__ __forceinline__ void unpack_act2(uint32_t u, float& lo, float& hi) {
+  lo = __uint_as_float(u << 16);
+  hi = __uint_as_float(u & 0xffff0000u);
+}
+#define SDD_ACT_TMAP_TYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define SDD_ACT_IDESC umma_idesc_bf16
+#endif
 __device__ __forceinline__ act_t float_to_act(float v) {
-  return __ushort_as_half((unsigned short)(pack_act2(v, 0.f) & 0xffffu));
+  const unsigned short bits = (unsigned short)(pack_act2(v, 0.f) & 0xffffu);
+  return *reinterpret_cast<const act_t*>(&bits);
 }
 
 }  // namespace sdd

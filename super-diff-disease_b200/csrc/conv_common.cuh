@@ -8,6 +8,10 @@
 
 namespace sdd {
 
+#ifndef SDD_CONV_HALF_MATH
+#define SDD_CONV_HALF_MATH false  // fused GroupNorm+SiLU transform in fp32 (true: packed fp16 math, see conv_tc4.cuh)
+#endif
+
 constexpr int kTileH = 16, kTileW = 8;  // 128 output pixels per CTA and accumulator
 constexpr int kHaloW = kTileW + 2;
 constexpr int kHaloRowsV2 = (kTileH + 2) * kHaloW;                              // 180 rows of 128 B per 64-channel box
@@ -27,7 +31,7 @@ struct ConvTc3Args {
   const float* in_ab;          // [2][B][Cin] pre-halved GroupNorm+SiLU scale (plane 0) / shift (plane 1) per sample and
                                // channel, written by gn_scale_shift_kernel; nullptr: the input is used as is
   long long* out_sums;         // [B][4][2] fixed-point accumulators of the OUTPUT (zeroed by the caller), or nullptr
-  int B, H, W, Cin;
+  int B, H, W;
   int tiles_w, tiles_per_sample, num_tiles, num_pairs;
   int stages;
   int contig;                  // contiguous tile-pair ranges per CTA pair (0 = strided by the grid)

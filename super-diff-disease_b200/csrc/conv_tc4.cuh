@@ -29,7 +29,12 @@ namespace sdd {
 // conflict-free LDS.128 from the same swizzled offsets they write to (the TMA box lands in the UMMA layout), no thread
 // has a global load outstanding at the fence, and address arithmetic leaves the loaders entirely.  Cost: one more
 // shared-memory write + read per byte (23 KB + 23 KB per item), affordable where the MMA leaves bandwidth.
-template <int COUT, bool kRaw = false>
+// CIN is a template parameter: with the chunk count a compile-time constant every weight-slice / tap offset below is an
+// immediate added to ONE base descriptor (the 40-register control warps spill anything the compiler hoists), the loaders'
+// address arithmetic folds, and all chunk loops unroll.
+// kHalfMath: the fused GroupNorm+SiLU transform on packed fp16 pairs (HFMA2, MUFU.TANH.F16 x2, HFMA2: 5 instructions per
+// pair, no conversions) instead of fp32 (7 per pair); costs ~1e-3 of forward rel-L2 (tools/error_budget.py).
+template <int COUT, int CIN, bool kRaw = false, bool kHalfMath = SDD_CONV_HALF_MATH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
 conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ConvTc3Args a) {
@@ -37,8 +42,8 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   constexpr int kTmemCols = 2 * COUT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int kchunks = a.Cin / 64;
-  const uint32_t w_bytes = 9u * kchunks * kWSlot;
+  constexpr int kchunks = CIN / 64;
+  constexpr uint32_t w_bytes = 9u * kchunks * kWSlot;
   const uint32_t a_base = smem_base + w_bytes;
   const uint32_t raw_base = a_base + (uint32_t)a.stages * kHaloBytes;
   const uint32_t bar_base = raw_base + (uint32_t)(kRaw ? a.raw_slots : 0) * kHaloBytes;
@@ -119,28 +124,35 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA; whole warp walks the loop, one elected lane issues) ===
     if (rank == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(256, COUT);
+      constexpr uint32_t idesc = SDD_ACT_IDESC(256, COUT);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int pair = pair0; pair < pair_end; pair += pair_step()) {
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = SDD_TMEM_BASE() + (uint32_t)(acc * COUT);
+#pragma unroll
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait_cluster(ready_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = a_base + stage * kHaloBytes;
           if (elect_one_sync()) {
+            // one base descriptor per operand; taps, chunks and K steps are immediates in 16-byte units (shared-memory
+            // addresses are < 2^18, so the 14-bit start-address field never carries)
+            // (`opaque` is a zero ptxas cannot see through: without it the 36 x 2 loop-invariant B descriptors are hoisted
+            // out of the tile loop and, at 40 registers, spilled and re-loaded from local memory in front of every MMA)
+            uint32_t opaque;
+            asm volatile("mov.u32 %0, 0;" : "=r"(opaque));
+            const uint64_t adesc0 = umma_desc_sw128(a_base + stage * kHaloBytes, kHaloW * 128);
+            const uint64_t bdesc0 = umma_desc_sw128(smem_base + opaque);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
-                const uint64_t adesc = umma_desc_sw128(sa + (ky * kHaloW + kx) * 128, kHaloW * 128);
-                const uint64_t bdesc = umma_desc_sw128(smem_base + (uint32_t)((kx * 3 + ky) * kchunks + kc) * kWSlot);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)  // 4 x UMMA_K (16 fp16 = 32 B) inside the 128-byte swizzle row
-                  umma_f16_2cta(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
-                                 (kc | kx | ky | k) ? 1u : 0u);
+                  umma_f16_2cta(d_tmem, adesc0 + (uint64_t)((ky * kHaloW + kx) * 8 + k * 2),
+                                bdesc0 + (uint64_t)((((kx * 3 + ky) * kchunks + kc) * kWSlot) / 16 + k * 2), idesc,
+                                (kc | kx | ky | k) ? 1u : 0u);
               }
             umma_commit_2cta(empty_bar(stage));                         // frees the stage in both CTAs
             if (kc == kchunks - 1) umma_commit_2cta(tfull_bar(acc));    // accumulator complete -> both epilogues
@@ -334,7 +346,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
     for (int i = 0; i < kVecs; ++i) {
       const int r = col + 16 * i, hr = r / kHaloW, wr = r - hr * kHaloW;
-      goff[i] = (uint32_t)((hr * a.W + wr) * a.Cin * 2 + piece * 16);
+      goff[i] = (uint32_t)((hr * a.W + wr) * CIN * 2 + piece * 16);
     }
     const uint32_t soff = (uint32_t)col * 128u + (uint32_t)((piece ^ (col & 7)) << 4);  // + i * 2048
 
@@ -368,7 +380,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // pointer to the box origin of a tile (chunk kc) and the mask of this thread's in-image vectors
     auto tile_src = [&](const Cursor& c, const uint8_t*& base, uint32_t& okmask) {
       const int h0 = c.th * kTileH - 1, w0 = c.tw * kTileW - 1;
-      base = in_bytes + (((long long)c.n * a.H + h0) * a.W + w0) * (long long)(a.Cin * 2) + kc * 128;
+      base = in_bytes + (((long long)c.n * a.H + h0) * a.W + w0) * (long long)(CIN * 2) + kc * 128;
       const uint32_t all = (1u << nvec) - 1u;
       const bool interior = c.th > 0 && c.th < tiles_h - 1 && c.tw > 0 && c.tw < a.tiles_w - 1;
       if (interior) { okmask = all; return; }
@@ -402,31 +414,46 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t ga2[4] = {0ull, 0ull, 0ull, 0ull}, gb2[4] = {0ull, 0ull, 0ull, 0ull};
     mbar_wait(w_bar, 0);  // this CTA's weights have landed (the MMA warp relies on the loaders for this)
 
-    // silu(gn(v)) of one fp16 pair: 2 cvt + FFMA2 + 2 MUFU.TANH + FFMA2 + 1 cvt.f16x2
+    // silu(gn(v)) of one fp16 pair, silu(v) = h + h tanh(h), h = v / 2 (scale / shift arrive pre-halved):
+    //   fp32 math: 2 cvt + FFMA2 + 2 MUFU.TANH + FFMA2 + 1 cvt.f16x2;  fp16 math: HFMA2 + 2 MUFU.TANH.F16 + PRMT + HFMA2
+    uint32_t gah[4] = {0u, 0u, 0u, 0u}, gbh[4] = {0u, 0u, 0u, 0u};  // kHalfMath: packed fp16 scale / shift
     auto xform_pair = [&](uint32_t u, int j) -> uint32_t {
-      float vl, vh;
-      unpack_act2(u, vl, vh);
-      const uint64_t h = fma_f32x2(pack_f32x2(vl, vh), ga2[j], gb2[j]);
-      float hl, hh;
-      unpack_f32x2(h, hl, hh);
-      const uint64_t q2 = fma_f32x2(h, pack_f32x2(tanh_approx(hl), tanh_approx(hh)), h);
-      float rl, rh;
-      unpack_f32x2(q2, rl, rh);
-      return pack_act2(rl, rh);
+      if constexpr (kHalfMath) {
+        uint32_t h, t, r;
+        asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(h) : "r"(u), "r"(gah[j]), "r"(gbh[j]));
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(h));
+        asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(h), "r"(t));
+        return r;
+      } else {
+        float vl, vh;
+        unpack_act2(u, vl, vh);
+        const uint64_t h = fma_f32x2(pack_f32x2(vl, vh), ga2[j], gb2[j]);
+        float hl, hh;
+        unpack_f32x2(h, hl, hh);
+        const uint64_t q2 = fma_f32x2(h, pack_f32x2(tanh_approx(hl), tanh_approx(hh)), h);
+        float rl, rh;
+        unpack_f32x2(q2, rl, rh);
+        return pack_act2(rl, rh);
+      }
     };
 
     while (item < my_items) {
       // ---- GroupNorm scale / shift: this group's chunk is fixed, so the registers only change with the sample
       if (fuse && c.n != cur_n) {
         // precomputed by gn_scale_shift_kernel: this thread's eight channels, four 16-byte loads, no barrier
-        const float* pa = a.in_ab + ((size_t)c.n * a.Cin + kc * 64 + piece * 8);
-        const float* pb = pa + (size_t)a.B * a.Cin;
+        const float* pa = a.in_ab + ((size_t)c.n * CIN + kc * 64 + piece * 8);
+        const float* pb = pa + (size_t)a.B * CIN;
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
           const float4 x = __ldg(reinterpret_cast<const float4*>(pa + 2 * j));
           const float4 y = __ldg(reinterpret_cast<const float4*>(pb + 2 * j));
-          ga2[j] = pack_f32x2(x.x, x.y); ga2[j + 1] = pack_f32x2(x.z, x.w);
-          gb2[j] = pack_f32x2(y.x, y.y); gb2[j + 1] = pack_f32x2(y.z, y.w);
+          if constexpr (kHalfMath) {
+            gah[j] = pack_act2(x.x, x.y); gah[j + 1] = pack_act2(x.z, x.w);
+            gbh[j] = pack_act2(y.x, y.y); gbh[j + 1] = pack_act2(y.z, y.w);
+          } else {
+            ga2[j] = pack_f32x2(x.x, x.y); ga2[j + 1] = pack_f32x2(x.z, x.w);
+            gb2[j] = pack_f32x2(y.x, y.y); gb2[j + 1] = pack_f32x2(y.z, y.w);
+          }
         }
         cur_n = c.n;
       }

@@ -97,7 +97,7 @@ static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, i
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)kHaloW, (cuuint32_t)(kTileH + 2), 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, SDD_ACT_TMAP_TYPE, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -114,7 +114,7 @@ static int make_wt_map(CUtensorMap* m, const void* base, int Cout, int Cin) {
   cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)(Cout / 2), 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, SDD_ACT_TMAP_TYPE, 3, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -149,10 +149,11 @@ static int ensure_func_attrs() {
   std::lock_guard<std::mutex> lock(g_dev_mu);
   if (c->attrs) return SDD_OK;
   const int reg_smem = conv_tc3_smem_bytes(128, 128, conv_tc3_stages(128, 128));
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, reg_smem));
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, reg_smem));
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
-  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
+  // the four instantiations the launch policy uses: <Cout, Cin, raw ring>
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, reg_smem));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, reg_smem));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
+  SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
   SDD_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   c->attrs = true;
   return SDD_OK;
@@ -188,7 +189,7 @@ static int launch_conv(const CUtensorMap& tmA_halo, const CUtensorMap& tmB, cons
     a.in_ab = gi.ab;
   }
   a.out_sums = out_sums;
-  a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+  a.B = B; a.H = H; a.W = W;
   a.tiles_w = W / kTileW;
   a.tiles_per_sample = (H / kTileH) * a.tiles_w;
   a.num_tiles = B * a.tiles_per_sample;
@@ -197,20 +198,19 @@ static int launch_conv(const CUtensorMap& tmA_halo, const CUtensorMap& tmB, cons
   a.raw_slots = 0;
   a.contig = (Cin == 64 && Cout == 64) ? 1 : 0;
   a.prefetch = 1;
-  bool use_raw = false;
-  if (Cin != Cout) {
+  if (Cin != Cout) {  // raw ring: 3 operand stages + up to 4 raw slots (both layers fit all 4)
     constexpr int kRawStages = 3, kRawMaxSlots = 4;
     int slots = kRawMaxSlots;
-    while (slots > 0 && conv_tc3_smem_bytes(Cout, Cin, kRawStages + slots) > kC2SmemLimit - 4096) --slots;
-    if (slots >= 3) { use_raw = true; a.stages = kRawStages; a.raw_slots = slots; }
+    while (slots > 3 && conv_tc3_smem_bytes(Cout, Cin, kRawStages + slots) > kC2SmemLimit - 4096) --slots;
+    a.stages = kRawStages; a.raw_slots = slots;
   }
   const int smem = conv_tc3_smem_bytes(Cout, Cin, a.stages + a.raw_slots);
+  SDD_CHECK(smem <= kC2SmemLimit - 4096, "conv shared-memory plan does not fit");
   const int grid = 2 * std::min(a.num_pairs, num_sms() / 2);
-  if (use_raw) {
-    if (Cout == 64) conv3x3_tc4_kernel<64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
-    else conv3x3_tc4_kernel<128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
-  } else if (Cout == 64) conv3x3_tc4_kernel<64><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
-  else conv3x3_tc4_kernel<128><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
+  if (Cin == 64 && Cout == 64) conv3x3_tc4_kernel<64, 64, false><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
+  else if (Cin == 128 && Cout == 128) conv3x3_tc4_kernel<128, 128, false><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
+  else if (Cin == 64) conv3x3_tc4_kernel<128, 64, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
+  else conv3x3_tc4_kernel<64, 128, true><<<grid, kC3Threads, smem, st>>>(tmA_halo, tmB, a);
   SDD_LAUNCH_CHECK();
   return SDD_OK;
 }

@@ -375,8 +375,13 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const act_t* __
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint32_t af[4] = {a[0][ks * 2], a[1][ks * 2], a[0][ks * 2 + 1], a[1][ks * 2 + 1]};
+#ifndef SDD_ACT_BF16
         mma_f16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
         mma_f16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
+#else
+        mma_bf16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
+        mma_bf16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
+#endif
       }
       // d0: taps 2t, 2t+1 of rows j and j+8; d1: taps 8+2t, 9+2t (only tap 8 exists)
       const int r0 = mt * 16 + j;

@@ -105,7 +105,7 @@ def _run(S, name, B, R, T, tf_stride=1, sensitivity=False):
     free = _curves(xs, kap, lq, xs_o, kap_o, lq_o)
     # ---- teacher-forced: one oracle step from the CUDA path's state at every tf_stride-th step
     D = R * R
-    tf = {"eps_rel_l2": [], "kappa_abs": [], "x_rel_l2": [], "inc_err_over_betaD2": [], "steps": []}
+    tf = {"eps_rel_l2": [], "kappa_abs": [], "x_rel_l2": [], "inc_rel": [], "steps": []}
     with torch.no_grad():
         for k in list(range(0, T, tf_stride)) + ([T - 1] if (T - 1) % tf_stride else []):
             t = T - 1 - k
@@ -119,9 +119,11 @@ def _run(S, name, B, R, T, tf_stride=1, sensitivity=False):
             tf["eps_rel_l2"].append(max(((c - o).norm() / o.norm()).item() for c, o in zip(eps_c, eps_o)))
             tf["kappa_abs"].append((kap[k] - kp).abs().max().item())
             tf["x_rel_l2"].append(((xs[k + 1] - x1).norm() / x1.norm()).item())
-            # the increment is a sum of cancelling O(beta D / 2) terms: its error is measured on that scale
-            scale = 0.5 * sched.betas[t].item() * D
-            tf["inc_err_over_betaD2"].append((((lq[k + 1] - lq[k]) - (lq1 - lq[k])).abs().max() / scale).item())
+            # Ito increment of this step: error relative to the increment's own size (floored by its beta D / 2 term, the
+            # scale of the cancelling parts at large t; near t = 0 the <s, dx> ~ |eps|^2 term dominates)
+            inc_c, inc_o = lq[k + 1] - lq[k], lq1 - lq[k]
+            scale = inc_o.abs() + 0.5 * sched.betas[t].item() * D
+            tf["inc_rel"].append(((inc_c - inc_o).abs() / scale).max().item())
     rec = {"config": {"B": B, "R": R, "T": T, "models": 2, "noise": "explicit stack, torch.randn on cuda, seed 1234+R",
                       "oracle": "fp32 PyTorch on cuda:0, TF32 disabled"},
            "free_running": {"summary": _summary(free), "curves": _thin(free)},
@@ -148,7 +150,7 @@ def _run(S, name, B, R, T, tf_stride=1, sensitivity=False):
 
 
 # Tolerance table.  teacher-forced = the kernels' per-step error; free-running = whole trajectory.
-TF_BOUNDS = {"eps_rel_l2": 4e-3, "kappa_abs": 2e-6, "x_rel_l2": 2e-5, "inc_err_over_betaD2": 2e-3}
+TF_BOUNDS = {"eps_rel_l2": 4e-3, "kappa_abs": 2e-6, "x_rel_l2": 4e-5, "inc_rel": 1e-2}
 
 
 def _check(rec, free_kappa, free_logq, free_x):
@@ -164,7 +166,7 @@ def _check(rec, free_kappa, free_logq, free_x):
 def test_c2_full_config_trajectory(S):
     """BASELINE configs[1] in full: 128 x 128, batch 16, 100 steps, two models."""
     rec = _run(S, "c2_B16_R128_T100", 16, 128, 100, sensitivity=True)
-    _check(rec, free_kappa=5e-2, free_logq=5e-3, free_x=1e-2)
+    _check(rec, free_kappa=2e-2, free_logq=5e-3, free_x=2e-3)
     # the CUDA path stays inside the fp32 oracle's own sensitivity to a 2e-3 perturbation of eps-hat (x2 margin)
     sens = rec["oracle_self_sensitivity_eps_2e-3"]["summary"]
     assert rec["free_running"]["summary"]["kappa_abs"]["max"] <= 2 * sens["kappa_abs"]["max"] + 1e-3
@@ -174,11 +176,11 @@ def test_c3_trajectory_at_full_step_count(S):
     """BASELINE configs[2] at its real step count (256 x 256, 250 steps) on 4 of the 64 samples (per-sample path:
     test_bench_shape_tie_to_small_batch shows a sample's bits do not depend on the batch it runs in)."""
     rec = _run(S, "c3_B4_R256_T250", 4, 256, 250)
-    _check(rec, free_kappa=5e-2, free_logq=5e-3, free_x=1e-2)
+    _check(rec, free_kappa=2e-2, free_logq=5e-3, free_x=2e-3)
 
 
 def test_c4_shard_trajectory_1000_steps(S):
     """BASELINE configs[3]: 512 x 512, the full 1000-step schedule, one sample of a GPU's 4-sample shard; teacher-forced
     at every 10th step."""
     rec = _run(S, "c4_B1_R512_T1000", 1, 512, 1000, tf_stride=10)
-    _check(rec, free_kappa=5e-2, free_logq=5e-3, free_x=1e-2)
+    _check(rec, free_kappa=2e-2, free_logq=5e-3, free_x=2e-3)
