@@ -27,7 +27,22 @@ UNIT = "samples/s"
 
 
 def metric_name(args):
-    return f"superposed samples/sec at {args.res}^2 (2 UNets, {args.diffusion_steps} steps)"
+    ext = " [EXTENSION: attention-variant UNets, oracle = ours]" if getattr(args, "arch", "ref") == "attn" else ""
+    return f"superposed samples/sec at {args.res}^2 (2 UNets, {args.diffusion_steps} steps){ext}"
+
+
+# conv MACs per FULL-RESOLUTION pixel of one forward of the attention variant (levels at 1, 1/4, 1/16, 1/64, 1/256 of the
+# pixels; include/sdd_b200.h lists the blocks) and attention FLOPs per sample (4 S^2 d heads per block + projections)
+ATTN_MAC_PER_PIXEL = (576 + 36864) + (73728 + 147456) / 4 + 2 * 147456 / 16 + 2 * 147456 / 64 + 2 * 147456 / 256 \
+    + 2 * 147456 / 256 + 2 * 147456 / 64 + 2 * 147456 / 16 + (73728 + 36864) / 4 + (576 + 9)
+
+
+def attn_flops_per_sample(R):
+    tot = 0.0
+    for lvl, nblocks in ((3, 2), (4, 2)):  # attention after enc3 + dec0 at R/8, after enc4 + mid at R/16
+        S_ = (R >> lvl) ** 2
+        tot += nblocks * (4.0 * S_ * S_ * 64 * 2 + 2.0 * S_ * 128 * (384 + 128))
+    return tot
 
 
 CONV_MAC_PER_PIXEL = 664713          # all 10 convs of one UNet forward
@@ -179,8 +194,11 @@ def workload_config(args, world):
              (512, 1000, 32): "BASELINE configs[3]"}.get((args.res, args.diffusion_steps, args.batch), "custom shape")
     pb = per_gpu_batch(args, world)
     gb = pb * world
+    arch = ("reference UNet architecture" if getattr(args, "arch", "ref") == "ref" else
+            "EXTENSION: class-conditional multi-resolution UNets with attention at R/8 and R/16 -- no reference code, "
+            "oracle = oracle/unet_attn_oracle.py")
     return {"workload": f"TB+Pneumonia superposition {args.res}x{args.res}, global batch {gb} ({pb} per GPU), "
-                        f"{args.diffusion_steps}-step DDPM schedule ({which}, reference UNet architecture)",
+                        f"{args.diffusion_steps}-step DDPM schedule ({which}, {arch})",
             "per_gpu_batch": pb, "global_batch": gb, "resolution": args.res,
             "diffusion_steps": args.diffusion_steps, "models": 2, "parallelism": f"batch-shard x{world}",
             "l2": "working set per call >> L2 (no flush needed between calls)",
@@ -252,6 +270,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-roofline", action="store_true", help="skip the kernel-alone roofline legs (ncu launch lists)")
+    ap.add_argument("--arch", default="ref", choices=["ref", "attn"],
+                    help="ref: the reference UNet (the BASELINE metric); attn: the UNetAttn extension (separately labelled "
+                         "line; no reference code exists for it)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -259,6 +280,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
+        if args.arch != "ref":
+            if rank == 0:
+                print(json.dumps({"impl": "reference", "unavailable": "the reference has no attention / multi-resolution "
+                                  "UNet (src/models/unet.py:37-65): --arch attn is an extension with its own oracle"}))
+            return
         run_reference_arm(args, rank, world)
         return
 
@@ -280,7 +306,7 @@ def main():
     models = []
     for i in range(M):
         torch.manual_seed(i)  # random-init weights, PyTorch default init of the reference architecture
-        models.append(S.UNet().to(dev).eval())
+        models.append(S.UNet().to(dev).eval() if args.arch == "ref" else S.UNetAttn().to(dev).eval().set_label(i))
     ddpm = S.DDPM(T)
     shape = (B, 1, R, R)
 
@@ -302,11 +328,12 @@ def main():
     roof_clk = None
     if rank == 0 and not args.no_roofline:
         chunk = max(1, min(B, (1536 << 20) // (R * R * 128 * 2)))
-        conv_roofline(S, dev, R, chunk, iters=3)  # warm-up: module load, attributes, clocks
+        rc_in = rc_out = 128 if args.arch == "ref" else 64  # dominant tensor-core layer: 128->128 (ref) / 64->64 @R (attn)
+        conv_roofline(S, dev, R, chunk, iters=3, cin=rc_in, cout=rc_out)  # warm-up: module load, attributes, clocks
         update_roofline(S, dev, B, D, iters=50)
         rclk = ClockSampler(local, period=0.02)
         rclk.start()
-        conv_tf, conv_ms = conv_roofline(S, dev, R, chunk)
+        conv_tf, conv_ms = conv_roofline(S, dev, R, chunk, cin=rc_in, cout=rc_out)
         upd_gbs, upd_ms = update_roofline(S, dev, B, D, iters=400)
         upd_gbs_n, upd_ms_n = update_roofline(S, dev, B, D, iters=400, noise=True)
         roof_clk = rclk.stop()
@@ -402,7 +429,11 @@ def main():
         conv_traffic, upd_traffic = ncu_traffic()
         if not (B == 64 and R == 256 and chunk == 64):
             conv_traffic = upd_traffic = None  # the captures were taken at the default launch shapes only
-        step_flops = 2.0 * CONV_MAC_PER_PIXEL * D * M * T  # per sample
+        if args.arch == "ref":
+            step_flops = 2.0 * CONV_MAC_PER_PIXEL * D * M * T  # per sample
+        else:
+            step_flops = (2.0 * ATTN_MAC_PER_PIXEL * D + attn_flops_per_sample(R)) * M * T
+        rch = 128 if args.arch == "ref" else 64
         line = {"metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": args.scaling, "vs_baseline": None, "dtype": "f16", "data": "synthetic",
@@ -410,12 +441,14 @@ def main():
                 "gpu_launches": int(launches) * args.steps * world,
                 "graph_instantiations_per_sampler": graphs,
                 "whole_path_tensor_frac_of_sustained": value / world * step_flops / (tf_sust * 1e12),
-                "roofline": {"kernel": "conv3x3_tc4_kernel<128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)", "bound": "tensor",
+                "roofline": {"kernel": ("conv3x3_tc4_kernel<128,128> (GN+SiLU+conv 128->128, 66.6% of conv FLOPs)" if rch == 128
+                                        else "conv3x3_tc4_kernel<64,64> (GN+SiLU+conv 64->64 at full resolution)"),
+                             "bound": "tensor",
                              "achieved": conv_tf, "peak": tf_burst, "unit": "TFLOP/s", "frac": conv_tf / tf_burst,
-                             "traffic": conv_traffic, "algorithmic_bytes": 2.0 * chunk * R * R * 128 * 2,
+                             "traffic": conv_traffic if rch == 128 else None, "algorithmic_bytes": 2.0 * chunk * R * R * rch * 2,
                              "peak_source": f"{src} bf16 burst (fp16 runs at the same tcgen05 kind::f16 rate)",
                              "launch_ms": conv_ms, "clocks": roof_clk,
-                             "how": f"kernel alone at the sampler's launch shape ({chunk}x{R}x{R}x128), CUDA events "
+                             "how": f"kernel alone at the sampler's launch shape ({chunk}x{R}x{R}x{rch}), CUDA events "
                                     "around each launch on the launching stream, L2 flushed between launches, taken "
                                     "before the long timed region; clocks sampled during the roofline legs"},
                 "roofline_update": {"kernel": "superpose_update_kernel<2> (the whole update step: one launch)",
@@ -433,7 +466,7 @@ def main():
         if e2e:
             line["e2e"] = e2e
             line["e2e_philox"] = e2e_philox
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.arch == "ref":
             v, secs, kind = cpu_reference_run(R, T, M, 4, 8)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": kind,
                                     "sample": f"B=4, 8 of {T} diffusion steps after 1 warm-up step "

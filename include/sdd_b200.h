@@ -75,6 +75,28 @@ int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps
 int sdd_unet_forward_xstats(sdd_unet_t* u, const float* x, const float* xstats, const int64_t* t, float* eps_out,
                             int B, int H, int W, void* stream);
 
+/* ---- Extension (NO reference code -- the reference UNet, unet.py:37-65, is five full-resolution
+ * blocks with no attention, resampling, skips or class input; oracle = oracle/unet_attn_oracle.py):
+ * class-conditional multi-resolution UNet with self-attention at R/8 and R/16 (32^2 / 16^2 at R = 256), built from the
+ * reference's own ResidualBlock (unet.py:18-34) so that every conv runs on the kernels of the reference path:
+ *   enc0 RB(1,64)@R | pool | enc1 RB(64,128)@R/2 | pool | enc2 RB(128,128)@R/4 | pool | enc3 RB(128,128)+Attn@R/8 | pool |
+ *   enc4 RB(128,128)+Attn@R/16 | mid RB(128,128)+Attn@R/16 | up+skip(enc3) | dec0 RB(128,128)+Attn@R/8 | up+skip(enc2) |
+ *   dec1 RB(128,128)@R/4 | up+skip(enc1) | dec2 RB(128,64)@R/2 | up+skip(enc0) | out RB(64,1)@R
+ * pool = 2x2 average, up = nearest neighbour, skips are ADDED; Attn = x + proj(softmax(q k^T / 8) v), [q|k|v] =
+ * GroupNorm(4,128)(x) W_qkv^T + b, 2 heads of 64; the time embedding of every block is time_mlp(t) + class_emb[y].
+ * tensors (129, fp32, device): time_mlp.1.{weight,bias}, time_mlp.3.{weight,bias}, class_emb.weight [num_classes,256];
+ * the ten blocks in the order above, each as in the reference (block.0, block.2, block.3, block.5, time_emb: 10 tensors);
+ * the four attention blocks (after enc3, enc4, mid, dec0), each norm.{weight,bias}, qkv.{weight [384,128],bias},
+ * proj.{weight [128,128],bias}.  H % 256 == 0 and W % 128 == 0.  The handle is a sdd_unet_t: sdd_unet_forward* /
+ * sdd_sampler_* accept it like a reference UNet (sdd_sampler_create conditions on the handle's label). */
+#define SDD_UNET_ATTN_NUM_TENSORS 129
+int sdd_unet_attn_create(sdd_unet_t** out, const float* const* tensors, int num_tensors, int num_classes, void* stream);
+/* The class a sampler built on this handle (and a forward without per-sample labels) conditions on; default 0. */
+int sdd_unet_set_label(sdd_unet_t* u, int label);
+/* sdd_unet_forward_xstats with per-sample class labels y[B] (int64; NULL: the handle's label).  Variant handles only. */
+int sdd_unet_forward_labeled(sdd_unet_t* u, const float* x, const float* xstats, const int64_t* t, const int64_t* y,
+                             float* eps_out, int B, int H, int W, void* stream);
+
 /* ---- Fused superposition update (A7): ONE kernel launch and one HBM pass per step ----
  * kappa = softmax_m(temperature * logq[b,:] + bias);  eps_bar = sum_m kappa_m eps[m,b,:]
  * x_out = alpha^-1/2 (x_in - (1-alpha)/sqrt(1-alpha_bar) eps_bar) + sqrt(beta) z        (ddpm.py:42-44)
@@ -107,13 +129,13 @@ int sdd_superpose_update_and(const float* x_in, float* x_out, const float* eps, 
 /* ---- Self-attention core (north-star-only extension, NO reference code -- the reference
  * UNet, unet.py:37-65, has no attention; oracle = this repo's oracle.attention_core) ----
  * out[bh,q,:] = softmax_k(scale * <q[bh,q,:], k[bh,k,:]>) @ v[bh,k,:]   fused flash-style on tcgen05 / TMEM / TMA:
- * the S x S scores never leave the SM.  All tensors bf16, device, contiguous:
+ * the S x S scores never leave the SM.  All tensors fp16, device, contiguous:
  *   q, k, out: [BH][S][64];   vt: V TRANSPOSED, [BH][64][S].   head_dim == 64, S % 128 == 0 (32^2 = 1024, 16^2 = 256). */
 int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, int BH, int S, int head_dim,
                       float scale, void* stream);
 /* Self-attention BLOCK (same extension; oracle = oracle.attention_block):
  *   out = x + W_o attention(q, k, v) + b_o,   [q | k | v] = GroupNorm(4, 128)(x) W_qkv^T + b_qkv,   2 heads of 64
- * x, out: bf16 NHWC [B][S = H*W][128] (out may not alias x); gn_gamma / gn_beta fp32 [128]; w_qkv fp32 [384][128] (rows:
+ * x, out: fp16 NHWC [B][S = H*W][128] (out may not alias x); gn_gamma / gn_beta fp32 [128]; w_qkv fp32 [384][128] (rows:
  * q, k, v; within each, head h = rows 64h..64h+63), b_qkv [384]; w_out fp32 [128][128], b_out [128].  S % 128 == 0.
  * GroupNorm statistics kernel -> projection GEMM (mma.sync, GroupNorm affine fused on load, head-split / V-transposed
  * epilogue) -> sdd_attention_fwd -> projection GEMM (+ bias + residual).  Synchronises the stream (scratch is freed). */

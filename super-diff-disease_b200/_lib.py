@@ -34,6 +34,9 @@ SYMBOLS = {
     "sdd_unet_set_max_chunk": (_i, [_vp, _i]),
     "sdd_unet_forward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "sdd_unet_forward_xstats": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "sdd_unet_attn_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i, _i, _vp]),
+    "sdd_unet_set_label": (_i, [_vp, _i]),
+    "sdd_unet_forward_labeled": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "sdd_superpose_update_workspace": (_sz, [_i, _i, _i]),
     "sdd_superpose_update": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _f, _f, _f, _vp, _u64,
                                   _i64, _i, _vp, _sz, _vp]),

@@ -16,14 +16,14 @@ from super_diff_disease_b200 import _lib
 def attention_core(q, k, v, scale=None, *, v_is_transposed=False):
     """softmax(scale * q k^T) v per (batch, head).
 
-    q, k: bf16 CUDA [B, heads, S, 64];  v: bf16 [B, heads, S, 64], or [B, heads, 64, S] with v_is_transposed=True (the
+    q, k: fp16 CUDA [B, heads, S, 64];  v: fp16 [B, heads, S, 64], or [B, heads, 64, S] with v_is_transposed=True (the
     layout the kernel consumes; a producer that writes V^T directly saves the transpose).  S % 128 == 0.
-    Returns bf16 [B, heads, S, 64].
+    Returns fp16 [B, heads, S, 64].
     """
     for name, t in (("q", q), ("k", k), ("v", v)):
         _lib.require_cuda(t, name)
-        if t.dtype != torch.bfloat16 or t.dim() != 4:
-            raise _lib.SddError(f"{name} must be a 4-d bfloat16 tensor")
+        if t.dtype != torch.float16 or t.dim() != 4:
+            raise _lib.SddError(f"{name} must be a 4-d float16 tensor")
     B, Hh, S, D = q.shape
     if D != 64 or S % 128 != 0:
         raise _lib.SddError(f"head_dim must be 64 and S a multiple of 128, got S={S}, head_dim={D}")
@@ -45,13 +45,13 @@ def attention_core(q, k, v, scale=None, *, v_is_transposed=False):
 def attention_block(x, gn_weight, gn_bias, w_qkv, b_qkv, w_out, b_out, heads=2):
     """out = x + proj(attention(q, k, v)) with [q|k|v] = GroupNorm(4, 128)(x) W_qkv^T + b_qkv (2 heads of 64).
 
-    x: bf16 CUDA NHWC [B, H, W, 128] (H*W % 128 == 0: 32^2, 16^2 ...); gn_weight / gn_bias fp32 [128];
-    w_qkv fp32 [384, 128], b_qkv [384]; w_out fp32 [128, 128], b_out [128].  Returns bf16 [B, H, W, 128].
+    x: fp16 CUDA NHWC [B, H, W, 128] (H*W % 128 == 0: 32^2, 16^2 ...); gn_weight / gn_bias fp32 [128];
+    w_qkv fp32 [384, 128], b_qkv [384]; w_out fp32 [128, 128], b_out [128].  Returns fp16 [B, H, W, 128].
     Wraps sdd_attention_block_nhwc (GroupNorm statistics -> mma.sync projection with the GroupNorm affine fused on load
     and a head-split / V-transposed epilogue -> fused tcgen05 attention -> projection + bias + residual)."""
     _lib.require_cuda(x, "x")
-    if x.dtype != torch.bfloat16 or x.dim() != 4 or x.shape[-1] != 128:
-        raise _lib.SddError("x must be bfloat16 NHWC [B, H, W, 128]")
+    if x.dtype != torch.float16 or x.dim() != 4 or x.shape[-1] != 128:
+        raise _lib.SddError("x must be float16 NHWC [B, H, W, 128]")
     B, H, W, C = x.shape
     dev = x.device
     f32 = lambda t: torch.as_tensor(t, dtype=torch.float32, device=dev).contiguous()  # noqa: E731

@@ -6,7 +6,7 @@
 // sized for the feature maps the north star names (32^2 = 1024 and 16^2 = 256 tokens).  The S x S score matrix never
 // leaves the SM: per CTA one (batch*head, 128-query) tile; per 128-key block
 //   MMA1  S[128 x 128]  = Q K^T        tcgen05.mma kind::f16, A = Q (smem, loaded once), B = K block (smem), D in TMEM
-//   softmax warps: tcgen05.ld S -> running row max / sum (online softmax, exp2 with the scale folded in) -> P as bf16
+//   softmax warps: tcgen05.ld S -> running row max / sum (online softmax, exp2 with the scale folded in) -> P as fp16
 //         straight into the K-major SWIZZLE_128B layout the next MMA reads as its A operand (fence.proxy.async)
 //   MMA2  PV[128 x 64]  = P V          A = P (smem), B = V^T block (smem, keys contiguous), D in TMEM
 //   softmax warps: O = O * exp2(m_old - m_new) + PV   (O lives in registers: 64 fp32 per row)
@@ -35,7 +35,7 @@ constexpr int kAttnSmem = kAttnQBytes + kAttnStages * (kAttnKBytes + kAttnVBytes
 constexpr int kAttnTmemCols = 256;  // S: columns [0,128), PV: [128,192)
 
 struct AttnArgs {
-  __nv_bfloat16* out;  // [BH][S][64]
+  act_t* out;  // [BH][S][64]
   int S, BH;
   float scale_log2e;   // softmax scale * log2(e)
 };
@@ -99,8 +99,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else if (warp == 0) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(kAttnBM, kAttnBN);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(kAttnBM, kAttnD);
+      constexpr uint32_t idesc_s = SDD_ACT_IDESC(kAttnBM, kAttnBN);
+      constexpr uint32_t idesc_o = SDD_ACT_IDESC(kAttnBM, kAttnD);
       auto issue_s = [&](int j) {
         const int s = j % kAttnStages;
         mbar_wait(bar_kv_full(s), (uint32_t)((j / kAttnStages) & 1));
@@ -108,7 +108,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const uint64_t adesc = umma_desc_sw128(q_smem), bdesc = umma_desc_sw128(k_smem(s));
 #pragma unroll
         for (int k = 0; k < kAttnD / 16; ++k)
-          umma_bf16(s_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+          umma_f16(s_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
         umma_commit(bar_s);
       };
       mbar_wait(bar_q, 0);
@@ -121,7 +121,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int k = 0; k < kAttnBN / 16; ++k) {
           const uint64_t adesc = umma_desc_sw128(p_smem + (uint32_t)(k >> 2) * (kAttnBM * 128)) + (uint64_t)((k & 3) * 2);
           const uint64_t bdesc = umma_desc_sw128(v_smem(s) + (uint32_t)(k >> 2) * (kAttnD * 128)) + (uint64_t)((k & 3) * 2);
-          umma_bf16(pv_tmem, adesc, bdesc, idesc_o, k ? 1u : 0u);
+          umma_f16(pv_tmem, adesc, bdesc, idesc_o, k ? 1u : 0u);
         }
         umma_commit(bar_pv);
         umma_commit(bar_kv_free(s));
@@ -157,7 +157,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const float m_new = fmaxf(m_run, mx);
       const float alpha = ex2_approx((m_run - m_new) * a.scale_log2e);  // exp2(-inf) = 0 on the first block
       const float mb = m_new * a.scale_log2e;
-      // pass 2: p = exp2(s * c - m_new * c), row sum, bf16 P into the swizzled A-operand layout
+      // pass 2: p = exp2(s * c - m_new * c), row sum, fp16 P into the swizzled A-operand layout
       float lsum = 0.0f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -168,9 +168,11 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         for (int i = 0; i < 16; ++i) {
           const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), a.scale_log2e, -mb));
           const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), a.scale_log2e, -mb));
-          pk[i] = pack_bf16x2(p0, p1);
-          // the row sum uses the bf16-rounded values the tensor core will multiply (keeps rows normalised)
-          lsum += __uint_as_float(pk[i] << 16) + __uint_as_float(pk[i] & 0xffff0000u);
+          pk[i] = pack_act2(p0, p1);
+          // the row sum uses the rounded values the tensor core will multiply (keeps rows normalised)
+          float r0, r1;
+          unpack_act2(pk[i], r0, r1);
+          lsum += r0 + r1;
         }
         // keys c*32 .. c*32+31 = 64 bytes = pieces (c&1)*4 .. +3 of region c>>1
         const uint32_t reg_base = p_row + (uint32_t)(c >> 1) * (kAttnBM * 128);
@@ -198,14 +200,14 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       }
       tc_fence_before();
     }
-    // epilogue: out = O / l, bf16, this thread's 128-byte row
+    // epilogue: out = O / l, fp16, this thread's 128-byte row
     const float inv = 1.0f / l_run;
-    __nv_bfloat16* orow = a.out + ((size_t)bh * a.S + (size_t)qtile * kAttnBM + row) * kAttnD;
+    act_t* orow = a.out + ((size_t)bh * a.S + (size_t)qtile * kAttnBM + row) * kAttnD;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint32_t pk[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(o[c * 16 + 2 * i] * inv, o[c * 16 + 2 * i + 1] * inv);
+      for (int i = 0; i < 8; ++i) pk[i] = pack_act2(o[c * 16 + 2 * i] * inv, o[c * 16 + 2 * i + 1] * inv);
       st_global_v8(orow + c * 16, pk);
     }
   }

@@ -124,7 +124,7 @@ static int make_wt_map(CUtensorMap* m, const void* base, int Cout, int Cin) {
   return SDD_OK;
 }
 
-// bf16 [BH][rows][cols] (cols contiguous) -> box (64 cols = 128 B, box_rows, 1), 128-byte swizzle
+// fp16 [BH][rows][cols] (cols contiguous) -> box (64 cols = 128 B, box_rows, 1), 128-byte swizzle
 static int make_attn_map(CUtensorMap* m, const void* base, int BH, int rows, int cols, int box_rows) {
   EncodeTiledFn enc = get_encode();
   SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
@@ -132,7 +132,7 @@ static int make_attn_map(CUtensorMap* m, const void* base, int BH, int rows, int
   cuuint64_t strides[2] = {(cuuint64_t)cols * 2, (cuuint64_t)rows * cols * 2};
   cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, SDD_ACT_TMAP_TYPE, 3, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -234,6 +234,18 @@ constexpr int kBiasOff[5] = {0, 64, 192, 320, 384};
 constexpr int kBlkCin[5] = {1, 64, 128, 128, 64};
 constexpr int kBlkCout[5] = {64, 128, 128, 64, 1};
 constexpr int kTimeDim = 256;
+constexpr int kMaxBlocks = 10;
+// ---- extension N2 (no reference code; oracle/unet_attn_oracle.py): multi-resolution UNet with attention at R/8 and R/16
+// residual blocks: enc0 (1->64 @R), enc1 (64->128 @R/2), enc2..enc4 (128->128 @R/4, R/8, R/16), mid (128->128 @R/16),
+// dec0 (128->128 @R/8), dec1 (128->128 @R/4), dec2 (128->64 @R/2), out (64->1 @R)
+constexpr int kAnBlocks = 10;
+constexpr int kAnCin[kAnBlocks] = {1, 64, 128, 128, 128, 128, 128, 128, 128, 64};
+constexpr int kAnCout[kAnBlocks] = {64, 128, 128, 128, 128, 128, 128, 128, 64, 1};
+constexpr int kAnLevel[kAnBlocks] = {0, 1, 2, 3, 4, 4, 3, 2, 1, 0};
+constexpr int kAnBiasOff[kAnBlocks] = {0, 64, 192, 320, 448, 576, 704, 832, 960, 1024};
+constexpr int kAnBiasRow = 1028;  // 1025 values, padded to 16 B
+constexpr int kAnAttn = 4;        // attention blocks after enc3, enc4, mid, dec0
+constexpr int kAnTensors = 30;    // activation tensors of one forward (see attn_forward_impl)
 constexpr int kGnLayers = 9;  // GroupNorms fed by a conv output: downs.0 gn2 ... ups.1 gn2 (the first one reads x)
 
 struct Workspace {
@@ -258,20 +270,59 @@ struct Workspace {
 
 }  // namespace
 
+namespace {
+struct AttnParams { const float *gn_w, *gn_b, *w_qkv, *b_qkv, *w_out, *b_out; };
+struct AnTensor {  // one activation tensor of the attention variant's forward
+  act_t* p = nullptr;
+  int level = 0, C = 0;
+  long long* sums = nullptr;   // [cap_b][4][2] GroupNorm sums of this tensor
+  CUtensorMap tm;              // halo map (conv inputs)
+};
+struct AttnWorkspace {
+  int cap_b = 0, H = 0, W = 0;
+  int64_t generation = 0;
+  char* arena = nullptr;
+  AnTensor t[kAnTensors];
+  long long* sums_base = nullptr; size_t sums_bytes = 0;
+  act_t *q = nullptr, *k = nullptr, *vt = nullptr, *ao = nullptr;  // attention scratch at the R/8 level's size
+  float *e1 = nullptr, *gn_ab = nullptr, *xstats = nullptr, *partials = nullptr;
+  int* counters = nullptr;
+  void release() {
+    cudaFree(arena);
+    int64_t g = generation;
+    *this = AttnWorkspace();
+    generation = g;
+  }
+};
+}  // namespace
+
 struct sdd_unet {
-  float* params = nullptr;  // one arena holding all 54 fp32 tensors
+  int arch = 0;             // 0 = the reference UNet (unet.py:37-65); 1 = multi-resolution attention variant (extension N2)
+  int nblk = 5;             // residual blocks
+  int bias_row = kBiasRow;  // floats per (conv2 bias + time embedding) row
+  int bias_off[kMaxBlocks] = {0, 64, 192, 320, 384, 0, 0, 0, 0, 0};
+  float* params = nullptr;  // one arena holding all fp32 tensors of the state_dict
   act_t* wt = nullptr;
   float* freq = nullptr;    // [128]
   int max_chunk = 0;        // sdd_unet_set_max_chunk: 0 = automatic
   const float *time_w1, *time_b1, *time_w2, *time_b2;
-  BlockParams blk[5];
+  BlockParams blk[kMaxBlocks];
   Workspace ws;
+  // arch 1
+  const float* class_emb = nullptr;  // [num_classes][256], added to the time embedding
+  int num_classes = 0, label = 0;    // label: the class a sampler built on this handle conditions on
+  AttnParams attn[kAnAttn];
+  AttnWorkspace aws;
   // scratch for per-call time embeddings (forward with explicit t)
   int tscratch_n = 0;
   float *t_emb0 = nullptr, *t_h1 = nullptr, *t_emb = nullptr, *t_bias = nullptr;
 };
 
 namespace {
+
+int attn_ensure_workspace(sdd_unet* u, int B, int H, int W);
+int attn_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef tb, float* eps_out, int B, int H, int W,
+                      cudaStream_t st);
 
 int chunk_for(const sdd_unet* u, int B, int H, int W) {
   if (u->max_chunk > 0) return std::min(u->max_chunk, B);
@@ -284,6 +335,7 @@ int chunk_for(const sdd_unet* u, int B, int H, int W) {
 }
 
 int ensure_workspace(sdd_unet* u, int B, int H, int W) {
+  if (u->arch == 1) return attn_ensure_workspace(u, B, H, W);
   int need = chunk_for(u, B, H, W);
   Workspace& ws = u->ws;
   if (ws.cap_b >= need && ws.H == H && ws.W == W && (u->max_chunk == 0 || ws.cap_b == need)) return SDD_OK;
@@ -307,9 +359,18 @@ int ensure_workspace(sdd_unet* u, int B, int H, int W) {
   return SDD_OK;
 }
 
-// rows[n][385] = conv2.bias + time_emb(time_mlp(t_i)) for every block (unet.py:33, :58)
-int time_bias_rows(sdd_unet* u, const int64_t* t_dev, int n, float* emb0, float* h1, float* emb, float* rows,
-                   cudaStream_t st) {
+__global__ void add_class_emb_kernel(float* emb, const float* table, const int64_t* y, int y_const, int num_classes) {
+  const int i = blockIdx.x;
+  int c = y ? (int)y[i] : y_const;
+  c = c < 0 ? 0 : (c >= num_classes ? num_classes - 1 : c);
+  emb[(size_t)i * kTimeDim + threadIdx.x] += table[(size_t)c * kTimeDim + threadIdx.x];
+}
+
+int64_t ws_generation(const sdd_unet* u) { return u->arch == 1 ? u->aws.generation : u->ws.generation; }
+
+// rows[n][bias_row] = conv2.bias + time_emb(time_mlp(t_i) [+ class_emb(y_i)]) for every block (unet.py:33, :58)
+int time_bias_rows(sdd_unet* u, const int64_t* t_dev, const int64_t* y_dev, int n, float* emb0, float* h1, float* emb,
+                   float* rows, cudaStream_t st) {
   sinusoid_kernel<<<n, 128, 0, st>>>(t_dev, u->freq, emb0, n, kTimeDim / 2);
   SDD_LAUNCH_CHECK();
   auto lin = [&](const float* x, const float* Wm, const float* b, const float* extra, float* y, int K, int O,
@@ -322,9 +383,13 @@ int time_bias_rows(sdd_unet* u, const int64_t* t_dev, int n, float* emb0, float*
   SDD_LAUNCH_CHECK();
   lin(h1, u->time_w2, u->time_b2, nullptr, emb, 4 * kTimeDim, kTimeDim, kTimeDim, 0);
   SDD_LAUNCH_CHECK();
-  for (int i = 0; i < 5; ++i) {
-    lin(emb, u->blk[i].temb_w, u->blk[i].temb_b, u->blk[i].conv2_b, rows + kBiasOff[i], kTimeDim, kBlkCout[i],
-        kBiasRow, 0);
+  if (u->class_emb) {
+    add_class_emb_kernel<<<n, kTimeDim, 0, st>>>(emb, u->class_emb, y_dev, u->label, u->num_classes);
+    SDD_LAUNCH_CHECK();
+  }
+  for (int i = 0; i < u->nblk; ++i) {
+    lin(emb, u->blk[i].temb_w, u->blk[i].temb_b, u->blk[i].conv2_b, rows + u->bias_off[i], kTimeDim, u->blk[i].cout,
+        u->bias_row, 0);
     SDD_LAUNCH_CHECK();
   }
   return SDD_OK;
@@ -335,6 +400,7 @@ int time_bias_rows(sdd_unet* u, const int64_t* t_dev, int n, float* emb0, float*
 // tb: per-block bias rows; tb.base points at column 0 of the 385-wide row.
 int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef tb, float* eps_out, int B, int H,
                       int W, cudaStream_t st) {
+  if (u->arch == 1) return attn_forward_impl(u, x, xstats, tb, eps_out, B, H, W, st);
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
   Workspace& ws = u->ws;
   SDD_CHECK(ws.cap_b >= 1 && ws.H == H && ws.W == W, "workspace not prepared");
@@ -398,6 +464,222 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
   return SDD_OK;
 }
 
+
+// ------------------------------------------------------------------------------- attention block (graph-capturable)
+// out = x + W_o attention(q, k, v) + b_o with [q | k | v] = GroupNorm(4,128)(x) W_qkv^T + b_qkv: three launches, scratch
+// from the caller, no allocation and no synchronisation.  GroupNorm statistics of x: fixed-point sums from its producer
+// (in_sums) or (mean, rstd) floats; out_sums (optional) receives the output's GroupNorm sums for the next layer.
+int launch_attention_block(const act_t* x, const long long* in_sums, const float* in_meanrstd, const AttnParams& p,
+                           act_t* q, act_t* k, act_t* vt, act_t* ao, act_t* out, long long* out_sums, int B, int S,
+                           cudaStream_t st) {
+  SDD_CHECK(B > 0 && S >= kAttnBN && S % kAttnBN == 0, "attention needs S = H*W a positive multiple of 128");
+  SDD_CHECK(B * kAbHeads <= 65535, "batch * heads must be <= 65535");
+  SDD_TRY(ensure_func_attrs());
+  AttnBlockGemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.a = x; g.w = p.w_qkv; g.bias = p.b_qkv; g.in_sums = in_sums; g.meanrstd = in_meanrstd; g.gamma = p.gn_w; g.beta = p.gn_b;
+  g.q = q; g.k = k; g.vt = vt; g.B = B; g.S = S;
+  attn_block_gemm_kernel<0><<<dim3((unsigned)((size_t)B * S / kAbRows), 3 * kAbC / 64), 128, 0, st>>>(g);
+  SDD_LAUNCH_CHECK();
+  const int BH = B * kAbHeads;
+  CUtensorMap tmQ, tmK, tmVt;
+  SDD_TRY(make_attn_map(&tmQ, q, BH, S, kAttnD, kAttnBM));
+  SDD_TRY(make_attn_map(&tmK, k, BH, S, kAttnD, kAttnBN));
+  SDD_TRY(make_attn_map(&tmVt, vt, BH, kAttnD, S, kAttnD));
+  AttnArgs a;
+  a.out = ao; a.S = S; a.BH = BH;
+  a.scale_log2e = 0.125f * 1.4426950408889634f;
+  attention_fwd_kernel<<<dim3((unsigned)(S / kAttnBM), (unsigned)BH), kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmVt, a);
+  SDD_LAUNCH_CHECK();
+  memset(&g, 0, sizeof(g));
+  g.a = ao; g.w = p.w_out; g.bias = p.b_out; g.resid = x; g.out = out; g.out_sums = out_sums; g.B = B; g.S = S;
+  attn_block_gemm_kernel<1><<<dim3((unsigned)((size_t)B * S / kAbRows), kAbC / 64), 128, 0, st>>>(g);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+// ------------------------------------------------------------------------------- extension N2: attention-variant forward
+constexpr int kAnTLevel[kAnTensors] = {0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 3, 3, 3, 3, 2, 2, 2, 1, 1, 1, 0};
+constexpr int kAnTC[kAnTensors] = {64, 64, 64, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128,
+                                   128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 128, 64, 64, 64};
+
+int attn_ensure_workspace(sdd_unet* u, int B, int H, int W) {
+  SDD_CHECK(H % 256 == 0 && W % 128 == 0 && ((H >> 4) * (W >> 4)) % kAttnBN == 0,
+            "the attention variant needs H % 256 == 0 and W % 128 == 0 (five levels, attention at R/8 and R/16)");
+  // ~52 MB of activations per sample at 256^2: cap a chunk at ~4 GB
+  const size_t per_sample = (size_t)H * W * 800;
+  int need = u->max_chunk > 0 ? std::min(u->max_chunk, B) : (int)std::min<size_t>((size_t)B, std::max<size_t>(1, ((size_t)4 << 30) / per_sample));
+  AttnWorkspace& ws = u->aws;
+  if (ws.cap_b >= need && ws.H == H && ws.W == W && (u->max_chunk == 0 || ws.cap_b == need)) return SDD_OK;
+  ws.release();
+  auto al = [](size_t v) { return (v + 1023) & ~(size_t)1023; };
+  size_t off = 0, toff[kAnTensors];
+  for (int i = 0; i < kAnTensors; ++i) {
+    toff[i] = off;
+    off += al((size_t)need * (H >> kAnTLevel[i]) * (W >> kAnTLevel[i]) * kAnTC[i] * sizeof(act_t));
+  }
+  const size_t attn_elems = (size_t)need * (H >> 3) * (W >> 3) * kAbC;
+  const size_t o_attn = off; off += al(4 * attn_elems * sizeof(act_t));
+  const size_t o_e1 = off; off += al((size_t)need * H * W * sizeof(float));
+  const size_t o_sums = off; const size_t sums_bytes = (size_t)(kAnTensors + 1) * need * 8 * sizeof(long long); off += al(sums_bytes);
+  const size_t o_ab = off; off += al((size_t)2 * need * 128 * sizeof(float));
+  const size_t o_xs = off; off += al((size_t)need * 2 * sizeof(float));
+  const size_t o_part = off; off += al((size_t)need * kStatsBlocks * 2 * sizeof(float));
+  const size_t o_cnt = off; off += al((size_t)need * sizeof(int));
+  if (cudaMalloc(&ws.arena, off) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc(attention-variant workspace) failed"); return SDD_ENOMEM; }
+  ws.sums_base = reinterpret_cast<long long*>(ws.arena + o_sums); ws.sums_bytes = sums_bytes;
+  for (int i = 0; i < kAnTensors; ++i) {
+    AnTensor& t = ws.t[i];
+    t.p = reinterpret_cast<act_t*>(ws.arena + toff[i]); t.level = kAnTLevel[i]; t.C = kAnTC[i];
+    t.sums = ws.sums_base + (size_t)i * need * 8;
+    SDD_TRY(make_act_map(&t.tm, t.p, need, H >> t.level, W >> t.level, t.C));
+  }
+  act_t* ab = reinterpret_cast<act_t*>(ws.arena + o_attn);
+  ws.q = ab; ws.k = ab + attn_elems; ws.vt = ab + 2 * attn_elems; ws.ao = ab + 3 * attn_elems;
+  ws.e1 = reinterpret_cast<float*>(ws.arena + o_e1);
+  ws.gn_ab = reinterpret_cast<float*>(ws.arena + o_ab);
+  ws.xstats = reinterpret_cast<float*>(ws.arena + o_xs);
+  ws.partials = reinterpret_cast<float*>(ws.arena + o_part);
+  ws.counters = reinterpret_cast<int*>(ws.arena + o_cnt);
+  SDD_CUDA(cudaMemset(ws.counters, 0, (size_t)need * sizeof(int)));
+  ws.cap_b = need; ws.H = H; ws.W = W;
+  ++ws.generation;
+  return SDD_OK;
+}
+
+int launch_resample(bool up, const AnTensor& in, const AnTensor* skip, const AnTensor& out, bool want_sums, int nb, int H,
+                    int W, cudaStream_t st) {
+  const int Ho = H >> out.level, Wo = W >> out.level, C = out.C;
+  const int nvec = Ho * Wo * (C / 8);
+  const int blocks = std::max(1, std::min((nvec + 255) / 256, 8 * num_sms()));  // a function of the shape only (never of B)
+  if (up) resample_kernel<true><<<dim3(blocks, nb), 256, 0, st>>>(in.p, skip->p, out.p, want_sums ? out.sums : nullptr, Ho, Wo, C);
+  else resample_kernel<false><<<dim3(blocks, nb), 256, 0, st>>>(in.p, nullptr, out.p, want_sums ? out.sums : nullptr, Ho, Wo, C);
+  SDD_LAUNCH_CHECK();
+  return SDD_OK;
+}
+
+// One forward of the attention variant over B samples (chunked).  Same contract as unet_forward_impl.
+int attn_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef tb, float* eps_out, int B, int H, int W,
+                      cudaStream_t st) {
+  AttnWorkspace& ws = u->aws;
+  SDD_CHECK(ws.cap_b >= 1 && ws.H == H && ws.W == W, "workspace not prepared");
+  const int HW = H * W;
+  const dim3 egrid((W + kCinTW - 1) / kCinTW, (H + kCinTH - 1) / kCinTH, 1);
+  for (int b0 = 0; b0 < B; b0 += ws.cap_b) {
+    const int nb = std::min(ws.cap_b, B - b0);
+    const float* xc = x + (size_t)b0 * HW;
+    auto bias_const = [&](const float* p) { return BiasRef{p, nullptr, 0, 0}; };
+    auto bias_time = [&](int blk) {
+      return BiasRef{tb.base + u->bias_off[blk] + (int64_t)b0 * tb.batch_stride, tb.row_ptr, tb.row_stride, tb.batch_stride};
+    };
+    AnTensor* T = ws.t;
+    SDD_CUDA(cudaMemsetAsync(ws.sums_base, 0, ws.sums_bytes, st));
+    const float* xs = xstats ? xstats + (size_t)b0 * 2 : nullptr;
+    if (!xs) {
+      stats_x_kernel<<<dim3(kStatsBlocks, nb), 256, 0, st>>>(xc, HW, ws.partials, ws.counters, ws.xstats);
+      SDD_LAUNCH_CHECK();
+      xs = ws.xstats;
+    }
+    // conv of a residual block: input tensor `i` (GroupNorm+SiLU fused on the operand path) -> output tensor `o`
+    auto conv = [&](int i, int o, const CUtensorMap& tmw, BiasRef bias, const float* gw, const float* gb, bool want_sums) {
+      const AnTensor& ti = T[i];
+      return launch_conv(ti.tm, tmw, ti.p, T[o].p, bias, GnInput3{ti.sums, nullptr, gw, gb, ws.gn_ab},
+                         want_sums ? T[o].sums : nullptr, nb, H >> ti.level, W >> ti.level, ti.C, T[o].C, st);
+    };
+    auto rb = [&](int blk, int i, int mid, int o, bool want_sums) {  // blocks 1..8: two tensor-core convs
+      const BlockParams& p = u->blk[blk];
+      SDD_TRY(conv(i, mid, p.tm_w1h, bias_const(p.conv1_b), p.gn1_w, p.gn1_b, true));
+      return conv(mid, o, p.tm_w2h, bias_time(blk), p.gn2_w, p.gn2_b, want_sums);
+    };
+    auto attn = [&](int ai, int i, int o, bool want_sums) {
+      const int S = (H >> T[i].level) * (W >> T[i].level);
+      return launch_attention_block(T[i].p, T[i].sums, nullptr, u->attn[ai], ws.q, ws.k, ws.vt, ws.ao, T[o].p,
+                                    want_sums ? T[o].sums : nullptr, nb, S, st);
+    };
+    // ---- enc0 @R: 1 -> 64 (TF32 mma.sync), 64 -> 64
+    dim3 eg = egrid; eg.z = nb;
+    {
+      const BlockParams& p = u->blk[0];
+      const int in_tiles = (int)(eg.x * eg.y * eg.z);
+      conv_in_mma_kernel<<<std::min(in_tiles, 2 * num_sms()), 256, 0, st>>>(
+          xc, xs, p.gn1_w, p.gn1_b, p.conv1_w, bias_const(p.conv1_b), T[0].p, T[0].sums, H, W, (int)eg.x, (int)eg.y, in_tiles);
+      SDD_LAUNCH_CHECK();
+      SDD_TRY(conv(0, 1, p.tm_w2h, bias_time(0), p.gn2_w, p.gn2_b, false));
+    }
+    // ---- encoder: average-pool, residual block (+ attention at R/8 and R/16)
+    SDD_TRY(launch_resample(false, T[1], nullptr, T[2], true, nb, H, W, st));
+    SDD_TRY(rb(1, 2, 3, 4, false));
+    SDD_TRY(launch_resample(false, T[4], nullptr, T[5], true, nb, H, W, st));
+    SDD_TRY(rb(2, 5, 6, 7, false));
+    SDD_TRY(launch_resample(false, T[7], nullptr, T[8], true, nb, H, W, st));
+    SDD_TRY(rb(3, 8, 9, 10, true));
+    SDD_TRY(attn(0, 10, 11, false));
+    SDD_TRY(launch_resample(false, T[11], nullptr, T[12], true, nb, H, W, st));
+    SDD_TRY(rb(4, 12, 13, 14, true));
+    SDD_TRY(attn(1, 14, 15, true));
+    // ---- middle @R/16
+    SDD_TRY(rb(5, 15, 16, 17, true));
+    SDD_TRY(attn(2, 17, 18, false));
+    // ---- decoder: nearest-neighbour upsampling + additive skip, residual block (+ attention at R/8)
+    SDD_TRY(launch_resample(true, T[18], &T[11], T[19], true, nb, H, W, st));
+    SDD_TRY(rb(6, 19, 20, 21, true));
+    SDD_TRY(attn(3, 21, 22, false));
+    SDD_TRY(launch_resample(true, T[22], &T[7], T[23], true, nb, H, W, st));
+    SDD_TRY(rb(7, 23, 24, 25, false));
+    SDD_TRY(launch_resample(true, T[25], &T[4], T[26], true, nb, H, W, st));
+    SDD_TRY(rb(8, 26, 27, 28, false));
+    SDD_TRY(launch_resample(true, T[28], &T[1], T[29], true, nb, H, W, st));
+    // ---- out @R: 64 -> 1 (fp16 mma.sync), 1 -> 1
+    {
+      const BlockParams& p = u->blk[9];
+      long long* e1_sums = ws.sums_base + (size_t)kAnTensors * ws.cap_b * 8;
+      const int o1_tiles = (int)(eg.x * eg.y * eg.z);
+      conv_out1_mma_kernel<2><<<std::min(o1_tiles, 2 * num_sms()), 256, 0, st>>>(
+          T[29].p, T[29].sums, p.gn1_w, p.gn1_b, p.conv1_w, p.conv1_b, ws.e1, e1_sums, H, W, (int)eg.x, (int)eg.y, o1_tiles);
+      SDD_LAUNCH_CHECK();
+      conv_out2_kernel<<<eg, 256, 0, st>>>(ws.e1, e1_sums, p.gn2_w, p.gn2_b, p.conv2_w, bias_time(9),
+                                           eps_out + (size_t)b0 * HW, H, W);
+      SDD_LAUNCH_CHECK();
+    }
+  }
+  return SDD_OK;
+}
+
+
+// fp16 kernel-layout copies + tensor maps of every tensor-core conv's weights, the sinusoid frequency table; syncs.
+int build_conv_weights(sdd_unet* u, cudaStream_t st) {
+  size_t wt_elems = 0;
+  for (int i = 0; i < u->nblk; ++i) {
+    const BlockParams& b = u->blk[i];
+    if (b.cin >= 64 && b.cout >= 64) wt_elems += (size_t)9 * b.cin * b.cout;
+    if (b.cout >= 64) wt_elems += (size_t)9 * b.cout * b.cout;
+  }
+  if (cudaMalloc(&u->wt, wt_elems * sizeof(act_t)) != cudaSuccess) { set_error("cudaMalloc(wt) failed"); return SDD_ENOMEM; }
+  act_t* wp = u->wt;
+  for (int i = 0; i < u->nblk; ++i) {
+    BlockParams& b = u->blk[i];
+    auto conv = [&](const float* w, int cout, int cin, act_t** dst, CUtensorMap* tmh) -> int {
+      int total_w = 9 * cout * cin;
+      conv_weight_to_act_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wp, cout, cin);
+      SDD_LAUNCH_CHECK();
+      *dst = wp;
+      SDD_TRY(make_wt_map(tmh, wp, cout, cin));
+      wp += total_w;
+      return SDD_OK;
+    };
+    if (b.cin >= 64 && b.cout >= 64) SDD_TRY(conv(b.conv1_w, b.cout, b.cin, &b.conv1_wt, &b.tm_w1h));
+    if (b.cout >= 64) SDD_TRY(conv(b.conv2_w, b.cout, b.cout, &b.conv2_wt, &b.tm_w2h));
+  }
+  // sinusoid frequencies exactly as unet.py:14 evaluates them in fp32
+  float hf[kTimeDim / 2];
+  const float step = -(std::log(10000.0f) / (float)(kTimeDim / 2 - 1));
+  for (int k = 0; k < kTimeDim / 2; ++k) hf[k] = std::exp((float)k * step);
+  if (cudaMalloc(&u->freq, sizeof(hf)) != cudaSuccess) { set_error("cudaMalloc(freq) failed"); return SDD_ENOMEM; }
+  SDD_CUDA(cudaMemcpyAsync(u->freq, hf, sizeof(hf), cudaMemcpyHostToDevice, st));
+  SDD_CUDA(cudaStreamSynchronize(st));
+  return SDD_OK;
+}
+
 }  // namespace
 
 // =============================================================================== C ABI
@@ -433,7 +715,6 @@ int sdd_unet_create(sdd_unet_t** out, const float* const* tensors, int num_tenso
   }
   const float* P = u->params;
   u->time_w1 = P + off[0]; u->time_b1 = P + off[1]; u->time_w2 = P + off[2]; u->time_b2 = P + off[3];
-  size_t wt_elems = 0;
   for (int i = 0; i < 5; ++i) {
     BlockParams& b = u->blk[i];
     const size_t* o = &off[4 + 10 * i];
@@ -442,39 +723,73 @@ int sdd_unet_create(sdd_unet_t** out, const float* const* tensors, int num_tenso
     b.gn2_w = P + o[4]; b.gn2_b = P + o[5]; b.conv2_w = P + o[6]; b.conv2_b = P + o[7];
     b.temb_w = P + o[8]; b.temb_b = P + o[9];
     b.conv1_wt = b.conv2_wt = nullptr;
-    if (b.cin >= 64 && b.cout >= 64) wt_elems += (size_t)9 * b.cin * b.cout;
-    if (b.cout >= 64) wt_elems += (size_t)9 * b.cout * b.cout;
   }
-  if (cudaMalloc(&u->wt, wt_elems * sizeof(act_t)) != cudaSuccess) { set_error("cudaMalloc(wt) failed"); return fail(SDD_ENOMEM); }
-  act_t* wp = u->wt;
-  for (int i = 0; i < 5; ++i) {
-    BlockParams& b = u->blk[i];
-    auto conv = [&](const float* w, int cout, int cin, act_t** dst, CUtensorMap* tmh) -> int {
-      int total_w = 9 * cout * cin;
-      conv_weight_to_act_kernel<<<(total_w + 255) / 256, 256, 0, st>>>(w, wp, cout, cin);
-      SDD_LAUNCH_CHECK();
-      *dst = wp;
-      SDD_TRY(make_wt_map(tmh, wp, cout, cin));
-      wp += total_w;
-      return SDD_OK;
-    };
-    if (b.cin >= 64 && b.cout >= 64) { int r = conv(b.conv1_w, b.cout, b.cin, &b.conv1_wt, &b.tm_w1h); if (r) return fail(r); }
-    if (b.cout >= 64) { int r = conv(b.conv2_w, b.cout, b.cout, &b.conv2_wt, &b.tm_w2h); if (r) return fail(r); }
-  }
-  // sinusoid frequencies exactly as unet.py:14 evaluates them in fp32
-  float hf[kTimeDim / 2];
-  const float step = -(std::log(10000.0f) / (float)(kTimeDim / 2 - 1));
-  for (int k = 0; k < kTimeDim / 2; ++k) hf[k] = std::exp((float)k * step);
-  if (cudaMalloc(&u->freq, sizeof(hf)) != cudaSuccess) { set_error("cudaMalloc(freq) failed"); return fail(SDD_ENOMEM); }
-  if (cudaMemcpyAsync(u->freq, hf, sizeof(hf), cudaMemcpyHostToDevice, st) != cudaSuccess) { set_error("freq upload failed"); return fail(SDD_ECUDA); }
-  if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("sync after unet_create failed"); return fail(SDD_ECUDA); }
+  int rc = build_conv_weights(u, st);
+  if (rc != SDD_OK) return fail(rc);
   *out = u;
+  return SDD_OK;
+}
+
+int sdd_unet_attn_create(sdd_unet_t** out, const float* const* tensors, int num_tensors, int num_classes, void* stream) {
+  SDD_CHECK(out && tensors, "null argument");
+  SDD_CHECK(num_classes >= 1, "num_classes must be >= 1");
+  SDD_CHECK(num_tensors == SDD_UNET_ATTN_NUM_TENSORS, "expected the 129 tensors of the UNetAttn state_dict");
+  SDD_TRY(device_check());
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<size_t> n;
+  n.insert(n.end(), {(size_t)1024 * 256, 1024, (size_t)256 * 1024, 256, (size_t)num_classes * 256});
+  for (int i = 0; i < kAnBlocks; ++i) {
+    size_t ci = kAnCin[i], co = kAnCout[i];
+    n.insert(n.end(), {ci, ci, co * ci * 9, co, co, co, co * co * 9, co, co * 256, co});
+  }
+  for (int i = 0; i < kAnAttn; ++i) n.insert(n.end(), {128, 128, (size_t)384 * 128, 384, (size_t)128 * 128, 128});
+  size_t total = 0;
+  std::vector<size_t> off(n.size());
+  for (size_t i = 0; i < n.size(); ++i) { off[i] = total; total += (n[i] + 3) & ~(size_t)3; }
+  sdd_unet* u = new sdd_unet();
+  u->arch = 1; u->nblk = kAnBlocks; u->bias_row = kAnBiasRow; u->num_classes = num_classes;
+  for (int i = 0; i < kAnBlocks; ++i) u->bias_off[i] = kAnBiasOff[i];
+  auto fail = [&](int code) { sdd_unet_destroy(u); return code; };
+  if (cudaMalloc(&u->params, total * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc(params) failed"); return fail(SDD_ENOMEM); }
+  for (size_t i = 0; i < n.size(); ++i) {
+    if (cudaMemcpyAsync(u->params + off[i], tensors[i], n[i] * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess) {
+      set_error("copying state-dict tensor " + std::to_string(i) + " failed (device pointers expected)");
+      return fail(SDD_ECUDA);
+    }
+  }
+  const float* P = u->params;
+  u->time_w1 = P + off[0]; u->time_b1 = P + off[1]; u->time_w2 = P + off[2]; u->time_b2 = P + off[3];
+  u->class_emb = P + off[4];
+  for (int i = 0; i < kAnBlocks; ++i) {
+    BlockParams& b = u->blk[i];
+    const size_t* o = &off[5 + 10 * i];
+    b.cin = kAnCin[i]; b.cout = kAnCout[i];
+    b.gn1_w = P + o[0]; b.gn1_b = P + o[1]; b.conv1_w = P + o[2]; b.conv1_b = P + o[3];
+    b.gn2_w = P + o[4]; b.gn2_b = P + o[5]; b.conv2_w = P + o[6]; b.conv2_b = P + o[7];
+    b.temb_w = P + o[8]; b.temb_b = P + o[9];
+    b.conv1_wt = b.conv2_wt = nullptr;
+  }
+  for (int i = 0; i < kAnAttn; ++i) {
+    const size_t* o = &off[5 + 10 * kAnBlocks + 6 * i];
+    u->attn[i] = AttnParams{P + o[0], P + o[1], P + o[2], P + o[3], P + o[4], P + o[5]};
+  }
+  int rc = build_conv_weights(u, st);
+  if (rc != SDD_OK) return fail(rc);
+  *out = u;
+  return SDD_OK;
+}
+
+int sdd_unet_set_label(sdd_unet_t* u, int label) {
+  SDD_CHECK(u && u->arch == 1, "class labels need the class-conditional variant (sdd_unet_attn_create)");
+  SDD_CHECK(label >= 0 && label < u->num_classes, "label out of range");
+  u->label = label;
   return SDD_OK;
 }
 
 int sdd_unet_destroy(sdd_unet_t* u) {
   if (!u) return SDD_OK;
   u->ws.release();
+  u->aws.release();
   cudaFree(u->params); cudaFree(u->wt); cudaFree(u->freq);
   cudaFree(u->t_emb0); cudaFree(u->t_h1); cudaFree(u->t_emb); cudaFree(u->t_bias);
   delete u;
@@ -494,7 +809,13 @@ int sdd_unet_forward(sdd_unet_t* u, const float* x, const int64_t* t, float* eps
 
 int sdd_unet_forward_xstats(sdd_unet_t* u, const float* x, const float* xstats, const int64_t* t, float* eps_out, int B,
                             int H, int W, void* stream) {
+  return sdd_unet_forward_labeled(u, x, xstats, t, nullptr, eps_out, B, H, W, stream);
+}
+
+int sdd_unet_forward_labeled(sdd_unet_t* u, const float* x, const float* xstats, const int64_t* t, const int64_t* y,
+                             float* eps_out, int B, int H, int W, void* stream) {
   SDD_CHECK(u && x && t && eps_out, "null argument");
+  SDD_CHECK(!y || u->arch == 1, "class labels need the class-conditional variant (sdd_unet_attn_create)");
   SDD_CHECK(B >= 1 && H >= 16 && W >= 8, "bad shape");
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
   cudaStream_t st = (cudaStream_t)stream;
@@ -505,11 +826,11 @@ int sdd_unet_forward_xstats(sdd_unet_t* u, const float* x, const float* xstats, 
     SDD_CUDA(cudaMalloc(&u->t_emb0, (size_t)B * kTimeDim * sizeof(float)));
     SDD_CUDA(cudaMalloc(&u->t_h1, (size_t)B * 4 * kTimeDim * sizeof(float)));
     SDD_CUDA(cudaMalloc(&u->t_emb, (size_t)B * kTimeDim * sizeof(float)));
-    SDD_CUDA(cudaMalloc(&u->t_bias, (size_t)B * kBiasRow * sizeof(float)));
+    SDD_CUDA(cudaMalloc(&u->t_bias, (size_t)B * u->bias_row * sizeof(float)));
     u->tscratch_n = B;
   }
-  SDD_TRY(time_bias_rows(u, t, B, u->t_emb0, u->t_h1, u->t_emb, u->t_bias, st));
-  BiasRef tb{u->t_bias, nullptr, 0, kBiasRow};
+  SDD_TRY(time_bias_rows(u, t, y, B, u->t_emb0, u->t_h1, u->t_emb, u->t_bias, st));
+  BiasRef tb{u->t_bias, nullptr, 0, u->bias_row};
   return unet_forward_impl(u, x, xstats, tb, eps_out, B, H, W, st);
 }
 
@@ -627,7 +948,7 @@ int sdd_attention_fwd(const void* q, const void* k, const void* vt, void* out, i
   SDD_TRY(make_attn_map(&tmVt, vt, BH, kAttnD, S, kAttnD));
   SDD_TRY(ensure_func_attrs());
   AttnArgs a;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out); a.S = S; a.BH = BH;
+  a.out = reinterpret_cast<act_t*>(out); a.S = S; a.BH = BH;
   a.scale_log2e = scale * 1.4426950408889634f;
   attention_fwd_kernel<<<dim3((unsigned)(S / kAttnBM), (unsigned)BH), kAttnThreads, kAttnSmem, (cudaStream_t)stream>>>(
       tmQ, tmK, tmVt, a);
@@ -643,31 +964,17 @@ int sdd_attention_block_nhwc(const void* x, const float* gn_gamma, const float* 
   SDD_CHECK(B > 0 && S >= kAttnBN && S % kAttnBN == 0, "S must be a positive multiple of 128");
   SDD_TRY(device_check());
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t per = (size_t)B * S * kAbC;  // elements of one [B, S, 128] bf16 tensor
-  __nv_bfloat16* buf = nullptr; float* mr = nullptr;
-  if (cudaMalloc(&buf, 4 * per * sizeof(__nv_bfloat16)) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 8 * sizeof(float)) != cudaSuccess) {
+  // operator form: scratch is allocated and freed here (the UNet variant passes its own arena and never synchronises)
+  const size_t per = (size_t)B * S * kAbC;  // elements of one [B, S, 128] fp16 tensor
+  act_t* buf = nullptr; float* mr = nullptr;
+  if (cudaMalloc(&buf, 4 * per * sizeof(act_t)) != cudaSuccess || cudaMalloc(&mr, (size_t)B * 8 * sizeof(float)) != cudaSuccess) {
     cudaFree(buf); cudaFree(mr);
     set_error("cudaMalloc failed"); return SDD_ENOMEM;
   }
-  __nv_bfloat16 *q = buf, *k = buf + per, *vt = buf + 2 * per, *ao = buf + 3 * per;
-  int rc = SDD_OK;
-  gn_stats_nhwc_kernel<<<B * 4, 256, 0, st>>>((const __nv_bfloat16*)x, mr, S, kAbC);
+  gn_stats_nhwc_kernel<<<B * 4, 256, 0, st>>>((const act_t*)x, mr, S, kAbC);
   ++g_launches;
-  AttnBlockGemmArgs g;
-  memset(&g, 0, sizeof(g));
-  g.a = (const __nv_bfloat16*)x; g.w = w_qkv; g.bias = b_qkv; g.meanrstd = mr; g.gamma = gn_gamma; g.beta = gn_beta;
-  g.q = q; g.k = k; g.vt = vt; g.B = B; g.S = S;
-  attn_block_gemm_kernel<0><<<dim3((unsigned)((size_t)B * S / kAbRows), 3 * kAbC / 64), 128, 0, st>>>(g);
-  ++g_launches;
-  if (cudaGetLastError() != cudaSuccess) { set_error("attention block: qkv launch failed"); rc = SDD_ECUDA; }
-  if (rc == SDD_OK) rc = sdd_attention_fwd(q, k, vt, ao, B * kAbHeads, S, kAttnD, 0.125f, stream);
-  if (rc == SDD_OK) {
-    memset(&g, 0, sizeof(g));
-    g.a = ao; g.w = w_out; g.bias = b_out; g.resid = (const __nv_bfloat16*)x; g.out = (__nv_bfloat16*)out; g.B = B; g.S = S;
-    attn_block_gemm_kernel<1><<<dim3((unsigned)((size_t)B * S / kAbRows), kAbC / 64), 128, 0, st>>>(g);
-    ++g_launches;
-    if (cudaGetLastError() != cudaSuccess) { set_error("attention block: proj launch failed"); rc = SDD_ECUDA; }
-  }
+  int rc = launch_attention_block((const act_t*)x, nullptr, mr, AttnParams{gn_gamma, gn_beta, w_qkv, b_qkv, w_out, b_out},
+                                  buf, buf + per, buf + 2 * per, buf + 3 * per, (act_t*)out, nullptr, B, S, st);
   cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(buf); cudaFree(mr);
   if (rc != SDD_OK) return rc;
@@ -758,7 +1065,7 @@ namespace {
 
 int enqueue_step(sdd_sampler* s, int mode, cudaStream_t st) {
   for (int m = 0; m < s->M; ++m) {
-    BiasRef tb{s->tables[m], s->step, kBiasRow, 0};
+    BiasRef tb{s->tables[m], s->step, s->models[m]->bias_row, 0};
     SDD_TRY(unet_forward_impl(s->models[m], s->x, s->xstats, tb, s->eps + (size_t)m * s->B * s->D, s->B, s->H, s->W,
                               st));
   }
@@ -828,9 +1135,9 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
   for (int m = 0; m < M && rc == SDD_OK; ++m) {
     s->models[m] = models[m];
     if (!models[m]) { set_error("null model"); rc = SDD_EINVAL; break; }
-    if (cudaMalloc(&s->tables[m], (size_t)T * kBiasRow * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc(table) failed"); rc = SDD_ENOMEM; break; }
+    if (cudaMalloc(&s->tables[m], (size_t)T * models[m]->bias_row * sizeof(float)) != cudaSuccess) { set_error("cudaMalloc(table) failed"); rc = SDD_ENOMEM; break; }
     // every timestep's (conv2 bias + time embedding) rows, once: t is batch-uniform in sampling (ddpm.py:35)
-    rc = time_bias_rows(models[m], t_dev, T, emb0, h1, emb, s->tables[m], st);
+    rc = time_bias_rows(models[m], t_dev, nullptr, T, emb0, h1, emb, s->tables[m], st);
     if (rc == SDD_OK) rc = ensure_workspace(models[m], B, H, W);
   }
   cudaError_t se = cudaStreamSynchronize(st);
@@ -885,7 +1192,7 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
     // The graph holds only pointers to sampler-owned device state (x, eps, logq, step counter, RunParams block, bias
     // tables): seed, shard offset, noise stack, temperature, bias and trajectory buffers change WITHOUT a re-capture.
     bool stale = !s->exec || s->captured_mode != args->mode;
-    for (int m = 0; m < s->M; ++m) stale = stale || s->captured_gen[m] != s->models[m]->ws.generation;
+    for (int m = 0; m < s->M; ++m) stale = stale || s->captured_gen[m] != ws_generation(s->models[m]);
     if (stale) {
       if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
       cudaGraph_t graph = nullptr;
@@ -901,7 +1208,7 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
       SDD_CUDA(ce);
       s->captured_mode = args->mode;
       ++s->graph_instantiations;
-      for (int m = 0; m < s->M; ++m) s->captured_gen[m] = s->models[m]->ws.generation;
+      for (int m = 0; m < s->M; ++m) s->captured_gen[m] = ws_generation(s->models[m]);
     }
     for (int k = 1; k < s->T; ++k) SDD_CUDA(cudaGraphLaunch(s->exec, st));
   } else {

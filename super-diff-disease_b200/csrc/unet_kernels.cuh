@@ -451,9 +451,9 @@ __global__ void __launch_bounds__(256) conv_out2_kernel(const float* __restrict_
   }
 }
 
-// ------------------------------------------------------------------ GroupNorm(4,C) statistics of a bf16 NHWC tensor
-// (attention block only: the conv layers get their statistics from the producer's epilogue)
-__global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const __nv_bfloat16* __restrict__ act, float* meanrstd,
+// ------------------------------------------------------------------ GroupNorm(4,C) statistics of an fp16 NHWC tensor
+// (attention-block operator only: inside the networks the statistics come from the producer's epilogue)
+__global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const act_t* __restrict__ act, float* meanrstd,
                                                             int HW, int C) {
   const int b = blockIdx.x / 4, g = blockIdx.x % 4;
   const int cpg = C / 4;
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(256) gn_stats_nhwc_kernel(const __nv_bfloat16*
   for (size_t i = threadIdx.x; i < (size_t)HW * cpg; i += 256) {
     size_t p = i / cpg;
     int c = g * cpg + (int)(i % cpg);
-    float v = __bfloat162float(act[((size_t)b * HW + p) * C + c]);
+    float v = (float)act[((size_t)b * HW + p) * C + c];
     s += v;
     ss += (double)v * v;
   }

@@ -49,7 +49,7 @@ class _Sampler:
 
 def _get_sampler(models, ddpm, B, H, W, device):
     key = (tuple(id(m) for m in models), tuple(m._param_key() for m in models), ddpm.T,
-           ddpm.betas.numpy().tobytes(), B, H, W, str(device))
+           ddpm.betas.numpy().tobytes(), B, H, W, tuple(getattr(m, "label", None) for m in models), str(device))
     s = _SAMPLERS.get(key)
     if s is None:
         stale = [k for k in _SAMPLERS if k[0] == key[0] and k[-1] == key[-1]]
@@ -84,7 +84,8 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
                       return_x_trajectory=False):
     """Sample from the superposition of ``models`` (one model == DDPM.sample).
 
-    models: sequence of super_diff_disease_b200.UNet on ``device``; ddpm: DDPM (schedule);
+    models: sequence of super_diff_disease_b200.UNet (or the UNetAttn extension, each conditioning on the class set
+    with ``set_label``) on ``device``; ddpm: DDPM (schedule);
     image_shape: (B, 1, H, W), H % 16 == 0, W % 8 == 0.
     noise: fp32 [T, B, 1, H, W] stack (parity mode), or seed: int for in-kernel Philox keyed by
     (seed, sample_offset + b, draw, element) -- shard-invariant.  Exactly one of the two.

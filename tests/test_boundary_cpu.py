@@ -52,11 +52,11 @@ def test_no_cpu_fallback():
         S.DDPM(4).q_sample(x0, torch.zeros(2, dtype=torch.long), torch.zeros_like(x0))
     with pytest.raises(S.SddError):
         S.DDPM(4).p_losses(m, x0, torch.zeros(2, dtype=torch.long))
-    q = torch.zeros(1, 1, 128, 64, dtype=torch.bfloat16)
+    q = torch.zeros(1, 1, 128, 64, dtype=torch.float16)
     with pytest.raises(S.SddError):
         S.attention_core(q, q, q)
     with pytest.raises(S.SddError):
-        S.attention_block(torch.zeros(1, 16, 16, 128, dtype=torch.bfloat16), torch.ones(128), torch.zeros(128),
+        S.attention_block(torch.zeros(1, 16, 16, 128, dtype=torch.float16), torch.ones(128), torch.zeros(128),
                           torch.zeros(384, 128), torch.zeros(384), torch.zeros(128, 128), torch.zeros(128))
     # the C ABI itself refuses without an sm_100 device (every compute entry point starts with the device check)
     L = S.lib()

@@ -434,13 +434,13 @@ def test_n4_q_sample_and_p_losses_match_reference_golden(S, dev, golden_dir, nam
 @pytest.mark.parametrize("spread", [1.0, 6.0])
 def test_attention_core_matches_oracle(S, dev, B, heads, S_, spread):
     """Extension (oracle = ours, no reference code): fused flash-style tcgen05 attention vs
-    fp32 softmax(q k^T / sqrt(d)) v of the same bf16 operands.  P is rounded to bf16 before the second GEMM and the
-    output is bf16: max-abs <= 2e-2 * max|ref|, rel-L2 <= 1e-2.  spread = 6 makes the softmax peaky (online-softmax
+    fp32 softmax(q k^T / sqrt(d)) v of the same fp16 operands.  P is rounded to fp16 before the second GEMM and the
+    output is fp16: max-abs <= 4e-3 * max|ref|, rel-L2 <= 2e-3.  spread = 6 makes the softmax peaky (online-softmax
     rescaling across key blocks is exercised: the row maximum moves between blocks)."""
     g = torch.Generator().manual_seed(B * 1000 + S_ + int(spread))
-    q = (torch.randn(B, heads, S_, 64, generator=g) * spread).to(torch.bfloat16)
-    k = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16)
-    v = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16)
+    q = (torch.randn(B, heads, S_, 64, generator=g) * spread).to(torch.float16)
+    k = torch.randn(B, heads, S_, 64, generator=g).to(torch.float16)
+    v = torch.randn(B, heads, S_, 64, generator=g).to(torch.float16)
     ref = O.attention_core(q, k, v)
     out = S.attention_core(q.to(dev), k.to(dev), v.to(dev)).float().cpu()
     out_t = S.attention_core(q.to(dev), k.to(dev), v.to(dev).transpose(2, 3).contiguous(), v_is_transposed=True).float().cpu()
@@ -448,20 +448,20 @@ def test_attention_core_matches_oracle(S, dev, B, heads, S_, spread):
     rel = _rel(out, ref)
     mx = ((out - ref).abs().max() / ref.abs().max()).item()
     _report(test="attention", B=B, heads=heads, S=S_, spread=spread, rel_l2=rel, max_abs_rel=mx)
-    assert rel <= 1e-2 and mx <= 2e-2
+    assert rel <= 2e-3 and mx <= 4e-3
 
 
 @pytest.mark.parametrize("B,R", [(2, 16), (3, 32)])
 def test_attention_block_matches_oracle(S, dev, B, R):
     """Extension (oracle = ours): GroupNorm(4,128) -> qkv projection -> fused attention -> projection +
-    residual at the 16^2 / 32^2 feature maps, vs the fp32 oracle on the same bf16 input and bf16-rounded weights.
-    Intermediate q, k, v, P and the attention output are rounded to bf16 inside the kernels: rel-L2 <= 1.5e-2 of the
-    block output, max-abs <= 4e-2 of max|ref|; the residual path (zero projection weights) is exact."""
+    residual at the 16^2 / 32^2 feature maps, vs the fp32 oracle on the same fp16 input and fp16-rounded weights.
+    Intermediate q, k, v, P and the attention output are rounded to fp16 inside the kernels: rel-L2 <= 2e-3 of the
+    block output, max-abs <= 5e-3 of max|ref|; the residual path (zero projection weights) is exact."""
     g = torch.Generator().manual_seed(B * 10 + R)
-    x = torch.randn(B, R, R, 128, generator=g).to(torch.bfloat16)
+    x = torch.randn(B, R, R, 128, generator=g).to(torch.float16)
     gw = 1 + 0.1 * torch.randn(128, generator=g); gb = 0.1 * torch.randn(128, generator=g)
-    wq = (torch.randn(384, 128, generator=g) * 0.09).to(torch.bfloat16).float(); bq = 0.1 * torch.randn(384, generator=g)
-    wo = (torch.randn(128, 128, generator=g) * 0.09).to(torch.bfloat16).float(); bo = 0.1 * torch.randn(128, generator=g)
+    wq = (torch.randn(384, 128, generator=g) * 0.09).to(torch.float16).float(); bq = 0.1 * torch.randn(384, generator=g)
+    wo = (torch.randn(128, 128, generator=g) * 0.09).to(torch.float16).float(); bo = 0.1 * torch.randn(128, generator=g)
     ref = O.attention_block(x, gw, gb, wq, bq, wo, bo)
     out = S.attention_block(x.to(dev), gw, gb, wq, bq, wo, bo).float().cpu()
     delta_ref = ref - x.float()
@@ -469,7 +469,7 @@ def test_attention_block_matches_oracle(S, dev, B, R):
     rel_delta = _rel(out - x.float(), delta_ref)
     mx = ((out - ref).abs().max() / ref.abs().max()).item()
     _report(test="attention_block", B=B, R=R, rel_l2=rel, rel_l2_of_update=rel_delta, max_abs_rel=mx)
-    assert rel <= 1.5e-2 and mx <= 4e-2 and rel_delta <= 5e-2
+    assert rel <= 2e-3 and mx <= 5e-3 and rel_delta <= 1e-2
     zero = S.attention_block(x.to(dev), gw, gb, wq, bq, torch.zeros(128, 128), torch.zeros(128)).cpu()
     assert torch.equal(zero, x)
 
@@ -479,15 +479,15 @@ def test_attention_core_properties(S, dev):
     the mean of V, and the kernel is deterministic."""
     g = torch.Generator().manual_seed(9)
     B, heads, S_ = 2, 2, 1024
-    q = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16).to(dev)
-    k = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16).to(dev)
-    vrow = torch.randn(B, heads, 1, 64, generator=g).to(torch.bfloat16).to(dev)
+    q = torch.randn(B, heads, S_, 64, generator=g).to(torch.float16).to(dev)
+    k = torch.randn(B, heads, S_, 64, generator=g).to(torch.float16).to(dev)
+    vrow = torch.randn(B, heads, 1, 64, generator=g).to(torch.float16).to(dev)
     out = S.attention_core(q, k, vrow.expand(B, heads, S_, 64).contiguous())
-    assert torch.allclose(out.float(), vrow.float().expand_as(out), atol=2e-2, rtol=1e-2)
-    v = torch.randn(B, heads, S_, 64, generator=g).to(torch.bfloat16).to(dev)
+    assert torch.allclose(out.float(), vrow.float().expand_as(out), atol=4e-3, rtol=2e-3)
+    v = torch.randn(B, heads, S_, 64, generator=g).to(torch.float16).to(dev)
     k_same = k[:, :, :1].expand(B, heads, S_, 64).contiguous()
     out2 = S.attention_core(q, k_same, v)
-    assert torch.allclose(out2.float(), v.float().mean(2, keepdim=True).expand_as(out2), atol=2e-2)
+    assert torch.allclose(out2.float(), v.float().mean(2, keepdim=True).expand_as(out2), atol=4e-3)
     assert torch.equal(S.attention_core(q, k, v), S.attention_core(q, k, v))
     with pytest.raises(S.SddError):
         S.attention_core(q[:, :, :100], k[:, :, :100], v[:, :, :100])

@@ -183,3 +183,26 @@ def test_philox_normal_moments_and_sharding():
     assert np.array_equal(a[2:], b)  # keyed by global sample id -> shard invariant
     c = O.philox_normal(1234, np.arange(4), 4, 4096)
     assert not np.array_equal(a, c)
+
+
+def test_unet_attn_oracle_extension_properties():
+    """EXTENSION oracle (oracle/unet_attn_oracle.py; no reference code): shape, class-conditioning, and the reduction to
+    an attention-free network when the attention projections are zero (out = x + 0)."""
+    from oracle import unet_attn_oracle as A
+    p = A.init_params(0)
+    assert len(p) == 129
+    x = torch.randn(1, 1, 256, 256, generator=torch.Generator().manual_seed(0))
+    t = torch.tensor([40])
+    with torch.no_grad():
+        e0 = A.unet_attn_forward(p, x, t, torch.tensor([0]))
+        e1 = A.unet_attn_forward(p, x, t, torch.tensor([1]))
+        assert e0.shape == x.shape and torch.isfinite(e0).all()
+        assert (e0 - e1).abs().max() > 1e-3
+        q = dict(p)
+        for i in range(4):
+            q[f"attn.{i}.proj.weight"] = torch.zeros(128, 128)
+            q[f"attn.{i}.proj.bias"] = torch.zeros(128)
+        a = A.unet_attn_forward(q, x, t, torch.tensor([0]))
+        q2 = dict(q)
+        q2["attn.0.qkv.weight"] = torch.randn(384, 128)  # irrelevant once proj is zero
+        assert torch.equal(a, A.unet_attn_forward(q2, x, t, torch.tensor([0])))

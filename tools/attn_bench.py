@@ -6,9 +6,9 @@ import super_diff_disease_b200 as S
 dev = torch.device("cuda:0")
 L = S.lib()
 for BH, S_ in ((128, 1024), (128, 256), (512, 1024)):
-    q = torch.randn(BH, S_, 64, device=dev).to(torch.bfloat16)
-    k = torch.randn(BH, S_, 64, device=dev).to(torch.bfloat16)
-    vt = torch.randn(BH, 64, S_, device=dev).to(torch.bfloat16)
+    q = torch.randn(BH, S_, 64, device=dev).to(torch.float16)
+    k = torch.randn(BH, S_, 64, device=dev).to(torch.float16)
+    vt = torch.randn(BH, 64, S_, device=dev).to(torch.float16)
     out = torch.empty_like(q)
     ms = ctypes.c_float()
     rc = L.sdd_attention_profile(q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr(), BH, S_, 64, 0.125, 20,
