@@ -18,7 +18,8 @@ namespace sdd {
 
 constexpr int kAbC = 128;      // channels
 constexpr int kAbHeads = 2;    // heads of 64
-constexpr int kAbRows = 64;    // rows (tokens) per CTA: 4 warps x 16
+constexpr int kAbRows = 128;   // rows (tokens) per CTA: two passes of 4 warps x 16
+constexpr int kAbWStride = kAbC + 8;  // halfs per staged weight row: 272 B, so a warp's B-fragment loads hit 32 distinct banks
 
 struct AttnBlockGemmArgs {
   const act_t* a;                // MODE_QKV: x [B*S][128];  MODE_PROJ: attention out [B*heads][S][64]
@@ -45,16 +46,23 @@ __device__ __forceinline__ void mma_act_16816(float (&d)[4], const uint32_t (&a)
 #endif
 }
 
-// grid: (B*S / 64, N / 64); 128 threads.  Warp w owns rows 16w..16w+15 of the CTA's 64 and all 64 columns of its slab.
+// grid: (B*S / 128, N / 64); 128 threads.  The CTA's 64 x 128 weight slab is staged ONCE in shared memory as fp16 (the
+// first version re-read fp32 weights from global memory for every MMA: 114 us per qkv launch at 64 x 32^2 tokens, 9 % of
+// the variant's step); per pass warp w owns rows 16w..16w+15 of 64 and all 64 columns of the slab.
 template <int MODE>
 __global__ void __launch_bounds__(128) attn_block_gemm_kernel(const AttnBlockGemmArgs g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = lane & 3, j = lane >> 2;
-  const int row0 = blockIdx.x * kAbRows + warp * 16;  // first token row of this warp (global over B*S)
   const int col0 = blockIdx.y * 64;                   // first output column of this CTA
-  const int b = row0 / g.S;                           // S % 64 == 0: a CTA never straddles two samples
+  const int b = (blockIdx.x * kAbRows) / g.S;         // S % 128 == 0: a CTA never straddles two samples
   __shared__ float s_sc[kAbC], s_sh[kAbC];
   __shared__ float s_red[4][2][2];
+  __shared__ __align__(16) act_t s_w[64 * kAbWStride];
+  for (int i = threadIdx.x; i < 64 * (kAbC / 2); i += 128) {
+    const int n = i / (kAbC / 2), kp = i - n * (kAbC / 2);
+    const float2 wv = *reinterpret_cast<const float2*>(g.w + (size_t)(col0 + n) * kAbC + 2 * kp);
+    *reinterpret_cast<uint32_t*>(&s_w[n * kAbWStride + 2 * kp]) = pack_act2(wv.x, wv.y);
+  }
   if (MODE == 0) {
     for (int c = threadIdx.x; c < kAbC; c += 128) {
       const int grp = c / (kAbC / 4);
@@ -68,6 +76,10 @@ __global__ void __launch_bounds__(128) attn_block_gemm_kernel(const AttnBlockGem
   }
   __syncthreads();
 
+  float gs[2] = {0.f, 0.f}, gss[2] = {0.f, 0.f};  // MODE_PROJ: this CTA's 64 columns = GroupNorm groups col0/32, col0/32 + 1
+#pragma unroll 1
+  for (int pass = 0; pass < kAbRows / 64; ++pass) {
+  const int row0 = blockIdx.x * kAbRows + pass * 64 + warp * 16;  // first token row of this warp (global over B*S)
   float acc[8][4];
 #pragma unroll
   for (int n = 0; n < 8; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
@@ -90,13 +102,11 @@ __global__ void __launch_bounds__(128) attn_block_gemm_kernel(const AttnBlockGem
     af[0] = load_a(r_lo, k0); af[1] = load_a(r_hi, k0); af[2] = load_a(r_lo, k0 + 8); af[3] = load_a(r_hi, k0 + 8);
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const float* wr = g.w + (size_t)(col0 + n * 8 + j) * kAbC;  // B operand "col": W[n][k]
-      const float2 w0 = *reinterpret_cast<const float2*>(wr + k0), w1 = *reinterpret_cast<const float2*>(wr + k0 + 8);
-      mma_act_16816(acc[n], af, pack_act2(w0.x, w0.y), pack_act2(w1.x, w1.y));
+      const act_t* wr = &s_w[(n * 8 + j) * kAbWStride + k0];  // B operand "col": W[n][k]
+      mma_act_16816(acc[n], af, *reinterpret_cast<const uint32_t*>(wr), *reinterpret_cast<const uint32_t*>(wr + 8));
     }
   }
   // epilogue: lane holds columns col0 + 8n + 2t, +1 of rows r_lo (acc[n][0..1]) and r_hi (acc[n][2..3])
-  float gs[2] = {0.f, 0.f}, gss[2] = {0.f, 0.f};  // MODE_PROJ: this CTA's 64 columns = GroupNorm groups col0/32, col0/32 + 1
 #pragma unroll
   for (int n = 0; n < 8; ++n) {
     const int c = col0 + n * 8 + 2 * t;
@@ -126,6 +136,7 @@ __global__ void __launch_bounds__(128) attn_block_gemm_kernel(const AttnBlockGem
       }
     }
   }
+  }  // pass
   if (MODE == 1 && g.out_sums) {
     // statistics of the fp32 values before rounding (as the conv epilogue does): warp shuffle, fixed-order sum over the
     // four warps, one fixed-point RED per (group, statistic)
@@ -152,8 +163,10 @@ __global__ void __launch_bounds__(128) attn_block_gemm_kernel(const AttnBlockGem
 // and output pixel, GroupNorm(4,C) sums of the OUTPUT accumulated for the next layer.  HBM-bound elementwise passes.
 //   pool2 : out[n,h,w,:] = mean of the 2x2 block in[n,2h..2h+1,2w..2w+1,:]                      (F.avg_pool2d(., 2))
 //   up2add: out[n,h,w,:] = in[n,h/2,w/2,:] + skip[n,h,w,:]      (nearest-neighbour upsampling + additive skip connection)
-// grid = (blocks, B): a block stays inside one sample; per-thread partial sums are a fixed function of the shape, and the
-// cross-thread accumulation is integer (fixed-point), so the statistics are bit-reproducible.
+// grid = (blocks, B): a block stays inside one sample; per-thread partial sums are a fixed function of the shape, the
+// cross-lane / cross-warp sums run in a fixed order, and blocks meet in integer (fixed-point) REDs, so the statistics are
+// bit-reproducible.  (A first version had every thread add into shared-memory 64-bit atomics: the contended CAS loops
+// made the full-resolution up+skip pass cost 2.5 ms per 64 samples, 30 % of the variant's step.)
 template <bool kUp>
 __global__ void __launch_bounds__(256) resample_kernel(const act_t* __restrict__ in, const act_t* __restrict__ skip,
                                                        act_t* __restrict__ out, long long* out_sums, int Ho, int Wo,
@@ -165,16 +178,12 @@ __global__ void __launch_bounds__(256) resample_kernel(const act_t* __restrict__
   const uint4* inb = reinterpret_cast<const uint4*>(in + (size_t)b * Hi * Wi * C);
   const uint4* skb = kUp ? reinterpret_cast<const uint4*>(skip + (size_t)b * Ho * Wo * C) : nullptr;
   uint4* outb = reinterpret_cast<uint4*>(out + (size_t)b * Ho * Wo * C);
-  __shared__ unsigned long long s_acc[4][2];
-  if (threadIdx.x < 8) s_acc[threadIdx.x >> 1][threadIdx.x & 1] = 0ull;
-  __syncthreads();
-  // a thread's vector index v = i % cv is the same for every i it visits when the stride is a multiple of cv
-  const int stride = gridDim.x * 256;        // launch with gridDim.x * 256 % cv == 0 (cv is 8 or 16)
+  __shared__ float s_red[8][4][2];
+  // a thread's vector index v = i % cv = threadIdx.x % cv is the same for every i it visits (256 % cv == 0, cv = 8 or 16)
+  const int stride = gridDim.x * 256;
   float s = 0.f, ss = 0.f;
-  int grp = 0;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < nvec; i += stride) {
     const int v = i % cv, p = i / cv, w = p % Wo, h = p / Wo;
-    grp = v / (cv >> 2);
     float f[8];
     if (kUp) {
       const uint4 a = __ldg(inb + ((size_t)(h >> 1) * Wi + (w >> 1)) * cv + v);
@@ -213,12 +222,23 @@ __global__ void __launch_bounds__(256) resample_kernel(const act_t* __restrict__
     for (int j = 0; j < 8; ++j) { s += f[j]; ss = fmaf(f[j], f[j], ss); }
   }
   if (out_sums) {
-    atomicAdd(&s_acc[grp][0], (unsigned long long)__float2ll_rn(s * kGnFixScale));
-    atomicAdd(&s_acc[grp][1], (unsigned long long)__float2ll_rn(ss * kGnFixScale));
+    // lanes of one GroupNorm group inside a warp: lane % cv in [g * cv/4, (g+1) * cv/4)  ->  sum over the lane bits that
+    // do not select the group (cv = 8: bits 0, 3, 4; cv = 16: bits 0, 1, 4), then over the 8 warps in order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);  ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 16); ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+    const int o3 = cv == 8 ? 8 : 2;
+    s += __shfl_xor_sync(0xffffffffu, s, o3); ss += __shfl_xor_sync(0xffffffffu, ss, o3);
+    const int gshift = cv == 8 ? 1 : 2;       // first lane of group g: g << gshift
+    if (lane < 4 * (1 << gshift) && (lane & ((1 << gshift) - 1)) == 0) {
+      s_red[warp][lane >> gshift][0] = s; s_red[warp][lane >> gshift][1] = ss;
+    }
     __syncthreads();
-    if (threadIdx.x < 8)
-      atomicAdd(reinterpret_cast<unsigned long long*>(out_sums + (size_t)b * 8 + threadIdx.x),
-                s_acc[threadIdx.x >> 1][threadIdx.x & 1]);
+    if (threadIdx.x < 8) {
+      float a = 0.f;
+      for (int wq = 0; wq < 8; ++wq) a += s_red[wq][threadIdx.x >> 1][threadIdx.x & 1];
+      gn_red_add(out_sums + (size_t)b * 8 + threadIdx.x, a);
+    }
   }
 }
 

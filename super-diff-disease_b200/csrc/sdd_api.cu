@@ -106,6 +106,23 @@ static int make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, i
   }
   return SDD_OK;
 }
+// act fp16 [N][H][W][64] -> conv_out1's halo box (64 c, 34 w, 10 h, 1 n), 128-byte swizzle, zero fill out of bounds
+static int make_o1_map(CUtensorMap* m, const void* base, int N, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  SDD_CHECK(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {128, (cuuint64_t)W * 128, (cuuint64_t)H * W * 128};
+  cuuint32_t box[4] = {64, (cuuint32_t)kO1HW, (cuuint32_t)kO1HH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, SDD_ACT_TMAP_TYPE, 4, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(conv_out1) failed: " + std::to_string((int)r));
+    return SDD_ECUDA;
+  }
+  return SDD_OK;
+}
+
 // wt fp16 [9 = kx*3+ky][Cout][Cin] -> box (64 ci, Cout/2 rows, 1 tap): each CTA of a pair keeps its N half resident
 static int make_wt_map(CUtensorMap* m, const void* base, int Cout, int Cin) {
   EncodeTiledFn enc = get_encode();
@@ -155,6 +172,7 @@ static int ensure_func_attrs() {
   SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<128, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
   SDD_CUDA(cudaFuncSetAttribute(conv3x3_tc4_kernel<64, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kC2SmemLimit - 4096));
   SDD_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
+  SDD_CUDA(cudaFuncSetAttribute(conv_out1_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kO1SmemBytes));
   c->attrs = true;
   return SDD_OK;
 }
@@ -259,6 +277,7 @@ struct Workspace {
   float* xstats = nullptr;    // [cap_b][2] (used when the caller has no stats of x)
   float* gn_ab = nullptr;     // [2][cap_b][128] fused GroupNorm+SiLU scale / shift of the layer being launched
   CUtensorMap tm_halo[2][2];  // [buffer][Cin == 128], halo box (64, 10, 18)
+  CUtensorMap tm_o1[2];       // [buffer] as 64-channel input of conv_out1: box (64, 34, 10)
   void release() {
     cudaFree(act[0]); cudaFree(act[1]); cudaFree(e1); cudaFree(partials); cudaFree(counters);
     cudaFree(gnsums); cudaFree(xstats); cudaFree(gn_ab);
@@ -278,12 +297,14 @@ struct AnTensor {  // one activation tensor of the attention variant's forward
   long long* sums = nullptr;   // [cap_b][4][2] GroupNorm sums of this tensor
   CUtensorMap tm;              // halo map (conv inputs)
 };
+
 struct AttnWorkspace {
   int cap_b = 0, H = 0, W = 0;
   int64_t generation = 0;
   char* arena = nullptr;
   AnTensor t[kAnTensors];
   long long* sums_base = nullptr; size_t sums_bytes = 0;
+  CUtensorMap tm_o1;           // tensor 29 as the input of conv_out1
   act_t *q = nullptr, *k = nullptr, *vt = nullptr, *ao = nullptr;  // attention scratch at the R/8 level's size
   float *e1 = nullptr, *gn_ab = nullptr, *xstats = nullptr, *partials = nullptr;
   int* counters = nullptr;
@@ -353,6 +374,7 @@ int ensure_workspace(sdd_unet* u, int B, int H, int W) {
   for (int bi = 0; bi < 2; ++bi) {
     SDD_TRY(make_act_map(&ws.tm_halo[bi][0], ws.act[bi], need, H, W, 64));
     SDD_TRY(make_act_map(&ws.tm_halo[bi][1], ws.act[bi], need, H, W, 128));
+    SDD_TRY(make_o1_map(&ws.tm_o1[bi], ws.act[bi], need, H, W));
   }
   ws.cap_b = need; ws.H = H; ws.W = W;
   ++ws.generation;
@@ -451,9 +473,9 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     const BlockParams& u1 = u->blk[4];
     {
       const int o1_tiles = (int)(eg.x * eg.y * eg.z);
-      // two persistent CTAs per SM at 119 registers (three at the 80-register cap spill and run at the old 85 us)
-      conv_out1_mma_kernel<2><<<std::min(o1_tiles, 2 * num_sms()), 256, 0, st>>>(
-          ws.act[cur], sums(gi), u1.gn1_w, u1.gn1_b, u1.conv1_w, u1.conv1_b, ws.e1, sums(gi + 1), H, W, (int)eg.x,
+      SDD_TRY(ensure_func_attrs());
+      conv_out1_tma_kernel<<<std::min(o1_tiles, 2 * num_sms()), 256, kO1SmemBytes, st>>>(  // two persistent CTAs per SM
+          ws.tm_o1[cur], sums(gi), u1.gn1_w, u1.gn1_b, u1.conv1_w, u1.conv1_b, ws.e1, sums(gi + 1), H, W, (int)eg.x,
           (int)eg.y, o1_tiles);
     }
     SDD_LAUNCH_CHECK();
@@ -534,6 +556,7 @@ int attn_ensure_workspace(sdd_unet* u, int B, int H, int W) {
     t.sums = ws.sums_base + (size_t)i * need * 8;
     SDD_TRY(make_act_map(&t.tm, t.p, need, H >> t.level, W >> t.level, t.C));
   }
+  SDD_TRY(make_o1_map(&ws.tm_o1, ws.t[29].p, need, H, W));
   act_t* ab = reinterpret_cast<act_t*>(ws.arena + o_attn);
   ws.q = ab; ws.k = ab + attn_elems; ws.vt = ab + 2 * attn_elems; ws.ao = ab + 3 * attn_elems;
   ws.e1 = reinterpret_cast<float*>(ws.arena + o_e1);
@@ -634,8 +657,8 @@ int attn_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
       const BlockParams& p = u->blk[9];
       long long* e1_sums = ws.sums_base + (size_t)kAnTensors * ws.cap_b * 8;
       const int o1_tiles = (int)(eg.x * eg.y * eg.z);
-      conv_out1_mma_kernel<2><<<std::min(o1_tiles, 2 * num_sms()), 256, 0, st>>>(
-          T[29].p, T[29].sums, p.gn1_w, p.gn1_b, p.conv1_w, p.conv1_b, ws.e1, e1_sums, H, W, (int)eg.x, (int)eg.y, o1_tiles);
+      conv_out1_tma_kernel<<<std::min(o1_tiles, 2 * num_sms()), 256, kO1SmemBytes, st>>>(
+          ws.tm_o1, T[29].sums, p.gn1_w, p.gn1_b, p.conv1_w, p.conv1_b, ws.e1, e1_sums, H, W, (int)eg.x, (int)eg.y, o1_tiles);
       SDD_LAUNCH_CHECK();
       conv_out2_kernel<<<eg, 256, 0, st>>>(ws.e1, e1_sums, p.gn2_w, p.gn2_b, p.conv2_w, bias_time(9),
                                            eps_out + (size_t)b0 * HW, H, W);

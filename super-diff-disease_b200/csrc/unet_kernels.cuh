@@ -3,6 +3,7 @@
 // Reference semantics: /root/reference/src/models/unet.py:11-16, :21-34, :40-45, :57-65.
 #pragma once
 #include "common.cuh"
+#include "conv_common.cuh"
 
 namespace sdd {
 
@@ -415,6 +416,161 @@ __global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const act_t* __
       gn_red_add(out_sums + (size_t)b * 8 + tid, x0);
     }
     b = nb; h0 = nh0; w0 = nw0; img = nimg;
+  }
+}
+
+// ------------------------------------------------------------------ the same layer with TMA-staged input (product path)
+// Same contract and arithmetic as conv_out1_mma_kernel; what changes is how the raw activations reach the warps.  The
+// register-prefetch version keeps one 2 KB m-tile per warp in flight (32 KB per SM): at ~1.5 us of loaded latency that
+// caps the input stream at ~2.1 TB/s (0.33 of the HBM peak; 252 us per 64 samples at 256^2).  Here one thread fetches
+// the WHOLE (10 x 34 pixel x 64 channel) halo box of the CTA's next tile with a single TMA (43.5 KB, SWIZZLE_128B, zero
+// fill outside the image) into a two-stage shared-memory ring while the current tile is computed: 87 KB per CTA in
+// flight without a register, and the lanes read their 32-byte pieces back with conflict-free LDS.128.
+constexpr int kO1BoxBytes = kO1Pix * 128;                                   // 43520
+constexpr int kO1StageBytes = (kO1BoxBytes + 1023) / 1024 * 1024;          // 44032
+constexpr int kO1SmemBytes = 2 * kO1StageBytes + 1024 /*alignment*/ + 64;  // + barriers
+
+__global__ void __launch_bounds__(256, 2) conv_out1_tma_kernel(const __grid_constant__ CUtensorMap tmIn,
+                                                             const long long* __restrict__ in_sums /*[B][4][2]*/,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const float* __restrict__ w /*[1][64][3][3]*/,
+                                                             const float* __restrict__ bias, float* __restrict__ out,
+                                                             long long* out_sums /*[B][8], first two used*/, int H, int W,
+                                                             int tiles_x, int tiles_y, int num_tiles) {
+  extern __shared__ uint8_t o1_smem_raw[];
+  const uint32_t smem_base = (smem_u32(o1_smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + 2u * kO1StageBytes;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = lane & 3, j = lane >> 2;
+  __shared__ float tb[kO1MT * 16][kO1Taps + 1];  // T[halo pixel][tap], padded against bank conflicts
+  __shared__ float red[2][8][2];
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmIn);
+    mbar_init(bar_base, 1);
+    mbar_init(bar_base + 8, 1);
+    fence_mbar_init();
+  }
+  // weight fragments in the permuted K order: once per CTA
+  uint32_t bw[2][4][2];
+#pragma unroll
+  for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int tap = nt * 8 + j, c = t * 16 + ks * 4 + h * 2;
+        const float w0v = tap < kO1Taps ? w[c * 9 + tap] : 0.f, w1v = tap < kO1Taps ? w[(c + 1) * 9 + tap] : 0.f;
+        bw[nt][ks][h] = pack_act2(w0v, w1v);
+      }
+  const float bias0 = bias[0];
+  __syncthreads();  // barriers initialised
+
+  auto tile_coords = [&](int tile, int& b, int& h0, int& w0) {
+    const int per = tiles_x * tiles_y;
+    b = tile / per;
+    const int r = tile - b * per;
+    const int ty = r / tiles_x;
+    h0 = ty * kO1TH; w0 = (r - ty * tiles_x) * kO1TW;
+  };
+  auto issue = [&](int tile, int stage) {  // one thread
+    int b, h0, w0;
+    tile_coords(tile, b, h0, w0);
+    mbar_arrive_expect_tx(bar_base + 8u * stage, (uint32_t)kO1BoxBytes);
+    tma_load_4d(smem_base + (uint32_t)stage * kO1StageBytes, &tmIn, bar_base + 8u * stage, 0, w0 - 1, h0 - 1, b);
+  };
+
+  int tile = (int)(((long long)blockIdx.x * num_tiles) / gridDim.x);
+  const int tile_end = (int)(((long long)(blockIdx.x + 1) * num_tiles) / gridDim.x);
+  if (tile >= tile_end) return;
+  if (tid == 0) issue(tile, 0);
+  int cur_b = -1;
+  float ga[16], gb[16];
+
+  for (int it = 0; tile < tile_end; ++tile, ++it) {
+    const int stage = it & 1;
+    // the other stage was last read during tile it-1, which ended with a __syncthreads: free to refill
+    if (tid == 0 && tile + 1 < tile_end) issue(tile + 1, stage ^ 1);
+    int b, h0, w0;
+    tile_coords(tile, b, h0, w0);
+    if (b != cur_b) {  // lane t owns channels [16t, 16t+16) = exactly GroupNorm group t
+      float mean, rstd;
+      gn_mean_rstd_from_sums(in_sums + ((size_t)b * 4 + t) * 2, (double)H * (double)W * 16.0, kGnEps, mean, rstd);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        ga[i] = rstd * gamma[t * 16 + i];
+        gb[i] = beta[t * 16 + i] - mean * ga[i];
+      }
+      cur_b = b;
+    }
+    mbar_wait(bar_base + 8u * stage, (uint32_t)((it >> 1) & 1));
+    const uint32_t box = smem_base + (uint32_t)stage * kO1StageBytes;
+
+    for (int mt = warp; mt < kO1MT; mt += 8) {
+      uint32_t a[2][8];  // [row half][ks*2+h]
+#pragma unroll
+      for (int rh = 0; rh < 2; ++rh) {
+        const int p = mt * 16 + j + 8 * rh;
+        const int hr = p / kO1HW, wr = p - hr * kO1HW;
+        const int hh = h0 - 1 + hr, ww = w0 - 1 + wr;
+        const bool ok = p < kO1Pix && hh >= 0 && hh < H && ww >= 0 && ww < W;
+        uint32_t u[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        if (ok) {  // padding must be zero AFTER the activation: out-of-image pixels are skipped, not transformed
+          const uint32_t row = box + (uint32_t)p * 128u;
+          const uint4 v0 = lds_v4(row + ((uint32_t)((2 * t) ^ (p & 7)) << 4));
+          const uint4 v1 = lds_v4(row + ((uint32_t)((2 * t + 1) ^ (p & 7)) << 4));
+          u[0] = v0.x; u[1] = v0.y; u[2] = v0.z; u[3] = v0.w; u[4] = v1.x; u[5] = v1.y; u[6] = v1.z; u[7] = v1.w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float vl, vh;
+            unpack_act2(u[i], vl, vh);
+            u[i] = pack_act2(silu_tanh(fmaf(vl, ga[2 * i], gb[2 * i])), silu_tanh(fmaf(vh, ga[2 * i + 1], gb[2 * i + 1])));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[rh][i] = u[i];
+      }
+      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t af[4] = {a[0][ks * 2], a[1][ks * 2], a[0][ks * 2 + 1], a[1][ks * 2 + 1]};
+#ifndef SDD_ACT_BF16
+        mma_f16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
+        mma_f16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
+#else
+        mma_bf16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
+        mma_bf16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
+#endif
+      }
+      // d0: taps 2t, 2t+1 of rows j and j+8; d1: taps 8+2t, 9+2t (only tap 8 exists)
+      const int r0 = mt * 16 + j;
+      tb[r0][2 * t] = d0[0]; tb[r0][2 * t + 1] = d0[1];
+      tb[r0 + 8][2 * t] = d0[2]; tb[r0 + 8][2 * t + 1] = d0[3];
+      if (t == 0) { tb[r0][8] = d1[0]; tb[r0 + 8][8] = d1[2]; }
+    }
+    __syncthreads();  // tb complete; every read of this stage's box is done
+
+    const int r = tid / kO1TW, c = tid % kO1TW;
+    const int h = h0 + r, ww = w0 + c;
+    float s = 0.f, ss = 0.f;
+    if (h < H && ww < W) {
+      float acc = bias0;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) acc += tb[(r + ky) * kO1HW + (c + kx)][ky * 3 + kx];
+      out[((size_t)b * H + h) * W + ww] = acc;
+      s = acc; ss = acc * acc;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if (lane == 0) { red[it & 1][warp][0] = s; red[it & 1][warp][1] = ss; }
+    __syncthreads();  // gather reads of tb done (the next tile may overwrite it); red[it & 1] complete
+    if (tid < 2) {
+      float x0 = 0.f;
+      for (int wq = 0; wq < 8; ++wq) x0 += red[it & 1][wq][tid];
+      gn_red_add(out_sums + (size_t)b * 8 + tid, x0);
+    }
   }
 }
 
