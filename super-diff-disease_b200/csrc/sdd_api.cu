@@ -1077,6 +1077,8 @@ struct sdd_sampler {
   void* upd_ws = nullptr;
   float* stat_partials = nullptr; int* stat_counters = nullptr;
   cudaStream_t work = nullptr;   // private stream: graph capture is illegal on the legacy default stream
+  cudaStream_t side[kMaxModels] = {nullptr, nullptr, nullptr, nullptr};  // models 1.. run beside model 0 (enqueue_step)
+  cudaEvent_t ev_fork = nullptr, ev_join[kMaxModels] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t exec = nullptr;
   int captured_mode = -1;        // the only per-call argument that changes the graph's topology
@@ -1086,12 +1088,27 @@ struct sdd_sampler {
 
 namespace {
 
+// One sampling step.  The M forwards are independent (they read x, write their own eps-hat, use their own workspaces), so
+// models 1.. are enqueued on side streams forked from / joined into the work stream (captured as parallel branches of the
+// step graph).  Every conv launch is a persistent grid with one CTA per SM, so the branches cannot share an SM -- what
+// the fork buys is that a kernel's tail (SMs idle while the last tiles finish) and the next kernel's prologue (resident
+// weights, TMEM allocation) are filled with the other model's CTAs instead of a drain between dependent launches, and
+// the tiny launches (scale / shift tables, memsets, 1->1 conv) hide under the other branch's convs.
+// A handle that appears twice (self-superposition) owns ONE workspace: then everything stays on the work stream.
 int enqueue_step(sdd_sampler* s, int mode, cudaStream_t st) {
-  for (int m = 0; m < s->M; ++m) {
+  bool fork = s->M > 1;
+  for (int m = 0; m < s->M; ++m)
+    for (int j = 0; j < m; ++j) fork = fork && s->models[m] != s->models[j];
+  if (fork) SDD_CUDA(cudaEventRecord(s->ev_fork, st));
+  for (int m = s->M - 1; m >= 0; --m) {
+    cudaStream_t ms = (m == 0 || !fork) ? st : s->side[m];
+    if (ms != st) SDD_CUDA(cudaStreamWaitEvent(ms, s->ev_fork, 0));
     BiasRef tb{s->tables[m], s->step, s->models[m]->bias_row, 0};
     SDD_TRY(unet_forward_impl(s->models[m], s->x, s->xstats, tb, s->eps + (size_t)m * s->B * s->D, s->B, s->H, s->W,
-                              st));
+                              ms));
+    if (ms != st) SDD_CUDA(cudaEventRecord(s->ev_join[m], ms));
   }
+  for (int m = 1; fork && m < s->M; ++m) SDD_CUDA(cudaStreamWaitEvent(st, s->ev_join[m], 0));
   UpdateArgs a;
   memset(&a, 0, sizeof(a));
   a.x_in = s->x; a.x_out = s->x; a.eps = s->eps;
@@ -1121,6 +1138,11 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
 #define S_CUDA(expr) do { if ((expr) != cudaSuccess) { set_error(#expr " failed"); return fail(SDD_ECUDA); } } while (0)
   const size_t BD = (size_t)B * s->D;
   S_CUDA(cudaStreamCreateWithFlags(&s->work, cudaStreamNonBlocking));
+  S_CUDA(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+  for (int m = 1; m < M; ++m) {
+    S_CUDA(cudaStreamCreateWithFlags(&s->side[m], cudaStreamNonBlocking));
+    S_CUDA(cudaEventCreateWithFlags(&s->ev_join[m], cudaEventDisableTiming));
+  }
   S_CUDA(cudaEventCreateWithFlags(&s->ev_in, cudaEventDisableTiming));
   S_CUDA(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
   S_CUDA(cudaMalloc(&s->x, BD * sizeof(float)));
@@ -1255,6 +1277,11 @@ int64_t sdd_sampler_graph_instantiations(const sdd_sampler_t* s) { return s ? s-
 int sdd_sampler_destroy(sdd_sampler_t* s) {
   if (!s) return SDD_OK;
   if (s->work) cudaStreamSynchronize(s->work);
+  for (int m = 1; m < kMaxModels; ++m) {
+    if (s->side[m]) { cudaStreamSynchronize(s->side[m]); cudaStreamDestroy(s->side[m]); }
+    if (s->ev_join[m]) cudaEventDestroy(s->ev_join[m]);
+  }
+  if (s->ev_fork) cudaEventDestroy(s->ev_fork);
   if (s->exec) cudaGraphExecDestroy(s->exec);
   if (s->ev_in) cudaEventDestroy(s->ev_in);
   if (s->ev_out) cudaEventDestroy(s->ev_out);
