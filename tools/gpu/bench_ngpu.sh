@@ -3,4 +3,4 @@
 mkdir -p gpurun_out
 N=${1:-8}; shift
 TAG=${TAG:-n$N}
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 2 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/bench_$TAG.log 2>&1; echo "$TAG rc=$?"; tail -1 gpurun_out/bench_$TAG.log | cut -c1-600
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --no-cpu-baseline --steps 2 --warmup 3 "$@" > gpurun_out/bench_$TAG.log 2>&1; echo "$TAG rc=$?"; tail -1 gpurun_out/bench_$TAG.log | cut -c1-600
