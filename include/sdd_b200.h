@@ -219,7 +219,8 @@ int sdd_superpose_update_profile(float* x, const float* eps, const float* noise,
                                  int M, int iters, void* flush, size_t flush_bytes, float* ms_host,
                                  void* stream);
 
-/* Same kernel, timed as `iters` back-to-back launches between ONE event pair, each launch on the next of
+/* The update step's launch exactly as the sampler's step graph issues it (schedule table + device step counter,
+ * deferred finalisation), timed as `iters` back-to-back launches between ONE event pair, each launch on the next of
  * ceil(rot_bytes / set bytes) (>= 2) private buffer sets (x, eps[M], optional noise), so that with rot_bytes >= 2 x L2 every launch
  * reads and writes data that is not in L2 while code, constants and TLBs stay warm (an L2 flush before every launch
  * also evicts the kernel's instructions, which dominates a 10-20 us kernel).  *ms_host = mean launch duration. */

@@ -156,6 +156,52 @@ __device__ __forceinline__ void gn_mean_rstd_from_sums(const long long* sums2, d
   rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Per-sample reductions of the fused update step travel as per-segment fp32 partial sums [sample][segment][value]; every
+// consumer reduces them with THIS function -- sequential over the segments, in double -- so the update kernel's own
+// finaliser, the next step's update prologue and the next forward's first layer obtain bit-identical totals.
+__device__ __forceinline__ double reduce_partials(const float* sample_base, int nblk, int per_block, int j) {
+  double v = 0.0;
+  for (int p = 0; p < nblk; ++p) v += (double)__ldcg(sample_base + (size_t)p * per_block + j);
+  return v;
+}
+// Where the first layer gets GroupNorm(1,1) statistics of x from: (mean, rstd) floats, or -- inside the sampler's step
+// graph -- the partial sums (sum x', sum x'^2 at value index off, off + 1) the previous step's update launch left in the
+// buffer of parity (step - 1) & 1.
+struct XStatsSrc {
+  const float* xstats;    // [B][2] or nullptr
+  const float* partials;  // [2][B][nblk][per_block] or nullptr
+  size_t parity_stride;   // floats between the two parity buffers
+  int nblk, per_block, off;
+  const int* step_ptr;
+  float count;            // elements per sample (D)
+};
+constexpr int kPartialStage = 64;  // segments staged through shared memory at a time (512^2 has 64)
+// Called by ALL threads of a CTA (b is CTA-uniform).  The partials are fetched with one load per thread (independent
+// loads: one L2 round trip instead of 2 * nblk chained ones) into `stage`, then summed in the canonical order.
+__device__ __forceinline__ void xstats_load(const XStatsSrc& s, int b, float (*stage)[kPartialStage], float& mean,
+                                            float& rstd) {
+  if (s.xstats) { mean = s.xstats[b * 2]; rstd = s.xstats[b * 2 + 1]; return; }
+  const int step = *s.step_ptr;
+  const float* base = s.partials + (size_t)((step - 1) & 1) * s.parity_stride + (size_t)b * s.nblk * s.per_block;
+  double sum[2] = {0.0, 0.0};
+  for (int p0 = 0; p0 < s.nblk; p0 += kPartialStage) {
+    const int n = min(kPartialStage, s.nblk - p0);
+    __syncthreads();
+    if ((int)threadIdx.x < 2 * n) {
+      const int j = threadIdx.x / n, p = threadIdx.x - j * n;
+      stage[j][p] = __ldcg(base + (size_t)(p0 + p) * s.per_block + s.off + j);
+    }
+    __syncthreads();
+    for (int p = 0; p < n; ++p) { sum[0] += (double)stage[0][p]; sum[1] += (double)stage[1][p]; }
+  }
+  const double m = sum[0] / (double)s.count;
+  double var = sum[1] / (double)s.count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + (double)kGnEps));
+}
+
 __device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float tanh_approx(float x) {
   float y;

@@ -342,7 +342,7 @@ struct sdd_unet {
 namespace {
 
 int attn_ensure_workspace(sdd_unet* u, int B, int H, int W);
-int attn_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef tb, float* eps_out, int B, int H, int W,
+int attn_forward_impl(sdd_unet* u, const float* x, XStatsSrc xsrc, BiasRef tb, float* eps_out, int B, int H, int W,
                       cudaStream_t st);
 
 int chunk_for(const sdd_unet* u, int B, int H, int W) {
@@ -418,11 +418,25 @@ int time_bias_rows(sdd_unet* u, const int64_t* t_dev, const int64_t* y_dev, int 
 }
 
 // One UNet forward over B samples, chunked so that a chunk's activations stay L2-resident.
-// xstats: (mean, rstd) of each x sample for the first GroupNorm(1,1), or nullptr to compute here.
+// xsrc: where the first GroupNorm(1,1) gets (mean, rstd) of each x sample from (all null: computed here).
 // tb: per-block bias rows; tb.base points at column 0 of the 385-wide row.
-int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef tb, float* eps_out, int B, int H,
+XStatsSrc xstats_src(const float* xstats) {
+  XStatsSrc s;
+  memset(&s, 0, sizeof(s));
+  s.xstats = xstats;
+  return s;
+}
+// the source for samples [b0, ...) of the batch; falls back to `computed` (statistics this forward computed itself)
+XStatsSrc xstats_chunk(XStatsSrc s, int b0, const float* computed) {
+  if (s.xstats) s.xstats += (size_t)b0 * 2;
+  else if (s.partials) s.partials += (size_t)b0 * s.nblk * s.per_block;
+  else s.xstats = computed;
+  return s;
+}
+
+int unet_forward_impl(sdd_unet* u, const float* x, XStatsSrc xsrc, BiasRef tb, float* eps_out, int B, int H,
                       int W, cudaStream_t st) {
-  if (u->arch == 1) return attn_forward_impl(u, x, xstats, tb, eps_out, B, H, W, st);
+  if (u->arch == 1) return attn_forward_impl(u, x, xsrc, tb, eps_out, B, H, W, st);
   SDD_CHECK(H % kTileH == 0 && W % kTileW == 0, "H must be a multiple of 16 and W a multiple of 8");
   Workspace& ws = u->ws;
   SDD_CHECK(ws.cap_b >= 1 && ws.H == H && ws.W == W, "workspace not prepared");
@@ -440,12 +454,11 @@ int unet_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     };
     // every GroupNorm accumulator of this forward starts at zero (producers only ever RED.ADD into them)
     SDD_CUDA(cudaMemsetAsync(ws.gnsums, 0, (size_t)kGnLayers * ws.cap_b * 8 * sizeof(long long), st));
-    const float* xs = xstats ? xstats + (size_t)b0 * 2 : nullptr;
-    if (!xs) {
+    if (!xsrc.xstats && !xsrc.partials) {
       stats_x_kernel<<<dim3(kStatsBlocks, nb), 256, 0, st>>>(xc, HW, ws.partials, ws.counters, ws.xstats);
       SDD_LAUNCH_CHECK();
-      xs = ws.xstats;
     }
+    const XStatsSrc xs = xstats_chunk(xsrc, b0, ws.xstats);
     dim3 eg = egrid; eg.z = nb;
     // downs.0: GN(1,1)+SiLU fused into the 1->64 conv; raw result in act[0], its GroupNorm(4,64) sums -> sums(0)
     const BlockParams& d0 = u->blk[0];
@@ -582,7 +595,7 @@ int launch_resample(bool up, const AnTensor& in, const AnTensor* skip, const AnT
 }
 
 // One forward of the attention variant over B samples (chunked).  Same contract as unet_forward_impl.
-int attn_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef tb, float* eps_out, int B, int H, int W,
+int attn_forward_impl(sdd_unet* u, const float* x, XStatsSrc xsrc, BiasRef tb, float* eps_out, int B, int H, int W,
                       cudaStream_t st) {
   AttnWorkspace& ws = u->aws;
   SDD_CHECK(ws.cap_b >= 1 && ws.H == H && ws.W == W, "workspace not prepared");
@@ -597,12 +610,11 @@ int attn_forward_impl(sdd_unet* u, const float* x, const float* xstats, BiasRef 
     };
     AnTensor* T = ws.t;
     SDD_CUDA(cudaMemsetAsync(ws.sums_base, 0, ws.sums_bytes, st));
-    const float* xs = xstats ? xstats + (size_t)b0 * 2 : nullptr;
-    if (!xs) {
+    if (!xsrc.xstats && !xsrc.partials) {
       stats_x_kernel<<<dim3(kStatsBlocks, nb), 256, 0, st>>>(xc, HW, ws.partials, ws.counters, ws.xstats);
       SDD_LAUNCH_CHECK();
-      xs = ws.xstats;
     }
+    const XStatsSrc xs = xstats_chunk(xsrc, b0, ws.xstats);
     // conv of a residual block: input tensor `i` (GroupNorm+SiLU fused on the operand path) -> output tensor `o`
     auto conv = [&](int i, int o, const CUtensorMap& tmw, BiasRef bias, const float* gw, const float* gb, bool want_sums) {
       const AnTensor& ti = T[i];
@@ -854,7 +866,7 @@ int sdd_unet_forward_labeled(sdd_unet_t* u, const float* x, const float* xstats,
   }
   SDD_TRY(time_bias_rows(u, t, y, B, u->t_emb0, u->t_h1, u->t_emb, u->t_bias, st));
   BiasRef tb{u->t_bias, nullptr, 0, u->bias_row};
-  return unet_forward_impl(u, x, xstats, tb, eps_out, B, H, W, st);
+  return unet_forward_impl(u, x, xstats_src(xstats), tb, eps_out, B, H, W, st);
 }
 
 // ------------------------------------------------------------------------------- fused update
@@ -870,7 +882,8 @@ int launch_superpose_update(UpdateArgs a, void* workspace, cudaStream_t st) {
   SDD_CHECK(a.mode == 0 || a.mode == 1, "mode must be 0 (OR) or 1 (AND)");
   char* w = reinterpret_cast<char*>(workspace);
   a.partials = reinterpret_cast<float*>(w);
-  w += update_ws_part_bytes(a.B, a.D);
+  a.parity_stride = update_ws_part_bytes(a.B, a.D) / sizeof(float);
+  w += 2 * update_ws_part_bytes(a.B, a.D);
   a.and_partials = reinterpret_cast<float*>(w);
   w += update_ws_and_bytes(a.B, a.D);
   a.kappa_in = reinterpret_cast<float*>(w);
@@ -1073,7 +1086,7 @@ struct sdd_sampler {
   StepScalars* sched = nullptr;  // [T], row = loop iteration (t = T-1-row)
   int* step = nullptr;
   RunParams* rp = nullptr;       // per-call parameters, rewritten by begin_run_kernel
-  float *x = nullptr, *eps = nullptr, *logq = nullptr, *xstats = nullptr;
+  float *x = nullptr, *eps = nullptr, *logq = nullptr, *xstats = nullptr;  // logq: [2][B][M], double-buffered by step parity
   void* upd_ws = nullptr;
   float* stat_partials = nullptr; int* stat_counters = nullptr;
   cudaStream_t work = nullptr;   // private stream: graph capture is illegal on the legacy default stream
@@ -1095,25 +1108,36 @@ namespace {
 // weights, TMEM allocation) are filled with the other model's CTAs instead of a drain between dependent launches, and
 // the tiny launches (scale / shift tables, memsets, 1->1 conv) hide under the other branch's convs.
 // A handle that appears twice (self-superposition) owns ONE workspace: then everything stays on the work stream.
-int enqueue_step(sdd_sampler* s, int mode, cudaStream_t st) {
+int enqueue_step(sdd_sampler* s, int mode, bool first_step, cudaStream_t st) {
   bool fork = s->M > 1;
   for (int m = 0; m < s->M; ++m)
     for (int j = 0; j < m; ++j) fork = fork && s->models[m] != s->models[j];
+  // GroupNorm(1,1) statistics of x: step 0 -> stats_x_kernel's (mean, rstd) of x_T; later steps -> the partial sums the
+  // previous update launch left behind (deferred finalisation, update.cuh)
+  XStatsSrc xs;
+  memset(&xs, 0, sizeof(xs));
+  if (first_step) {
+    xs.xstats = s->xstats;
+  } else {
+    xs.partials = reinterpret_cast<const float*>(s->upd_ws);
+    xs.parity_stride = update_ws_part_bytes(s->B, s->D) / sizeof(float);
+    xs.nblk = update_blocks_per_sample(s->D, kSegSteps); xs.per_block = kPartialsPerBlock; xs.off = 3 * s->M;
+    xs.step_ptr = s->step; xs.count = (float)s->D;
+  }
   if (fork) SDD_CUDA(cudaEventRecord(s->ev_fork, st));
   for (int m = s->M - 1; m >= 0; --m) {
     cudaStream_t ms = (m == 0 || !fork) ? st : s->side[m];
     if (ms != st) SDD_CUDA(cudaStreamWaitEvent(ms, s->ev_fork, 0));
     BiasRef tb{s->tables[m], s->step, s->models[m]->bias_row, 0};
-    SDD_TRY(unet_forward_impl(s->models[m], s->x, s->xstats, tb, s->eps + (size_t)m * s->B * s->D, s->B, s->H, s->W,
-                              ms));
+    SDD_TRY(unet_forward_impl(s->models[m], s->x, xs, tb, s->eps + (size_t)m * s->B * s->D, s->B, s->H, s->W, ms));
     if (ms != st) SDD_CUDA(cudaEventRecord(s->ev_join[m], ms));
   }
   for (int m = 1; fork && m < s->M; ++m) SDD_CUDA(cudaStreamWaitEvent(st, s->ev_join[m], 0));
   UpdateArgs a;
   memset(&a, 0, sizeof(a));
   a.x_in = s->x; a.x_out = s->x; a.eps = s->eps;
-  a.logq = s->logq; a.logq_out = s->logq; a.kappa_out = nullptr; a.xstats_out = s->xstats;
-  a.table = s->sched; a.step_ptr = s->step; a.advance_step = 1;
+  a.logq = s->logq; a.logq_out = s->logq; a.kappa_out = nullptr; a.xstats_out = nullptr;
+  a.table = s->sched; a.step_ptr = s->step; a.advance_step = 1; a.defer = 1;
   a.rp = s->rp;
   a.B = s->B; a.D = s->D; a.M = s->M; a.mode = mode;
   return launch_superpose_update(a, s->upd_ws, st);
@@ -1147,7 +1171,7 @@ int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M, co
   S_CUDA(cudaEventCreateWithFlags(&s->ev_out, cudaEventDisableTiming));
   S_CUDA(cudaMalloc(&s->x, BD * sizeof(float)));
   S_CUDA(cudaMalloc(&s->eps, (size_t)M * BD * sizeof(float)));
-  S_CUDA(cudaMalloc(&s->logq, (size_t)B * M * sizeof(float)));
+  S_CUDA(cudaMalloc(&s->logq, (size_t)2 * B * M * sizeof(float)));
   S_CUDA(cudaMalloc(&s->xstats, (size_t)B * 2 * sizeof(float)));
   S_CUDA(cudaMalloc(&s->step, sizeof(int)));
   S_CUDA(cudaMalloc(&s->rp, sizeof(RunParams)));
@@ -1212,7 +1236,7 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
   begin_run_kernel<<<1, 1, 0, st>>>(s->rp, rv, s->step);
   SDD_LAUNCH_CHECK();
   // --- x_T, logq = 0, GN(1,1) stats of x_T
-  SDD_CUDA(cudaMemsetAsync(s->logq, 0, (size_t)s->B * s->M * sizeof(float), st));
+  SDD_CUDA(cudaMemsetAsync(s->logq, 0, (size_t)2 * s->B * s->M * sizeof(float), st));
   if (args->logq_traj) SDD_CUDA(cudaMemsetAsync(args->logq_traj, 0, (size_t)s->B * s->M * sizeof(float), st));
   if (args->noise_stack) {
     SDD_CUDA(cudaMemcpyAsync(s->x, args->noise_stack, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1230,7 +1254,7 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
   // --- T steps.  Step 0 always runs eagerly (so every kernel is loaded before a capture begins).
   {
     const int64_t lk = g_launches;
-    SDD_TRY(enqueue_step(s, args->mode, st));
+    SDD_TRY(enqueue_step(s, args->mode, true, st));
     s->launches_per_step = g_launches - lk;
   }
   if (args->use_graph && s->T > 1) {
@@ -1243,7 +1267,7 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
       cudaGraph_t graph = nullptr;
       const int64_t lk = g_launches;
       SDD_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_step(s, args->mode, st);
+      int rc = enqueue_step(s, args->mode, false, st);
       cudaError_t ce = cudaStreamEndCapture(st, &graph);  // always leave capture mode, even on error
       g_launches = lk;                                    // captured, not launched
       if (rc != SDD_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
@@ -1257,9 +1281,25 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
     }
     for (int k = 1; k < s->T; ++k) SDD_CUDA(cudaGraphLaunch(s->exec, st));
   } else {
-    for (int k = 1; k < s->T; ++k) SDD_TRY(enqueue_step(s, args->mode, st));
+    for (int k = 1; k < s->T; ++k) SDD_TRY(enqueue_step(s, args->mode, false, st));
   }
-  s->launches_fixed = (l1 - l0) + 1;
+  {  // close the run: log q_T from the last step's partials (the per-step finalisation is deferred, update.cuh)
+    UpdateArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.logq = s->logq; fa.logq_out = s->logq; fa.table = s->sched; fa.rp = s->rp;
+    fa.partials = reinterpret_cast<float*>(s->upd_ws);
+    fa.parity_stride = update_ws_part_bytes(s->B, s->D) / sizeof(float);
+    fa.nblk = update_blocks_per_sample(s->D, kSegSteps);
+    fa.B = s->B; fa.D = s->D; fa.M = s->M;
+    switch (s->M) {
+      case 1: finish_run_kernel<1><<<s->B, 32, 0, st>>>(fa, s->T); break;
+      case 2: finish_run_kernel<2><<<s->B, 32, 0, st>>>(fa, s->T); break;
+      case 3: finish_run_kernel<3><<<s->B, 32, 0, st>>>(fa, s->T); break;
+      default: finish_run_kernel<4><<<s->B, 32, 0, st>>>(fa, s->T); break;
+    }
+    SDD_LAUNCH_CHECK();
+  }
+  s->launches_fixed = (l1 - l0) + 2;
   int blocks = (int)std::min<size_t>((BD + 255) / 256, 2048);
   copy_f32_kernel<<<blocks, 256, 0, st>>>(args->x_out, s->x, BD);
   SDD_LAUNCH_CHECK();
@@ -1399,15 +1439,28 @@ int sdd_superpose_update_profile_rotating(int B, int D, int M, int use_noise, in
   const size_t set_floats = BD * (size_t)(1 + M + (use_noise ? 1 : 0));
   int nsets = (int)((rot_bytes + set_floats * 4 - 1) / (set_floats * 4));
   nsets = nsets < 2 ? 2 : (nsets > 512 ? 512 : nsets);
-  float* pool = nullptr; float* logq = nullptr; void* ws = nullptr; float* xstats = nullptr;
+  // exactly the sampler's launch: deferred finalisation, schedule table + device step counter, double-buffered log q
+  float* pool = nullptr; float* logq = nullptr; void* ws = nullptr; StepScalars* table = nullptr; int* step = nullptr;
   const size_t wb = update_workspace_bytes(B, D, M);
-  if (cudaMalloc(&pool, set_floats * 4 * nsets) != cudaSuccess || cudaMalloc(&logq, (size_t)B * M * 4) != cudaSuccess ||
-      cudaMalloc(&ws, wb) != cudaSuccess || cudaMalloc(&xstats, (size_t)B * 8) != cudaSuccess) {
-    cudaFree(pool); cudaFree(logq); cudaFree(ws); cudaFree(xstats);
+  const int rows = nsets + iters + 8;
+  if (cudaMalloc(&pool, set_floats * 4 * nsets) != cudaSuccess || cudaMalloc(&logq, (size_t)2 * B * M * 4) != cudaSuccess ||
+      cudaMalloc(&ws, wb) != cudaSuccess || cudaMalloc(&table, (size_t)rows * sizeof(StepScalars)) != cudaSuccess ||
+      cudaMalloc(&step, sizeof(int)) != cudaSuccess) {
+    cudaFree(pool); cudaFree(logq); cudaFree(ws); cudaFree(table); cudaFree(step);
     set_error("cudaMalloc failed"); return SDD_ENOMEM;
   }
   cudaMemsetAsync(ws, 0, wb, st);
-  cudaMemsetAsync(logq, 0, (size_t)B * M * 4, st);
+  cudaMemsetAsync(logq, 0, (size_t)2 * B * M * 4, st);
+  cudaMemsetAsync(step, 0, sizeof(int), st);
+  {
+    std::vector<StepScalars> h(rows);
+    for (int i = 0; i < rows; ++i) {
+      h[i].alpha = 0.99f; h[i].alpha_bar = 0.5f; h[i].beta = 0.01f; h[i].draw_index = use_noise ? 0 : i;
+      step_scalars_fill(h[i]);
+    }
+    cudaMemcpyAsync(table, h.data(), (size_t)rows * sizeof(StepScalars), cudaMemcpyHostToDevice, st);
+    cudaStreamSynchronize(st);
+  }
   {  // standard normals everywhere (values only matter for not being denormal / NaN)
     const size_t total = set_floats * nsets;
     const size_t nq = total / 4;
@@ -1418,17 +1471,15 @@ int sdd_superpose_update_profile_rotating(int B, int D, int M, int use_noise, in
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   UpdateArgs a;
   memset(&a, 0, sizeof(a));
-  a.logq = logq; a.logq_out = logq; a.xstats_out = xstats;  // the whole step, as the sampler launches it
+  a.logq = logq; a.logq_out = logq;
+  a.table = table; a.step_ptr = step; a.advance_step = 1; a.defer = 1;
   a.rv.temperature = 1.0f; a.rv.seed = 1234;
-  a.sc.alpha = 0.99f; a.sc.alpha_bar = 0.5f; a.sc.beta = 0.01f;
-  step_scalars_fill(a.sc);
   a.B = B; a.D = D; a.M = M;
   int rc = SDD_OK;
   auto run = [&](int n, int first) {
     for (int i = 0; rc == SDD_OK && i < n; ++i) {
       float* set = pool + (size_t)((first + i) % nsets) * set_floats;
       a.x_in = set; a.x_out = set; a.eps = set + BD; a.rv.noise = use_noise ? set + BD * (1 + M) : nullptr;
-      a.sc.draw_index = use_noise ? 0 : first + i;
       rc = launch_superpose_update(a, ws, st);
     }
   };
@@ -1439,7 +1490,7 @@ int sdd_superpose_update_profile_rotating(int B, int D, int M, int use_noise, in
   if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("update profile: kernel failed"); rc = SDD_ECUDA; }
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws); cudaFree(logq); cudaFree(pool); cudaFree(xstats);
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(ws); cudaFree(logq); cudaFree(pool); cudaFree(table); cudaFree(step);
   if (rc == SDD_OK) *ms_host = ms / iters;
   return rc;
 }

@@ -1,8 +1,10 @@
 // Fused superposition update: ONE launch per step, one coalesced, vectorised HBM pass.
 //   reads  x[B,D], eps[M,B,D], (noise[B,D] | Philox)      writes x'[B,D]
-//   per-sample reductions <eps_m,dx>, <x,eps_m>, |eps_m|^2, sum x', sum x'^2 via warp shuffles -> per-segment partials;
-//   the LAST-ARRIVING CTA of each sample reduces them in a fixed order (independent of which CTA that is) -> logq',
-//   kappa, GN(1,1) statistics of x'; the CTA that finalises the last sample advances the device-side step counter.
+//   per-sample reductions <eps_m,dx>, <x,eps_m>, |eps_m|^2, sum x', sum x'^2 via warp shuffles -> per-segment partials,
+//   reduced in ONE canonical order (common.cuh: reduce_partials) -> logq', kappa, GN(1,1) statistics of x':
+//     operator API: by the last-arriving CTA of each sample, inside the launch (results are there when it returns);
+//     sampler step graph (defer): by the prologue of the NEXT step's launch and by the next forward's first layer, so
+//     that the launch has no serial tail; the last CTA to have read the device-side step counter advances it.
 // Algorithmic bytes / element: 4 + 4M + (4 if noise tensor) + 4.
 #pragma once
 #include "common.cuh"
@@ -60,8 +62,14 @@ struct UpdateArgs {
   StepScalars sc;            // used when table == nullptr
   const RunParams* rp;       // device copy (sampler) or nullptr
   RunParams rv;              // used when rp == nullptr
-  float* partials;           // [B][nblk][kPartialsPerBlock]
-  int* counters;             // [B + 1]: per-sample arrivals, then finalised samples; zero between launches
+  float* partials;           // [B][nblk][kPartialsPerBlock]  (defer: two such buffers, parity_stride floats apart)
+  int* counters;             // [B + 2]: per-sample arrivals, finalised samples, CTAs that have read the step counter
+  // defer (the sampler's step graph): a sample's finalisation -- reduce the partials, Ito increment, log q -- is NOT done
+  // by the launch that produced the partials but in the prologue of the NEXT step's launch, where it overlaps the x / eps
+  // loads already in flight; the launch then ends with its partial stores (no fence, no arrival, no serial tail).
+  // logq is double-buffered by step parity ([2][B][M]); sdd_sampler_run closes a run with finish_run_kernel.
+  int defer;
+  size_t parity_stride;      // floats between the two partial buffers
   // "AND" mode: kappa solved per sample from a first reduction pass instead of the softmax
   float* and_partials;       // [B][nblk][kAndPartialsPerBlock] or nullptr
   float* kappa_in;           // [B][M]: written by superpose_and_solve_kernel, read by the update kernel
@@ -175,39 +183,27 @@ __device__ __forceinline__ void softmax_kappa(const UpdateArgs& a, const RunPara
   for (int m = 0; m < M; ++m) kap[m] = __fdividef(kap[m], den);
 }
 
-// Fixed-order reduce of one sample's segment partials by the 256 threads of its last-arriving CTA (16 strided lanes per
-// value, then the 16 lanes in order), Ito log-density increment in double, kappa / log q trajectory rows, GroupNorm(1,1)
-// statistics of x'.  `kap` is the kappa this step used (every CTA of the sample computed the same values).
+// Ito log-density increment of one model and step from the three per-sample sums A = <eps, dx>, Bx = <x, eps>,
+// C = |eps|^2, with s = -eps / sqrt(1 - alpha_bar):  <s,dx> - beta D/2 - beta/2 <x,s> - beta/2 |s|^2, in double.
+__device__ __forceinline__ double ito_increment(const StepScalars& sc, int D, double A, double Bx, double C) {
+  const double beta = (double)sc.beta;
+  const double inv_sig = 1.0 / sqrt(1.0 - (double)sc.alpha_bar);
+  return -inv_sig * A - 0.5 * beta * (double)D + 0.5 * beta * inv_sig * Bx - 0.5 * beta * inv_sig * inv_sig * C;
+}
+
+// Immediate finalisation (operator API): the canonical reduce of one sample's segment partials (common.cuh) by its
+// last-arriving CTA, Ito increment, kappa / log q trajectory rows, GroupNorm(1,1) statistics of x'.  `kap` is the kappa
+// this step used (every CTA of the sample computed the same values).
 template <int M>
 __device__ __forceinline__ void finalize_sample(const UpdateArgs& a, const RunParams& rp, const StepScalars& sc, int step,
                                                 int b, const float (&kap)[M]) {
   const int tid = threadIdx.x;
-  __shared__ float fin[16][16];
   __shared__ double tot[3 * M + 2];
-  {
-    const int j = tid & 15, g = tid >> 4;
-    float v = 0.0f;
-    if (j < 3 * M + 2) {
-      const float* src = a.partials + (size_t)b * a.nblk * kPartialsPerBlock + j;
-      for (int p = g; p < a.nblk; p += 16) v += __ldcg(src + (size_t)p * kPartialsPerBlock);
-    }
-    fin[g][j] = v;
-  }
-  __syncthreads();
-  if (tid < 3 * M + 2) {
-    double v = 0.0;
-#pragma unroll
-    for (int g = 0; g < 16; ++g) v += (double)fin[g][tid];
-    tot[tid] = v;
-  }
+  if (tid < 3 * M + 2)
+    tot[tid] = reduce_partials(a.partials + (size_t)b * a.nblk * kPartialsPerBlock, a.nblk, kPartialsPerBlock, tid);
   __syncthreads();
   if (tid < M) {
-    const double beta = (double)sc.beta;
-    const double inv_sig = 1.0 / sqrt(1.0 - (double)sc.alpha_bar);
-    const double A = tot[3 * tid], Bx = tot[3 * tid + 1], C = tot[3 * tid + 2];
-    // s = -eps * inv_sig:  <s,dx> - beta D/2 - beta/2 <x,s> - beta/2 |s|^2
-    const double inc = -inv_sig * A - 0.5 * beta * (double)a.D + 0.5 * beta * inv_sig * Bx - 0.5 * beta * inv_sig * inv_sig * C;
-    const float lq_new = (float)((double)a.logq[b * M + tid] + inc);
+    const float lq_new = (float)((double)a.logq[b * M + tid] + ito_increment(sc, a.D, tot[3 * tid], tot[3 * tid + 1], tot[3 * tid + 2]));
     float kv = 0.f;
 #pragma unroll
     for (int m = 0; m < M; ++m) if (m == tid) kv = kap[m];
@@ -256,7 +252,78 @@ __global__ void __launch_bounds__(kUpdThreads, STEPS == 1 ? 5 : 4) superpose_upd
   const bool noise_tensor = rp.noise != nullptr && have_noise;
   const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(rp.noise + (size_t)sc.draw_index * rp.noise_step_stride + (size_t)b * a.D) : nullptr;
   float kap[M];
-  softmax_kappa<M>(a, rp, b, kap);
+  if (a.defer) {
+    // ---- the previous step's finalisation, here: log q_k = log q_{k-1} + increment(partials of step k-1).  Every CTA of
+    // the sample computes the same values (canonical reduction order); segment 0 publishes them.  Then the step counter:
+    // the CTA that is the last of the launch to have READ it advances it (nobody can still observe the old value).
+    __shared__ float s_lq[M];
+    __shared__ float s_stage[kPartialStage][3 * M];
+    __shared__ double s_tot[3 * M];
+    const float* lq_prev = a.logq + (size_t)((step + 1) & 1) * a.B * M;   // parity (step - 1) & 1
+    float* lq_cur = a.logq_out + (size_t)(step & 1) * a.B * M;
+    if (step > 0) {
+      // one independent load per thread (a single L2 round trip), then the canonical sequential sums from shared memory
+      const float* pb = a.partials + (size_t)((step + 1) & 1) * a.parity_stride + (size_t)b * a.nblk * kPartialsPerBlock;
+      if (tid < 3 * M) s_tot[tid] = 0.0;
+      for (int p0 = 0; p0 < a.nblk; p0 += kPartialStage) {
+        const int n = min(kPartialStage, a.nblk - p0);
+        __syncthreads();
+        for (int i = tid; i < n * 3 * M; i += kUpdThreads) {
+          const int p = i / (3 * M), j = i - p * (3 * M);
+          s_stage[p][j] = __ldcg(pb + (size_t)(p0 + p) * kPartialsPerBlock + j);
+        }
+        __syncthreads();
+        if (tid < 3 * M) {
+          double v = s_tot[tid];
+          for (int p = 0; p < n; ++p) v += (double)s_stage[p][tid];
+          s_tot[tid] = v;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid < M) {
+      float lq = 0.0f;
+      if (step > 0)
+        lq = (float)((double)lq_prev[b * M + tid] +
+                     ito_increment(a.table[step - 1], a.D, s_tot[3 * tid], s_tot[3 * tid + 1], s_tot[3 * tid + 2]));
+      s_lq[tid] = lq;
+      if (seg == 0) {
+        lq_cur[b * M + tid] = lq;
+        if (rp.logq_traj && step > 0) rp.logq_traj[((size_t)step * a.B + b) * M + tid] = lq;
+      }
+    }
+    __syncthreads();
+    // (every thread of this CTA has issued its schedule-row load by now, whose address needs the step counter's value: the
+    // CTA's reads of the counter are complete before it reports in)
+    if (tid == 32 && a.advance_step) {
+      const int total = (int)(gridDim.x * gridDim.y);
+      if (atomicAdd(&a.counters[a.B + 1], 1) == total - 1) {
+        a.counters[a.B + 1] = 0;
+        *a.step_ptr = step + 1;
+      }
+    }
+    if (a.mode == 1) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) kap[m] = a.kappa_in[b * M + m];
+    } else {
+      float lg[M], mx = -INFINITY;
+#pragma unroll
+      for (int m = 0; m < M; ++m) { lg[m] = rp.temperature * s_lq[m] + (rp.bias ? rp.bias[m] : 0.0f); mx = fmaxf(mx, lg[m]); }
+      float den = 0.0f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) { kap[m] = __expf(lg[m] - mx); den += kap[m]; }
+#pragma unroll
+      for (int m = 0; m < M; ++m) kap[m] = __fdividef(kap[m], den);
+    }
+    if (seg == 0 && tid < M && rp.kappa_traj) {
+      float kv = 0.f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) if (m == tid) kv = kap[m];
+      rp.kappa_traj[((size_t)step * a.B + b) * M + tid] = kv;
+    }
+  } else {
+    softmax_kappa<M>(a, rp, b, kap);
+  }
   const uint64_t c1 = pack_f32x2(sc.c1, sc.c1), c2 = pack_f32x2(sc.c2, sc.c2), c3 = pack_f32x2(sc.c3, sc.c3);
   uint64_t kap2[M];
 #pragma unroll
@@ -334,9 +401,12 @@ __global__ void __launch_bounds__(kUpdThreads, STEPS == 1 ? 5 : 4) superpose_upd
     float v = 0.0f;
 #pragma unroll
     for (int w = 0; w < kUpdThreads / 32; ++w) v += red[w][tid];
-    __stcg(a.partials + ((size_t)b * a.nblk + seg) * kPartialsPerBlock + tid, v);
-    __threadfence();  // this thread's partial is visible device-wide before the arrival below
+    float* pdst = a.partials + (a.defer ? (size_t)(step & 1) * a.parity_stride : 0);
+    __stcg(pdst + ((size_t)b * a.nblk + seg) * kPartialsPerBlock + tid, v);
+    if (a.defer) return;  // consumed by the next launch (stream order): nothing to wait for, no tail
+    __threadfence();      // this thread's partial is visible device-wide before the arrival below
   }
+  if (a.defer) return;
   // ---- arrival: the last CTA of this sample finalises it (fixed reduction order: the result does not depend on which
   // CTA is last); the CTA that finalises the last sample advances the step counter (every CTA of the launch read it
   // before arriving, so nobody can still observe the old value)
@@ -498,6 +568,22 @@ __global__ void __launch_bounds__(256) superpose_and_solve_kernel(const UpdateAr
   }
 }
 
+// Closes a deferred run (one launch per sampling call, not per step): log q_T from the last step's partials.
+template <int M>
+__global__ void finish_run_kernel(const UpdateArgs a, int T) {
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid >= M) return;
+  const RunParams rp = load_run_params(a);
+  const float* pb = a.partials + (size_t)((T - 1) & 1) * a.parity_stride + (size_t)b * a.nblk * kPartialsPerBlock;
+  const float* lq_prev = a.logq + (size_t)((T - 1) & 1) * a.B * M;
+  const float lq = (float)((double)lq_prev[b * M + tid] +
+                           ito_increment(a.table[T - 1], a.D, reduce_partials(pb, a.nblk, kPartialsPerBlock, 3 * tid),
+                                         reduce_partials(pb, a.nblk, kPartialsPerBlock, 3 * tid + 1),
+                                         reduce_partials(pb, a.nblk, kPartialsPerBlock, 3 * tid + 2)));
+  a.logq_out[(size_t)(T & 1) * a.B * M + b * M + tid] = lq;
+  if (rp.logq_traj) rp.logq_traj[((size_t)T * a.B + b) * M + tid] = lq;
+}
+
 // Segments per sample depend on D only (steps * 2048 elements each).
 inline int update_blocks_per_sample(int D, int steps = kSegSteps) {
   int nq = D / 4;
@@ -505,8 +591,8 @@ inline int update_blocks_per_sample(int D, int steps = kSegSteps) {
   return nb < 1 ? 1 : nb;
 }
 
-// workspace = [update partials | AND partials | AND kappa[B][kMaxModels] | arrival counters[B + 1]], 256-byte aligned
-inline size_t update_ws_part_bytes(int B, int D) {
+// workspace = [update partials x 2 (step parity) | AND partials | AND kappa[B][kMaxModels] | counters[B + 2]], 256-byte aligned
+inline size_t update_ws_part_bytes(int B, int D) {  // ONE parity buffer
   return ((size_t)B * update_blocks_per_sample(D, 1) * kPartialsPerBlock * sizeof(float) + 255) & ~(size_t)255;  // any steps
 }
 inline size_t update_ws_and_bytes(int B, int D) {
@@ -514,8 +600,8 @@ inline size_t update_ws_and_bytes(int B, int D) {
 }
 inline size_t update_ws_kappa_bytes(int B) { return ((size_t)B * kMaxModels * sizeof(float) + 255) & ~(size_t)255; }
 inline size_t update_workspace_bytes(int B, int D, int /*M*/) {
-  return update_ws_part_bytes(B, D) + update_ws_and_bytes(B, D) + update_ws_kappa_bytes(B) +
-         ((((size_t)B + 1) * sizeof(int) + 255) & ~(size_t)255);
+  return 2 * update_ws_part_bytes(B, D) + update_ws_and_bytes(B, D) + update_ws_kappa_bytes(B) +
+         ((((size_t)B + 2) * sizeof(int) + 255) & ~(size_t)255);
 }
 
 __global__ void philox_normal_kernel(float* out, int B, int D, uint64_t seed, int64_t sample_offset, int draw);
