@@ -31,7 +31,11 @@ constexpr int kAttnKBytes = kAttnBN * 128;          // 16 KB
 constexpr int kAttnVBytes = 2 * kAttnD * 128;       // two 64-key halves of V^T: 16 KB
 constexpr int kAttnPBytes = 2 * kAttnBM * 128;      // two 64-key halves of P: 32 KB
 constexpr int kAttnStages = 2;
-constexpr int kAttnSmem = kAttnQBytes + kAttnStages * (kAttnKBytes + kAttnVBytes) + kAttnPBytes + 1024 + 256;
+// 112 KB of tiles + 128 B of barriers and NO alignment slack: two CTAs per SM need 2 x (dynamic + 1 KB reserved) <= 228 KB,
+// and with the round-1 "+ 1024 + 256" the kernel missed that by 512 bytes and ran ONE CTA per SM (ncu: 9 % warps active).
+// The kernel has no static shared memory, so its dynamic window starts at CTA-relative address 0 (1024-aligned, as the
+// SWIZZLE_128B tiles need); it verifies that and traps otherwise.
+constexpr int kAttnSmem = kAttnQBytes + kAttnStages * (kAttnKBytes + kAttnVBytes) + kAttnPBytes + 128;
 constexpr int kAttnTmemCols = 256;  // S: columns [0,128), PV: [128,192)
 
 struct AttnArgs {
@@ -49,8 +53,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
-  extern __shared__ uint8_t attn_smem_raw[];
-  const uint32_t smem_base = (smem_u32(attn_smem_raw) + 1023u) & ~1023u;
+  extern __shared__ __align__(1024) uint8_t attn_smem_raw[];
+  const uint32_t smem_base = smem_u32(attn_smem_raw);
+  if ((smem_base & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("sdd: attention_fwd_kernel needs a 1024-byte aligned dynamic shared-memory window\n");
+    __trap();
+  }
   const uint32_t q_smem = smem_base;
   auto k_smem = [&](int s) { return smem_base + kAttnQBytes + (uint32_t)s * (kAttnKBytes + kAttnVBytes); };
   auto v_smem = [&](int s) { return k_smem(s) + kAttnKBytes; };

@@ -269,3 +269,24 @@ def test_hot_kernels_are_tcgen05_tma_sass():
     for f in conv + attn:
         for key in ("UTCHMMA", "UTMALDG", "LDTM", "UTCBAR"):
             assert cnt[f][key] > 0, (f, key)
+
+
+def test_bench_config_helpers():
+    """bench.py host logic: the metric names the configuration actually run (it was hard-coded), strong
+    scaling splits BASELINE configs[2]'s global batch 64 into 64/32/16/8 per GPU, weak scaling keeps it per GPU."""
+    import argparse
+    import bench
+    a = argparse.Namespace(res=512, diffusion_steps=1000, batch=32, scaling="strong", arch="ref")
+    assert bench.metric_name(a) == "superposed samples/sec at 512^2 (2 UNets, 1000 steps)"
+    assert [bench.per_gpu_batch(a, w) for w in (1, 2, 4, 8)] == [32, 16, 8, 4]
+    cfg = bench.workload_config(a, 8)
+    assert cfg["global_batch"] == 32 and cfg["per_gpu_batch"] == 4 and "BASELINE configs[3]" in cfg["workload"]
+    c3 = argparse.Namespace(res=256, diffusion_steps=250, batch=64, scaling="strong", arch="ref")
+    assert [bench.per_gpu_batch(c3, w) for w in (1, 2, 4, 8)] == [64, 32, 16, 8]
+    assert "BASELINE configs[2]" in bench.workload_config(c3, 4)["workload"]
+    c3.scaling = "weak"
+    assert bench.per_gpu_batch(c3, 8) == 64 and bench.workload_config(c3, 8)["global_batch"] == 512
+    with pytest.raises(SystemExit):
+        bench.per_gpu_batch(argparse.Namespace(batch=10, scaling="strong"), 4)
+    ext = argparse.Namespace(res=256, diffusion_steps=250, batch=64, scaling="strong", arch="attn")
+    assert "EXTENSION" in bench.metric_name(ext) and "oracle/unet_attn_oracle.py" in bench.workload_config(ext, 1)["workload"]

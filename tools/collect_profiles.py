@@ -39,6 +39,15 @@ cp("parity_report.jsonl", f"{tag}_parity_report.jsonl")
 cp("update_sweep.json", f"{tag}_update_sweep_c5.json")
 cp("launches_ref.csv", f"{tag}_launches_ncu_ref.csv")
 cp("launches_attn.csv", f"{tag}_launches_ncu_attn.csv")
+cp("conv_layers.log", f"{tag}_conv_layers.txt")
+cp("attn_bench.log", f"{tag}_attn_core.txt")
+for n in ("layers_f16_a.log", "layers_bf16_a.log", "layers_f16_b.log", "layers_bf16_b.log", "layers_f32_1.log", "layers_half_1.log",
+          "layers_f32_2.log", "layers_half_2.log", "layers_f32_c8.log"):
+    cp(n, f"{tag}_ab_{n.replace('.log', '.txt')}")
+for src, dst in (("bench_b8.log", f"{tag}_bench_n1_batch8.json"),):
+    d = last_json_line(os.path.join(G, src))
+    if d:
+        json.dump(d, open(os.path.join(P, dst), "w"), indent=1)
 with open(os.path.join(P, f"{tag}_launch_shares.txt"), "w") as f:
     old = sys.stdout
     sys.stdout = f

@@ -1,7 +1,7 @@
 #!/bin/bash
-# experiment of the moment: deferred finalisation of the update step -- full suite, sweep, bench
+# experiment of the moment: attention kernel with two CTAs per SM
 mkdir -p gpurun_out
-rm -f gpurun_out/parity_report.jsonl gpurun_out/parity_growth.json
-timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/pytest_gpu.log | cut -c1-300
-timeout 300 python tools/update_sweep.py > gpurun_out/update_sweep.log 2>&1; echo "sweep rc=$?"; cat gpurun_out/update_sweep.log
-timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_exp.log 2>&1; head -c 250 gpurun_out/bench_exp.log; echo
+timeout 900 python -m pytest tests/test_gpu_unet_attn.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "attn or attention" > gpurun_out/pytest_attn.log 2>&1; tail -3 gpurun_out/pytest_attn.log | cut -c1-300
+timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1; cat gpurun_out/attn_bench.log
+timeout 600 python bench.py --steps 2 --warmup 3 --arch attn > gpurun_out/bench_attn.log 2>&1; head -c 300 gpurun_out/bench_attn.log; echo
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_fwd_kernel -s 3 -c 1 -o gpurun_out/prof_attn_r2 -f python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"

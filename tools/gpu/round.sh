@@ -8,10 +8,16 @@ timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/p
 grep -h "TRAJECTORY\|SAME-SEED" gpurun_out/pytest_gpu.log | cut -c1-700
 timeout 900 python bench.py > gpurun_out/bench_full.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench_full.log | cut -c1-400
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/bench_ref.log | cut -c1-400
+timeout 600 python bench.py --steps 2 --warmup 3 --arch attn > gpurun_out/bench_attn.log 2>&1; echo "bench attn rc=$?"; tail -1 gpurun_out/bench_attn.log | cut -c1-300
+timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --batch 8 > gpurun_out/bench_b8.log 2>&1; echo "bench b8 rc=$?"; tail -1 gpurun_out/bench_b8.log | cut -c1-250
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --res 128 --diffusion-steps 100 --batch 16 > gpurun_out/bench_c2.log 2>&1; echo "bench c2 rc=$?"; tail -1 gpurun_out/bench_c2.log | cut -c1-250
+timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --res 512 --diffusion-steps 1000 --batch 4 > gpurun_out/bench_c4.log 2>&1; echo "bench c4 shard rc=$?"; tail -1 gpurun_out/bench_c4.log | cut -c1-250
 timeout 300 python tools/update_sweep.py > gpurun_out/update_sweep.log 2>&1; echo "sweep rc=$?"; cat gpurun_out/update_sweep.log
+timeout 300 python tools/conv_layers.py > gpurun_out/conv_layers.log 2>&1; cat gpurun_out/conv_layers.log
+timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1; cat gpurun_out/attn_bench.log
 RED="--diffusion-steps 3 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-roofline"
 timeout 600 python bench.py $RED > gpurun_out/plain.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 395 -c 125 --csv --log-file gpurun_out/launches_ref.csv python bench.py $RED > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches(ref) rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 125 --csv --log-file gpurun_out/launches_ref.csv python bench.py $RED > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches(ref) rc=$?"
 timeout 600 python bench.py $RED --arch attn > gpurun_out/plain_attn.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1130 -c 360 --csv --log-file gpurun_out/launches_attn.csv python bench.py $RED --arch attn > gpurun_out/ncu_launches_attn.log 2>&1; echo "ncu launches(attn) rc=$?"
 CHUNK=64 ITERS=2 timeout 300 python tools/conv_one.py > gpurun_out/one.log 2>&1 && \
