@@ -179,7 +179,11 @@ typedef struct {
                                sample and step so that all models' log-density increments are equal; 8(f) N3) */
 } sdd_sample_args;
 
-/* models[M] are borrowed and must outlive the sampler.  alphas/alpha_bars/betas are HOST fp32[T]
+/* One step of the loop = the M UNet forwards (parallel branches of the captured step graph) + ONE update launch.  Inside the
+ * step graph the update launch defers a sample's finalisation (log q increment, kappa, GroupNorm(1,1) statistics of x') to
+ * the next step's consumers -- its own successor's prologue and the next forward's first layer -- so that the launch has
+ * no serial tail; results are bit-identical to driving sdd_unet_forward_xstats + sdd_superpose_update step by step.
+ * models[M] are borrowed and must outlive the sampler.  alphas/alpha_bars/betas are HOST fp32[T]
  * (ddpm.py:9-11).  All workspaces for (B,H,W) are allocated here. */
 int sdd_sampler_create(sdd_sampler_t** out, sdd_unet_t* const* models, int M,
                        const float* alphas_host, const float* alpha_bars_host, const float* betas_host,
