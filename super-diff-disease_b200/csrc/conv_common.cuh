@@ -34,7 +34,6 @@ struct ConvTc3Args {
   int B, H, W;
   int tiles_w, tiles_per_sample, num_tiles, num_pairs;
   int stages;
-  int contig;                  // contiguous tile-pair ranges per CTA pair (0 = strided by the grid)
   int raw_slots;               // kRaw: raw TMA slots behind the operand stages (0 = register-path loader)
   int prefetch;                // register-path loader: TMA L2 prefetch of a group's item after next (0 = off)
 };

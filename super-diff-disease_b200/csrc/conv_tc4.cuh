@@ -60,14 +60,18 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
-  // Tile pairs of this CTA pair: a CONTIGUOUS range [pair0, pair_end) (a.contig; default) or every (gridDim.x / 2)-th
+  // Tile pairs of this CTA pair: a CONTIGUOUS range [pair0, pair_end) (kContig) or every (gridDim.x / 2)-th
   // pair.  Contiguous ranges keep a loader group inside one sample for hundreds of items, so the per-sample GroupNorm
   // scale / shift (two named barriers, double-precision statistics, an LDS round trip: 15 % of the loaders' samples in
   // the 64->64 ncu capture, where the strided order changed sample every ~1.7 items) is rebuilt almost never.
   const int npp = gridDim.x >> 1, pidx = blockIdx.x >> 1;
-  const int pair0 = a.contig ? (int)(((long long)pidx * a.num_pairs) / npp) : pidx;
-  const int pair_end = a.contig ? (int)(((long long)(pidx + 1) * a.num_pairs) / npp) : a.num_pairs;
-  const int pair_stride = a.contig ? 1 : npp;
+  // (compile-time: only 64->64 gains from contiguous ranges; with the strided order pair_end is the
+  // kernel parameter itself, which lives in the constant bank -- as a computed value ptxas spilled it and the epilogue's
+  // loop test waited on the local-memory reload every tile: 17 % of its stall samples in the round-2 128->128 capture)
+  constexpr bool kContig = (CIN == 64 && COUT == 64);
+  const int pair0 = kContig ? (int)(((long long)pidx * a.num_pairs) / npp) : pidx;
+  const int pair_end = kContig ? (int)(((long long)(pidx + 1) * a.num_pairs) / npp) : a.num_pairs;
+  const int pair_stride = kContig ? 1 : npp;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
@@ -97,7 +101,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto pair_step = [&]() -> int {
     uint32_t g;
     asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(g));
-    return a.contig ? 1 : (int)(g >> 1);
+    return kContig ? 1 : (int)(g >> 1);
   };
 
   // tile of this CTA in a pair-iteration; an odd tile count leaves one dummy (clamped, computed, not stored)
@@ -482,12 +486,20 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                  make_uint4(xform_pair(r[kVecs - 1].x, 0), xform_pair(r[kVecs - 1].y, 1), xform_pair(r[kVecs - 1].z, 2),
                             xform_pair(r[kVecs - 1].w, 3)));
       } else {
+        // border tile (18 % of the tiles at 256^2, and they come in runs: a whole tile row at the top / bottom of a sample):
+        // the SAME straight-line transform, then out-of-image vectors are zeroed with a mask -- padding must be zero AFTER
+        // the activation.  (The first version branched per vector on its in-image bit: ~1.7x the instructions of the
+        // interior path exactly where 16 consecutive items of a CTA pair are border tiles, which starves the MMA.)
 #pragma unroll
         for (int i = 0; i < kVecs; ++i) {
-          uint4 v = r[i];
-          if (fuse && ((ok_c >> i) & 1u))
-            v = make_uint4(xform_pair(v.x, 0), xform_pair(v.y, 1), xform_pair(v.z, 2), xform_pair(v.w, 3));
-          if (i < nvec) sts_v4(dst + (uint32_t)i * 2048u, v);  // padding pixels hold the zeros they were "loaded" as
+          if (i < nvec) {
+            uint4 v = r[i];
+            if (fuse) {
+              const uint32_t m = ((ok_c >> i) & 1u) ? 0xffffffffu : 0u;
+              v = make_uint4(xform_pair(v.x, 0) & m, xform_pair(v.y, 1) & m, xform_pair(v.z, 2) & m, xform_pair(v.w, 3) & m);
+            }
+            sts_v4(dst + (uint32_t)i * 2048u, v);  // un-fused launches: padding pixels hold the zeros they were "loaded" as
+          }
         }
       }
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads

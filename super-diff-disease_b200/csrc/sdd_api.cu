@@ -188,7 +188,7 @@ struct GnInput3 {  // GroupNorm(4, Cin) + SiLU of the conv's input: fixed-point 
 // Launch policy, from same-box A/B runs:
 //  * generation 5 (kRaw: TMA-filled raw ring behind 3 operand stages) for the two Cin != Cout layers (64->128 314 -> 287,
 //    128->64 369 -> 348 us per 32 x 256^2 chunk); 64->64 is slower with it (227 -> 244) and 128->128 has no room;
-//  * contiguous tile ranges for 64->64 only (382 -> 373 us per 64-sample chunk; 64->128 508 -> 515);
+//  * contiguous tile ranges for 64->64 only (382 -> 373 us per 64-sample chunk; 64->128 508 -> 515): compile-time in the kernel;
 //  * TMA L2 prefetch of a loader group's item after next on the register path (+3..6 %).
 static int launch_conv(const CUtensorMap& tmA_halo, const CUtensorMap& tmB, const act_t* in, act_t* out, BiasRef bias,
                        GnInput3 gi, long long* out_sums, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
@@ -214,7 +214,6 @@ static int launch_conv(const CUtensorMap& tmA_halo, const CUtensorMap& tmB, cons
   a.num_pairs = (a.num_tiles + 1) / 2;
   a.stages = conv_tc3_stages(Cout, Cin);
   a.raw_slots = 0;
-  a.contig = (Cin == 64 && Cout == 64) ? 1 : 0;
   a.prefetch = 1;
   if (Cin != Cout) {  // raw ring: 3 operand stages + up to 4 raw slots (both layers fit all 4)
     constexpr int kRawStages = 3, kRawMaxSlots = 4;

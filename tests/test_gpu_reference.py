@@ -6,6 +6,9 @@ the CPU generator and the per-step noise on the device generator (ddpm.py:33,36)
 contract, so with identical ``torch.manual_seed`` / ``torch.cuda.manual_seed_all`` both consume identical noise and the
 only difference left is fp16-operand tensor-core arithmetic vs the reference's fp32.
 """
+import json
+import os
+
 import pytest
 import torch
 
@@ -13,6 +16,14 @@ from baseline import ref_loader
 from oracle import superdiff_oracle as O
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _report(**kw):
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "parity_report.jsonl"), "a") as f:
+        f.write(json.dumps(kw) + "\n")
+    print("PARITY", kw)
 
 
 @pytest.fixture(scope="module")
@@ -67,7 +78,7 @@ def test_same_seed_ddpm_sample_vs_reference_modules(S, ref, wseed, shape, T, see
     y = S.DDPM(T).sample(m, shape, dev)
     rel = ((y - y_ref).norm() / y_ref.norm()).item()
     mx = ((y - y_ref).abs().max() / y_ref.abs().max()).item()
-    print("SAME-SEED", shape, T, "rel-L2", rel, "max-abs/max", mx)
+    _report(test="same_seed_vs_reference_modules", shape=list(shape), T=T, seed=seed, rel_l2=rel, max_abs_rel=mx)
     assert y.shape == y_ref.shape and y.device == y_ref.device
     assert rel <= 5e-3 and mx <= 2e-2
 
@@ -83,6 +94,7 @@ def test_unet_forward_vs_reference_module_on_gpu(S, ref):
         y_ref = r(x, t)
     y = m(x, t)
     rel = ((y - y_ref).norm() / y_ref.norm()).item()
+    _report(test="unet_forward_vs_reference_module_gpu", rel_l2=rel)
     assert rel <= 4e-3, rel
 
 

@@ -1,7 +1,10 @@
 #!/bin/bash
-# experiment of the moment: attention kernel with two CTAs per SM
+# same-box A/B: previous commit's conv kernel (branchy border path, runtime contig) vs the working tree
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_unet_attn.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -k "attn or attention" > gpurun_out/pytest_attn.log 2>&1; tail -3 gpurun_out/pytest_attn.log | cut -c1-300
-timeout 300 python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1; cat gpurun_out/attn_bench.log
-timeout 600 python bench.py --steps 2 --warmup 3 --arch attn > gpurun_out/bench_attn.log 2>&1; head -c 300 gpurun_out/bench_attn.log; echo
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_fwd_kernel -s 3 -c 1 -o gpurun_out/prof_attn_r2 -f python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+PREV=$PWD/tools/_lib_prev.so
+for i in 1 2; do
+  python tools/conv_layers.py > gpurun_out/ab_new_$i.log 2>&1; tail -5 gpurun_out/ab_new_$i.log
+  SDD_LIB=$PREV python tools/conv_layers.py > gpurun_out/ab_prev_$i.log 2>&1; tail -5 gpurun_out/ab_prev_$i.log
+done
+RES=128 CHUNK=16 python tools/conv_layers.py > gpurun_out/ab_new_128.log 2>&1; tail -5 gpurun_out/ab_new_128.log
+RES=128 CHUNK=16 SDD_LIB=$PREV python tools/conv_layers.py > gpurun_out/ab_prev_128.log 2>&1; tail -5 gpurun_out/ab_prev_128.log
