@@ -8,6 +8,9 @@
 
 namespace sdd {
 
+#ifndef SDD_CONV_ACCS
+#define SDD_CONV_ACCS 4  // TMEM accumulators per CTA pair (2 = round 1; A/B builds: -DSDD_CONV_ACCS=2)
+#endif
 #ifndef SDD_CONV_HALF_MATH
 #define SDD_CONV_HALF_MATH false  // fused GroupNorm+SiLU transform in fp32 (true: packed fp16 math, see conv_tc4.cuh)
 #endif
@@ -115,7 +118,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 
 // shared memory needed for (COUT, Cin) with `stages` halo stages (operand stages + raw slots)
 inline int conv_tc3_smem_bytes(int Cout, int Cin, int stages) {
-  return 9 * (Cin / 64) * (Cout / 2) * 128 + stages * kHaloBytes + 1024 + 256;
+  return 9 * (Cin / 64) * (Cout / 2) * 128 + stages * kHaloBytes + 1024 /*alignment*/ + 512 /*barriers*/;
 }
 inline int conv_tc3_stages(int Cout, int Cin) {
   int s = kC3MaxStages;

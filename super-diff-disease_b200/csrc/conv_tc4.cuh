@@ -39,7 +39,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
 conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const ConvTc3Args a) {
   constexpr int kWSlot = (COUT / 2) * 128;  // bytes of one (tap, chunk) weight slice held by this CTA
-  constexpr int kTmemCols = 2 * COUT;
+  // FOUR fp32 accumulators in TMEM (4 x COUT columns: 256 or all 512; the kernel owns its SM): with two, the MMA warp of
+  // the 128->128 launch spent 11 % of its time waiting for the slower epilogue of the pair to release one (round-2 ncu
+  // capture) although the epilogue warps themselves idle 27 % -- hand-off jitter that two more tiles of slack absorb.
+  constexpr int kAccs = SDD_CONV_ACCS;
+  constexpr int kTmemCols = kAccs * COUT;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr int kchunks = CIN / 64;
@@ -47,14 +51,14 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t a_base = smem_base + w_bytes;
   const uint32_t raw_base = a_base + (uint32_t)a.stages * kHaloBytes;
   const uint32_t bar_base = raw_base + (uint32_t)(kRaw ? a.raw_slots : 0) * kHaloBytes;
-  auto raw_full_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + 6 + s); };
-  auto raw_empty_bar = [&](int s) { return bar_base + 8u * (3 * kC3MaxStages + 6 + s); };
+  auto raw_full_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + 10 + s); };
+  auto raw_empty_bar = [&](int s) { return bar_base + 8u * (3 * kC3MaxStages + 10 + s); };
   auto ready_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kC3MaxStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + 2 + s); };
-  const uint32_t w_bar = bar_base + 8u * (2 * kC3MaxStages + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kC3MaxStages + 5);
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + 4 + s); };
+  const uint32_t w_bar = bar_base + 8u * (2 * kC3MaxStages + 8);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * kC3MaxStages + 9);
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -77,7 +81,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1 && lane == 0) {
     // ready: one loader group (4 warps) per CTA and item -> 8 arrivals
     for (int s = 0; s < a.stages; ++s) { mbar_init(ready_bar(s), kC3LoaderWarps); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
+    for (int s = 0; s < kAccs; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
     mbar_init(w_bar, 1);
     if constexpr (kRaw)
       for (int s = 0; s < a.raw_slots; ++s) { mbar_init(raw_full_bar(s), 1); mbar_init(raw_empty_bar(s), 4); }
@@ -164,7 +168,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           __syncwarp();
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else if (warp == 3) {
@@ -321,7 +325,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int i = 0; i < G; ++i) st_global_v8(obase + (size_t)i * COUT, pk[i]);
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
       if (2 * (pair + pair_step()) + (int)rank < a.num_tiles) {  // advance to this CTA's next tile
         tw += e_dtw; th += e_dth; n += e_dn;
         if (tw >= a.tiles_w) { tw -= a.tiles_w; ++th; }
