@@ -19,6 +19,21 @@
 
 namespace sdd {
 
+// -DSDD_CONV_PROF (tools/conv_prof.py, never the product build): per-role cycle accounting of CTA 0 -- where the MMA
+// warp, one loader warp per group and one epilogue warp spend their clocks per item.
+#ifdef SDD_CONV_PROF
+__device__ unsigned long long g_conv_prof[64];
+#define SDD_PROF_DECL(n) long long pf[n] = {}; long long pf_t = clock64()
+#define SDD_PROF_LAP(i) { const long long t_ = clock64(); pf[i] += t_ - pf_t; pf_t = t_; }
+#define SDD_PROF_FLUSH(cond, base, n) if (cond) { for (int i_ = 0; i_ < (n); ++i_) atomicAdd(&g_conv_prof[(base) + i_], (unsigned long long)pf[i_]); }
+#define SDD_PROF_SINK(v) asm volatile("" ::"r"(v))
+#else
+#define SDD_PROF_DECL(n)
+#define SDD_PROF_LAP(i)
+#define SDD_PROF_FLUSH(cond, base, n)
+#define SDD_PROF_SINK(v)
+#endif
+
 // kRaw (generation 5, layers whose resident weights leave >= 3 spare 23 KB slots: every layer but 128->128): the
 // halo boxes are not fetched by the loader threads' own global loads but by TMA into a ring of RAW shared-memory slots,
 // issued by the otherwise idle warp 3 up to `raw_slots` items ahead.  Measured on v4: every layer spends 3800-3900
@@ -135,13 +150,18 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       constexpr uint32_t idesc = SDD_ACT_IDESC(256, COUT);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      SDD_PROF_DECL(4);
       for (int pair = pair0; pair < pair_end; pair += pair_step()) {
+        SDD_PROF_LAP(3);
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        SDD_PROF_LAP(0);
         tc_fence_after();
         const uint32_t d_tmem = SDD_TMEM_BASE() + (uint32_t)(acc * COUT);
 #pragma unroll
         for (int kc = 0; kc < kchunks; ++kc) {
+          SDD_PROF_LAP(3);
           mbar_wait_cluster(ready_bar(stage), phase);
+          SDD_PROF_LAP(1);
           tc_fence_after();
           if (elect_one_sync()) {
             // one base descriptor per operand; taps, chunks and K steps are immediates in 16-byte units (shared-memory
@@ -166,10 +186,12 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (kc == kchunks - 1) umma_commit_2cta(tfull_bar(acc));    // accumulator complete -> both epilogues
           }
           __syncwarp();
+          SDD_PROF_LAP(2);
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
         if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
       }
+      SDD_PROF_FLUSH(blockIdx.x == 0 && lane == 0, 0, 4);
     }
   } else if (warp == 3) {
     // ===================== kRaw: TMA producer of the raw halo boxes, `raw_slots` items ahead =====================
@@ -216,7 +238,9 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int tstep = 2 * pair_step();
     const int e_dn = tstep / a.tiles_per_sample, e_dr = tstep - e_dn * a.tiles_per_sample;
     const int e_dth = e_dr / a.tiles_w, e_dtw = e_dr - e_dth * a.tiles_w;
+    SDD_PROF_DECL(4);
     for (int pair = pair0; pair < pair_end; pair += pair_step()) {
+      SDD_PROF_LAP(3);
       const bool valid = 2 * pair + (int)rank < a.num_tiles;  // false: the dummy tile of an odd count (coordinates stay
                                                              // at the previous, valid tile; nothing is stored)
       const int h = th * kTileH + (m >> 3), w = tw * kTileW + (m & 7);
@@ -234,6 +258,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         bias_cur = bias_key;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
+      SDD_PROF_LAP(0);
       tc_fence_after();
       const uint32_t taddr = SDD_TMEM_BASE() + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + col0);
       float sg[2] = {0.f, 0.f}, ssg[2] = {0.f, 0.f};
@@ -284,6 +309,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed_remote(tempty_bar(acc), 0);  // orders TMEM reads only, not the stores
+      SDD_PROF_LAP(1);
       // (The statistics come BEFORE the stores: behind them, their first instruction had to wait for the store unit to read
       // the 256-bit stores' data registers it reuses -- a write-after-read stall worth 9 % of the epilogue's samples.)
       // warp reduction of (sg0, ssg0, sg1, ssg1) in 6 shuffles: halve the value count while halving the lanes.
@@ -325,6 +351,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int i = 0; i < G; ++i) st_global_v8(obase + (size_t)i * COUT, pk[i]);
       }
+      SDD_PROF_LAP(2);
       if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
       if (2 * (pair + pair_step()) + (int)rank < a.num_tiles) {  // advance to this CTA's next tile
         tw += e_dtw; th += e_dth; n += e_dn;
@@ -332,6 +359,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (th >= tiles_h_e) { th -= tiles_h_e; ++n; }
       }
     }
+    SDD_PROF_FLUSH(blockIdx.x == 0 && warp == 4 && lane == 0, 8, 4);
   } else {
     // ===================== loaders: global -> registers -> GroupNorm+SiLU -> swizzled shared memory ==========
     // TWO groups of four warps work on ALTERNATING items (group g: items g, g+2, ...).  Measured on the single-group
@@ -445,7 +473,9 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     };
 
+    SDD_PROF_DECL(8);
     while (item < my_items) {
+      SDD_PROF_LAP(7);
       // ---- GroupNorm scale / shift: this group's chunk is fixed, so the registers only change with the sample
       if (fuse && c.n != cur_n) {
         // precomputed by gn_scale_shift_kernel: this thread's eight channels, four 16-byte loads, no barrier
@@ -474,8 +504,19 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int i = 0; i < kVecs; ++i)
           if (i < nvec) r[i] = lds_v4(src + (uint32_t)i * 2048u);
+        SDD_PROF_LAP(0);
       }
       mbar_wait(empty_bar(stage), phase ^ 1u);
+      SDD_PROF_LAP(1);
+#ifdef SDD_CONV_PROF
+      {  // consume every load: the lap below is the exposed load latency
+        uint32_t x_ = 0;
+#pragma unroll
+        for (int i = 0; i < kVecs; ++i) x_ ^= r[i].x ^ r[i].w;
+        SDD_PROF_SINK(x_);
+      }
+      SDD_PROF_LAP(2);
+#endif
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes + soff;
       if (fuse && ok_c == (1u << nvec) - 1u) {
         // interior tile: straight-line code, the vectors' chains interleave freely.  (Three of a group's four warps own
@@ -506,8 +547,10 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           }
         }
       }
+      SDD_PROF_LAP(3);
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
       __syncwarp();
+      SDD_PROF_LAP(4);
       // relaxed: the proxy fence has completed this thread's shared-memory writes and made them visible to the async
       // proxy of THIS CTA's tensor core, the only reader
       if (lane == 0) mbar_arrive_relaxed_remote(ready_bar(stage), 0);
@@ -530,7 +573,9 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           tma_prefetch_l2_4d(&tmA, kc * 64, cp.tw * kTileW - 1, cp.th * kTileH - 1, cp.n);
         }
       }
+      SDD_PROF_LAP(5);
     }
+    SDD_PROF_FLUSH(blockIdx.x == 0 && (tg >> 5) == 0 && lane == 0, 16 + 8 * grp, 8);
   }
 
   tc_fence_before();

@@ -1333,6 +1333,17 @@ int sdd_sampler_destroy(sdd_sampler_t* s) {
 }
 
 // ------------------------------------------------------------------------------- operator entry points
+#ifdef SDD_CONV_PROF
+// prof build only (tools/conv_prof.py): read and clear the conv kernel's per-role cycle counters
+extern "C" int sdd_conv_prof_read(unsigned long long* out64) {
+  SDD_CUDA(cudaDeviceSynchronize());
+  SDD_CUDA(cudaMemcpyFromSymbol(out64, g_conv_prof, sizeof(unsigned long long) * 64));
+  unsigned long long z[64] = {};
+  SDD_CUDA(cudaMemcpyToSymbol(g_conv_prof, z, sizeof(z)));
+  return SDD_OK;
+}
+#endif
+
 // Kernel-only timing for the roofline: `iters` launches of the product conv at one shape, each bracketed by CUDA events
 // on the launching stream, with `flush_bytes` of `flush` rewritten before every launch (L2 flush).
 int sdd_conv3x3_profile(const void* act, const float* w, const float* bias, void* out, int B, int H, int W, int Cin,

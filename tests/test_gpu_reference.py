@@ -80,7 +80,7 @@ def test_same_seed_ddpm_sample_vs_reference_modules(S, ref, wseed, shape, T, see
     mx = ((y - y_ref).abs().max() / y_ref.abs().max()).item()
     _report(test="same_seed_vs_reference_modules", shape=list(shape), T=T, seed=seed, rel_l2=rel, max_abs_rel=mx)
     assert y.shape == y_ref.shape and y.device == y_ref.device
-    assert rel <= 5e-3 and mx <= 2e-2
+    assert rel <= 1.5e-3 and mx <= 4e-3  # measured: <= 3.8e-4 / 8.7e-4 (profiles/r2_parity_report.jsonl)
 
 
 def test_unet_forward_vs_reference_module_on_gpu(S, ref):
