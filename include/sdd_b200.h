@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDD_ABI_VERSION 1
+#define SDD_ABI_VERSION 2
 
 enum {
   SDD_OK = 0,
@@ -177,6 +177,12 @@ typedef struct {
   int use_graph;            /* 1: replay one captured step graph T-1 times (step 0 runs eagerly) */
   int mode;                 /* 0 = SuperDiff OR (kappa = softmax of the running log q); 1 = AND (kappa solved per
                                sample and step so that all models' log-density increments are equal; 8(f) N3) */
+  const float* noise_host;  /* ABI 2: PINNED HOST [T,B,D] stack (same meaning as noise_stack; at most one of the two):
+                               streamed to the device in step-range chunks on a copy stream while earlier steps compute,
+                               through a two-chunk device ring -- O(chunk) device memory instead of the [T,B,D] stack,
+                               and the host->device copy overlaps the loop instead of preceding it (ddpm.py:36 draws
+                               one z per step; this is the explicit-noise equivalent of that O(B*D) footprint) */
+  int noise_host_chunk;     /* slices per chunk of the streamed path; 0 = auto (~64 MB per chunk, at least one slice) */
 } sdd_sample_args;
 
 /* One step of the loop = the M UNet forwards (parallel branches of the captured step graph) + ONE update launch.  Inside the

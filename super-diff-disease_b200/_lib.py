@@ -19,7 +19,8 @@ class SampleArgs(ctypes.Structure):
     _fields_ = [("noise_stack", ctypes.c_void_p), ("seed", ctypes.c_uint64), ("sample_offset", ctypes.c_int64),
                 ("temperature", ctypes.c_float), ("bias", ctypes.c_void_p), ("x_out", ctypes.c_void_p),
                 ("kappa_traj", ctypes.c_void_p), ("logq_traj", ctypes.c_void_p), ("x_traj", ctypes.c_void_p),
-                ("use_graph", ctypes.c_int), ("mode", ctypes.c_int)]
+                ("use_graph", ctypes.c_int), ("mode", ctypes.c_int),
+                ("noise_host", ctypes.c_void_p), ("noise_host_chunk", ctypes.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/sdd_b200.h declares.
@@ -78,7 +79,7 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    if L.sdd_abi_version() != 1:
+    if L.sdd_abi_version() != 2:
         raise SddError("libsdd_b200.so ABI version mismatch")
     _LIB = L
     return L

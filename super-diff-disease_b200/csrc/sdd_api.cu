@@ -1093,6 +1093,10 @@ struct sdd_sampler {
   cudaEvent_t ev_fork = nullptr, ev_join[kMaxModels] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   cudaGraphExec_t exec = nullptr;
+  // streamed host-noise path (sdd_sample_args::noise_host): a ring of two chunks of noise slices refilled on `copy`
+  float* ring = nullptr; int ring_cap = 0;  // slices allocated
+  cudaStream_t copy = nullptr;
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   int captured_mode = -1;        // the only per-call argument that changes the graph's topology
   int64_t captured_gen[kMaxModels] = {0, 0, 0, 0};
   int64_t launches_per_step = 0, launches_fixed = 0, graph_instantiations = 0;
@@ -1227,9 +1231,66 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
   const size_t BD = (size_t)s->B * s->D;
   const int64_t l0 = g_launches;
   // --- this call's parameters -> device block read by the (possibly already instantiated) step graph; step = 0
+  // --- streamed host noise: slice j of the pinned host stack lives in ring slot j % (2 S); chunk c = slices [c S, (c+1) S)
+  // is copied on `copy` into ring half c & 1 once the steps that read chunk c-2 have finished (ev_free), and the step
+  // that needs its first slice waits for it (ev_ready).  All of it is enqueued up front: no host synchronisation.
+  const float* noise_dev = args->noise_stack;
+  int S = 0, nchunks = 0, ring_n = 0;  // slices per chunk, chunks, slots the kernels index modulo
+  SDD_CHECK(!(args->noise_stack && args->noise_host), "pass noise_stack or noise_host, not both");
+  if (args->noise_host) {
+    cudaPointerAttributes pa;
+    SDD_CHECK(cudaPointerGetAttributes(&pa, args->noise_host) == cudaSuccess && pa.type == cudaMemoryTypeHost,
+              "noise_host must be page-locked (pinned) host memory");
+    const size_t slice_bytes = BD * sizeof(float);
+    S = args->noise_host_chunk > 0 ? args->noise_host_chunk : (int)std::max<size_t>(1, ((size_t)64 << 20) / slice_bytes);
+    S = std::min(S, s->T);
+    ring_n = 2 * S >= s->T ? s->T : 2 * S;  // (the whole stack fits in two chunks: slot j = j)
+    if (s->ring_cap < ring_n) {
+      SDD_CUDA(cudaStreamSynchronize(s->work));
+      cudaFree(s->ring); s->ring = nullptr; s->ring_cap = 0;
+      if (cudaMalloc(&s->ring, (size_t)ring_n * slice_bytes) != cudaSuccess) { set_error("cudaMalloc(noise ring) failed"); return SDD_ENOMEM; }
+      s->ring_cap = ring_n;
+    }
+    if (!s->copy) {
+      SDD_CUDA(cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        SDD_CUDA(cudaEventCreateWithFlags(&s->ev_ready[i], cudaEventDisableTiming));
+        SDD_CUDA(cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
+      }
+    }
+    nchunks = (s->T + S - 1) / S;
+    noise_dev = s->ring;
+    SDD_CUDA(cudaStreamWaitEvent(s->copy, s->ev_in, 0));  // the previous run's readers of the ring are behind ev_in
+  }
+  auto enqueue_chunk = [&](int c) -> int {  // H2D copy of chunk c into its ring half
+    if (c >= nchunks) return SDD_OK;
+    if (c >= 2) SDD_CUDA(cudaStreamWaitEvent(s->copy, s->ev_free[c & 1], 0));
+    const int j0 = c * S, n = std::min(S, s->T - j0);
+    const int slot0 = ring_n == s->T ? j0 : (c & 1) * S;
+    SDD_CUDA(cudaMemcpyAsync(s->ring + (size_t)slot0 * BD, args->noise_host + (size_t)j0 * BD, (size_t)n * BD * sizeof(float),
+                             cudaMemcpyHostToDevice, s->copy));
+    SDD_CUDA(cudaEventRecord(s->ev_ready[c & 1], s->copy));
+    return SDD_OK;
+  };
+  // before the step that reads slice j: its chunk must have landed; the NEXT chunk's copy is enqueued at the same time,
+  // so that it runs under this chunk's steps.  after_slice(j): the last reader of a chunk releases its ring half.
+  auto before_slice = [&](int j) -> int {
+    if (!args->noise_host || j >= s->T || j % S != 0) return SDD_OK;
+    const int c = j / S;
+    if (c == 0) { SDD_TRY(enqueue_chunk(0)); }
+    SDD_TRY(enqueue_chunk(c + 1));
+    SDD_CUDA(cudaStreamWaitEvent(st, s->ev_ready[c & 1], 0));
+    return SDD_OK;
+  };
+  auto after_slice = [&](int j) -> int {
+    if (!args->noise_host || j >= s->T) return SDD_OK;
+    if (j % S == S - 1 || j == s->T - 1) SDD_CUDA(cudaEventRecord(s->ev_free[(j / S) & 1], st));
+    return SDD_OK;
+  };
   RunParams rv;
   memset(&rv, 0, sizeof(rv));
-  rv.noise = args->noise_stack; rv.noise_step_stride = (int64_t)BD;
+  rv.noise = noise_dev; rv.noise_step_stride = (int64_t)BD;
+  rv.noise_ring = ring_n;
   rv.seed = args->seed; rv.sample_offset = args->sample_offset; rv.temperature = args->temperature;
   rv.bias = args->bias; rv.kappa_traj = args->kappa_traj; rv.logq_traj = args->logq_traj; rv.x_traj = args->x_traj;
   begin_run_kernel<<<1, 1, 0, st>>>(s->rp, rv, s->step);
@@ -1237,8 +1298,10 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
   // --- x_T, logq = 0, GN(1,1) stats of x_T
   SDD_CUDA(cudaMemsetAsync(s->logq, 0, (size_t)2 * s->B * s->M * sizeof(float), st));
   if (args->logq_traj) SDD_CUDA(cudaMemsetAsync(args->logq_traj, 0, (size_t)s->B * s->M * sizeof(float), st));
-  if (args->noise_stack) {
-    SDD_CUDA(cudaMemcpyAsync(s->x, args->noise_stack, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (noise_dev) {
+    SDD_TRY(before_slice(0));  // slice 0 = x_T
+    SDD_CUDA(cudaMemcpyAsync(s->x, noise_dev, BD * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SDD_TRY(after_slice(0));
   } else {
     size_t n = BD / 4;
     philox_normal_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s->x, s->B, s->D, args->seed,
@@ -1253,7 +1316,9 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
   // --- T steps.  Step 0 always runs eagerly (so every kernel is loaded before a capture begins).
   {
     const int64_t lk = g_launches;
+    SDD_TRY(before_slice(1));  // step k reads slice k + 1 (the last step, t == 0, reads none)
     SDD_TRY(enqueue_step(s, args->mode, true, st));
+    SDD_TRY(after_slice(1));
     s->launches_per_step = g_launches - lk;
   }
   if (args->use_graph && s->T > 1) {
@@ -1278,9 +1343,17 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
       ++s->graph_instantiations;
       for (int m = 0; m < s->M; ++m) s->captured_gen[m] = ws_generation(s->models[m]);
     }
-    for (int k = 1; k < s->T; ++k) SDD_CUDA(cudaGraphLaunch(s->exec, st));
+    for (int k = 1; k < s->T; ++k) {
+      SDD_TRY(before_slice(k + 1));
+      SDD_CUDA(cudaGraphLaunch(s->exec, st));
+      SDD_TRY(after_slice(k + 1));
+    }
   } else {
-    for (int k = 1; k < s->T; ++k) SDD_TRY(enqueue_step(s, args->mode, false, st));
+    for (int k = 1; k < s->T; ++k) {
+      SDD_TRY(before_slice(k + 1));
+      SDD_TRY(enqueue_step(s, args->mode, false, st));
+      SDD_TRY(after_slice(k + 1));
+    }
   }
   {  // close the run: log q_T from the last step's partials (the per-step finalisation is deferred, update.cuh)
     UpdateArgs fa;
@@ -1321,6 +1394,12 @@ int sdd_sampler_destroy(sdd_sampler_t* s) {
     if (s->ev_join[m]) cudaEventDestroy(s->ev_join[m]);
   }
   if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+  if (s->copy) { cudaStreamSynchronize(s->copy); cudaStreamDestroy(s->copy); }
+  for (int i = 0; i < 2; ++i) {
+    if (s->ev_ready[i]) cudaEventDestroy(s->ev_ready[i]);
+    if (s->ev_free[i]) cudaEventDestroy(s->ev_free[i]);
+  }
+  cudaFree(s->ring);
   if (s->exec) cudaGraphExecDestroy(s->exec);
   if (s->ev_in) cudaEventDestroy(s->ev_in);
   if (s->ev_out) cudaEventDestroy(s->ev_out);

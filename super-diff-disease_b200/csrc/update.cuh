@@ -42,12 +42,15 @@ struct RunParams {
   uint64_t seed;             // Philox key when noise == nullptr
   int64_t sample_offset;     // global index of local sample 0
   float temperature;
-  int pad;
+  int noise_ring;            // > 0: `noise` is a RING of this many slices (slot = draw index % noise_ring): the sampler's
+                             // streamed host-noise path refills it in step-range chunks while earlier steps compute
   const float* bias;         // [M] or nullptr
   float* kappa_traj;         // [T,B,M] or nullptr (row = step)
   float* logq_traj;          // [T+1,B,M] or nullptr (row = step+1)
   float* x_traj;             // [T+1,B,D] or nullptr (row = step+1 receives x'; row 0 = x_T is written by the sampler)
 };
+
+__device__ __forceinline__ int noise_slot(int draw_index, int ring) { return ring > 0 ? draw_index % ring : draw_index; }
 
 struct UpdateArgs {
   const float* x_in;
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(kUpdThreads, STEPS == 1 ? 5 : 4) superpose_upd
   const RunParams rp = load_run_params(a);
   const bool have_noise = sc.draw_index >= 0;
   const bool noise_tensor = rp.noise != nullptr && have_noise;
-  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(rp.noise + (size_t)sc.draw_index * rp.noise_step_stride + (size_t)b * a.D) : nullptr;
+  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(rp.noise + (size_t)noise_slot(sc.draw_index, rp.noise_ring) * rp.noise_step_stride + (size_t)b * a.D) : nullptr;
   float kap[M];
   if (a.defer) {
     // ---- the previous step's finalisation, here: log q_k = log q_{k-1} + increment(partials of step k-1).  Every CTA of
@@ -445,7 +448,7 @@ __global__ void __launch_bounds__(kUpdThreads, 4) superpose_and_gram_kernel(cons
   const float4* x4 = reinterpret_cast<const float4*>(a.x_in + (size_t)b * a.D);
   const float4* e4 = reinterpret_cast<const float4*>(a.eps + (size_t)b * a.D);
   const size_t e_stride = (size_t)a.B * (size_t)nq;
-  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(rp.noise + (size_t)sc.draw_index * rp.noise_step_stride + (size_t)b * a.D) : nullptr;
+  const float4* n4 = noise_tensor ? reinterpret_cast<const float4*>(rp.noise + (size_t)noise_slot(sc.draw_index, rp.noise_ring) * rp.noise_step_stride + (size_t)b * a.D) : nullptr;
   const uint32_t gsample = (uint32_t)(rp.sample_offset + b);
   const int per_seg = nq / a.nblk + ((nq % a.nblk) ? 1 : 0);  // == kSubVec * steps for full segments
   float acc[NVAL];

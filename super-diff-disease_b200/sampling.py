@@ -81,7 +81,7 @@ _MODES = {"or": 0, "and": 1}
 @torch.no_grad()
 def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bias=None, noise=None, seed=None,
                       return_trajectory=False, use_graph=True, sample_offset=0, return_launches=False, mode="or",
-                      return_x_trajectory=False):
+                      return_x_trajectory=False, noise_chunk_steps=0):
     """Sample from the superposition of ``models`` (one model == DDPM.sample).
 
     models: sequence of super_diff_disease_b200.UNet (or the UNetAttn extension, each conditioning on the class set
@@ -89,6 +89,10 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
     image_shape: (B, 1, H, W), H % 16 == 0, W % 8 == 0.
     noise: fp32 [T, B, 1, H, W] stack (parity mode), or seed: int for in-kernel Philox keyed by
     (seed, sample_offset + b, draw, element) -- shard-invariant.  Exactly one of the two.
+    A noise stack on the HOST (CPU tensor; pinned, or it is pinned here) is STREAMED: the library copies it to the
+    device in chunks of ``noise_chunk_steps`` slices (0 = ~64 MB) on its own copy stream while earlier steps compute,
+    through a two-chunk device ring -- the [T,B,1,H,W] stack never exists on the device and the host->device copy
+    overlaps the loop.  Results are bit-identical to passing the same stack as a CUDA tensor.
     mode: "or" (kappa = softmax(temperature * log q + bias)) or "and" (kappa solved per sample and
     step so that every model's log-density increment is equal; temperature / bias unused).
     Returns x [B,1,H,W]; with return_trajectory also kappas [T,B,M] and logq [T+1,B,M]
@@ -113,12 +117,20 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
     args = _lib.SampleArgs()
     keep = []
     if noise is not None:
-        _lib.require_cuda(noise, "noise")
+        if not isinstance(noise, torch.Tensor):
+            raise _lib.SddError("noise must be a torch.Tensor")
         if tuple(noise.shape) != (T, B, 1, H, W):
             raise _lib.SddError(f"noise must be [T,B,1,H,W] = {(T, B, 1, H, W)}, got {tuple(noise.shape)}")
         noise = noise.to(torch.float32).contiguous()
+        if noise.is_cuda:
+            args.noise_stack = noise.data_ptr()
+        else:  # host stack: streamed by the library (pinned memory is a requirement of asynchronous copies)
+            if not noise.is_pinned():
+                noise = noise.pin_memory()
+            args.noise_stack = None
+            args.noise_host = noise.data_ptr()
+            args.noise_host_chunk = int(noise_chunk_steps)
         keep.append(noise)
-        args.noise_stack = noise.data_ptr()
     else:
         args.noise_stack = None
         args.seed = int(seed) & 0xFFFFFFFFFFFFFFFF

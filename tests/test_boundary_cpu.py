@@ -27,7 +27,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(L, name), f"{name} declared in sdd_b200.h but not exported"
     assert declared == set(S._lib.SYMBOLS), (declared ^ set(S._lib.SYMBOLS))
-    assert S.lib().sdd_abi_version() == 1
+    assert S.lib().sdd_abi_version() == 2
 
 
 def test_no_cpu_fallback():

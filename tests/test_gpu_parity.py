@@ -537,6 +537,51 @@ def test_graph_survives_new_seed_offset_and_trajectory_buffers(S, dev):
     assert smp.graph_instantiations() == 1
 
 
+def test_streamed_host_noise_equals_device_stack(S, dev):
+    """A noise stack in (pinned) HOST memory is streamed into a two-chunk device ring on the library's copy stream while
+    earlier steps compute (sdd_sample_args::noise_host).  Bit-identical to the same stack passed as a CUDA tensor, for every
+    chunk size (1 slice: a refill per step; 3: ragged last chunk; 4: T <= 2 chunks, the ring is the whole stack; auto),
+    graph and eager, OR and AND mode, M = 1 (DDPM.sample), and when a sampler is re-used across calls (ring reuse)."""
+    from super_diff_disease_b200 import sampling
+    _, models = _models(S, dev, [0, 1])
+    T, shape = 8, (2, 1, 32, 32)
+    d = S.DDPM(T)
+    g = torch.Generator().manual_seed(3)
+    stacks = [torch.randn((T,) + shape, generator=g) for _ in range(2)]
+    pinned = [st.clone().pin_memory() for st in stacks]
+    sampling.clear_cache()
+    for mode in ("or", "and"):
+        for i, st in enumerate(stacks):
+            ref = S.superposed_sample(models, d, shape, dev, noise=st.to(dev), return_trajectory=True, mode=mode)
+            for chunk in (1, 3, 4, 0):
+                for use_graph in (True, False):
+                    out = S.superposed_sample(models, d, shape, dev, noise=pinned[i], return_trajectory=True, mode=mode,
+                                              noise_chunk_steps=chunk, use_graph=use_graph)
+                    for a, b in zip(ref, out):
+                        assert torch.equal(a, b), (mode, i, chunk, use_graph)
+            # an unpinned CPU tensor is pinned by the wrapper
+            out = S.superposed_sample(models, d, shape, dev, noise=st, return_trajectory=True, mode=mode, noise_chunk_steps=2)
+            assert all(torch.equal(a, b) for a, b in zip(ref, out))
+    x1 = d.sample(models[0], shape, dev, noise=stacks[0].to(dev))
+    x2 = d.sample(models[0], shape, dev, noise=pinned[0])
+    assert torch.equal(x1, x2)
+    # the C ABI refuses pageable host memory and both stacks at once
+    import ctypes
+    from super_diff_disease_b200 import _lib
+    smp = next(iter(sampling._SAMPLERS.values()))
+    args = _lib.SampleArgs()
+    x = torch.empty(shape, device=dev)
+    args.x_out = x.data_ptr()
+    args.use_graph = 1
+    args.temperature = 1.0
+    args.noise_host = stacks[0].data_ptr()  # pageable
+    assert S.lib().sdd_sampler_run(smp.ptr, ctypes.byref(args), _lib.stream_ptr(dev)) != 0
+    args.noise_host = pinned[0].data_ptr()
+    args.noise_stack = stacks[0].to(dev).data_ptr()
+    assert S.lib().sdd_sampler_run(smp.ptr, ctypes.byref(args), _lib.stream_ptr(dev)) != 0
+    torch.cuda.synchronize()
+
+
 def test_bench_shape_tie_to_small_batch(S, dev):
     """The bench shape (64 x 1 x 256 x 256, in-kernel Philox) is tied to the oracle through a bit-exact identity: sample
     b of the 64-sample run equals the same global sample id produced by a 2-sample run with sample_offset = b (which
