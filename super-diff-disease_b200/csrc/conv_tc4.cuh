@@ -73,9 +73,15 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kC3MaxStages + 4 + s); };
   const uint32_t w_bar = bar_base + 8u * (2 * kC3MaxStages + 8);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * kC3MaxStages + 9);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  // CTA-lifetime values the 40-register control warps and the 88-register epilogue need inside their loops live in STATIC
+  // shared memory (address = an immediate, no register to keep alive): [0] TMEM base (written by tcgen05.alloc),
+  // [1] operand stages, [2] resident weights, [3] barriers, [4..6] this CTA pair's tile range.  Kept in registers,
+  // ptxas spilled them and re-loaded them from LOCAL memory in front of every MMA batch and at every loop test (~240
+  // cycles per reload with 213 KB of the L1 carved out as shared memory: 12 % of the MMA warp's stall samples in the 64->64
+  // capture, 13 % of the epilogue's; profiles/r2_stalls_conv.md).
+  __shared__ uint32_t s_cfg[8];
+  const uint32_t tmem_slot = smem_u32(&s_cfg[0]);
+#define SDD_CFG(i) (*reinterpret_cast<volatile uint32_t*>(&s_cfg[i]))
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -92,6 +98,16 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int pair_end = kContig ? (int)(((long long)(pidx + 1) * a.num_pairs) / npp) : a.num_pairs;
   const int pair_stride = kContig ? 1 : npp;
 
+  if (threadIdx.x == 0) {
+    // [5] pair iterations of this CTA pair, [6] how many of them are valid tiles for THIS CTA (an odd tile count leaves
+    // one dummy in the last pair): the MMA and epilogue loops count iterations and derive accumulator index / phase
+    // from the counter, so that ONE loop-carried control register is live across their bodies
+    const int n_it = pair_end > pair0 ? (pair_end - pair0 + pair_stride - 1) / pair_stride : 0;
+    const int last_pair = pair0 + (n_it - 1) * pair_stride;
+    s_cfg[1] = a_base; s_cfg[2] = smem_base; s_cfg[3] = bar_base; s_cfg[4] = (uint32_t)pair_end;
+    s_cfg[5] = (uint32_t)n_it;
+    s_cfg[6] = (uint32_t)((n_it > 0 && 2 * last_pair + (int)rank >= a.num_tiles) ? n_it - 1 : n_it);
+  }
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB); }
   if (warp == 1 && lane == 0) {
     // ready: one loader group (4 warps) per CTA and item -> 8 arrivals
@@ -116,7 +132,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   // hit in (~17 % of the epilogue's stall samples in the 128->128 ncu capture, and a ~300-cycle bubble per tile in
   // front of the MMA issue).  The TMEM base is re-read from its shared-memory slot (volatile: one LDS per use) and the
   // pair stride is re-derived from %nctaid behind a volatile asm, which ptxas cannot hoist.
-#define SDD_TMEM_BASE() (*tmem_slot_ptr)
+#define SDD_TMEM_BASE() SDD_CFG(0)
   auto pair_step = [&]() -> int {
     uint32_t g;
     asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(g));
@@ -149,18 +165,21 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (rank == 0) {
       constexpr uint32_t idesc = SDD_ACT_IDESC(256, COUT);
       int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
+      static_assert((kAccs & (kAccs - 1)) == 0, "accumulator count must be a power of two");
       SDD_PROF_DECL(4);
-      for (int pair = pair0; pair < pair_end; pair += pair_step()) {
+      for (int it = 0; it < (int)SDD_CFG(5); ++it) {
+        const int acc = it & (kAccs - 1);
+        const uint32_t acc_phase = (uint32_t)(it / kAccs) & 1u;
         SDD_PROF_LAP(3);
-        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);
+        const uint32_t bars = SDD_CFG(3);  // == bar_base (the lambdas above would keep it alive across the loop)
+        mbar_wait_cluster(bars + 8u * (2 * kC3MaxStages + 4 + acc), acc_phase ^ 1u);  // tempty_bar(acc)
         SDD_PROF_LAP(0);
         tc_fence_after();
         const uint32_t d_tmem = SDD_TMEM_BASE() + (uint32_t)(acc * COUT);
 #pragma unroll
         for (int kc = 0; kc < kchunks; ++kc) {
           SDD_PROF_LAP(3);
-          mbar_wait_cluster(ready_bar(stage), phase);
+          mbar_wait_cluster(bars + 8u * stage, phase);  // ready_bar(stage)
           SDD_PROF_LAP(1);
           tc_fence_after();
           if (elect_one_sync()) {
@@ -170,8 +189,8 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             // out of the tile loop and, at 40 registers, spilled and re-loaded from local memory in front of every MMA)
             uint32_t opaque;
             asm volatile("mov.u32 %0, 0;" : "=r"(opaque));
-            const uint64_t adesc0 = umma_desc_sw128(a_base + stage * kHaloBytes, kHaloW * 128);
-            const uint64_t bdesc0 = umma_desc_sw128(smem_base + opaque);
+            const uint64_t adesc0 = umma_desc_sw128(SDD_CFG(1) + stage * kHaloBytes, kHaloW * 128);
+            const uint64_t bdesc0 = umma_desc_sw128(SDD_CFG(2) + opaque);
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
@@ -182,14 +201,13 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 bdesc0 + (uint64_t)((((kx * 3 + ky) * kchunks + kc) * kWSlot) / 16 + k * 2), idesc,
                                 (kc | kx | ky | k) ? 1u : 0u);
               }
-            umma_commit_2cta(empty_bar(stage));                         // frees the stage in both CTAs
-            if (kc == kchunks - 1) umma_commit_2cta(tfull_bar(acc));    // accumulator complete -> both epilogues
+            umma_commit_2cta(bars + 8u * (kC3MaxStages + stage));       // empty_bar(stage): frees the stage in both CTAs
+            if (kc == kchunks - 1) umma_commit_2cta(bars + 8u * (2 * kC3MaxStages + acc));  // tfull_bar(acc) -> both epilogues
           }
           __syncwarp();
           SDD_PROF_LAP(2);
           if (++stage == a.stages) { stage = 0; phase ^= 1u; }
         }
-        if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
       }
       SDD_PROF_FLUSH(blockIdx.x == 0 && lane == 0, 0, 4);
     }
@@ -223,7 +241,6 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const float* bias_row = a.bias.base + (a.bias.row_ptr ? (int64_t)(*a.bias.row_ptr) : 0) * a.bias.row_stride + col0;
     __shared__ __align__(16) float s_bias[8][64];
     int bias_cur = -1;
-    int acc = 0; uint32_t acc_phase = 0;
     // division-free tile cursor (the two runtime-divisor divisions per tile were ~55 of the epilogue's ~450 instructions
     // per warp and tile): (n, th, tw) of this CTA's tile advance by a constant tile step with carries
     int n, th, tw;
@@ -239,10 +256,12 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int e_dn = tstep / a.tiles_per_sample, e_dr = tstep - e_dn * a.tiles_per_sample;
     const int e_dth = e_dr / a.tiles_w, e_dtw = e_dr - e_dth * a.tiles_w;
     SDD_PROF_DECL(4);
-    for (int pair = pair0; pair < pair_end; pair += pair_step()) {
+    for (int it = 0; it < (int)SDD_CFG(5); ++it) {
       SDD_PROF_LAP(3);
-      const bool valid = 2 * pair + (int)rank < a.num_tiles;  // false: the dummy tile of an odd count (coordinates stay
-                                                             // at the previous, valid tile; nothing is stored)
+      const int acc = it & (kAccs - 1);
+      const uint32_t acc_phase = (uint32_t)(it / kAccs) & 1u;
+      const bool valid = it < (int)SDD_CFG(6);  // false: the dummy tile of an odd count (coordinates stay at the
+                                                // previous, valid tile; nothing is stored)
       const int h = th * kTileH + (m >> 3), w = tw * kTileW + (m & 7);
       const float* bp = bias_row + (int64_t)n * a.bias.batch_stride;
       act_t* orow = a.out + (((size_t)n * a.H + h) * a.W + w) * COUT + col0;
@@ -352,8 +371,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int i = 0; i < G; ++i) st_global_v8(obase + (size_t)i * COUT, pk[i]);
       }
       SDD_PROF_LAP(2);
-      if (++acc == kAccs) { acc = 0; acc_phase ^= 1u; }
-      if (2 * (pair + pair_step()) + (int)rank < a.num_tiles) {  // advance to this CTA's next tile
+      if (it + 1 < (int)SDD_CFG(6)) {  // advance to this CTA's next (valid) tile
         tw += e_dtw; th += e_dth; n += e_dn;
         if (tw >= a.tiles_w) { tw -= a.tiles_w; ++th; }
         if (th >= tiles_h_e) { th -= tiles_h_e; ++n; }
@@ -383,6 +401,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     for (int i = 0; i < kVecs; ++i) {
       const int r = col + 16 * i, hr = r / kHaloW, wr = r - hr * kHaloW;
       goff[i] = (uint32_t)((hr * a.W + wr) * CIN * 2 + piece * 16);
+      asm volatile("" : "+r"(goff[i]));  // opaque: ptxas otherwise rebuilds each offset from (hr, W) in front of its load
     }
     const uint32_t soff = (uint32_t)col * 128u + (uint32_t)((piece ^ (col & 7)) << 4);  // + i * 2048
 
@@ -413,19 +432,26 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (c.th >= tiles_h) { c.th -= tiles_h; ++c.n; }
       return c;
     };
+    // this thread's vectors in the first / last halo row and column: the ones a tile on the image border loses
+    uint32_t m_top = 0, m_bot = 0, m_left = 0, m_right = 0;
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const int r = col + 16 * i, hr = r / kHaloW, wr = r - hr * kHaloW;
+      if (hr == 0) m_top |= 1u << i;
+      if (hr == kTileH + 1) m_bot |= 1u << i;
+      if (wr == 0) m_left |= 1u << i;
+      if (wr == kHaloW - 1) m_right |= 1u << i;
+    }
     // pointer to the box origin of a tile (chunk kc) and the mask of this thread's in-image vectors
     auto tile_src = [&](const Cursor& c, const uint8_t*& base, uint32_t& okmask) {
       const int h0 = c.th * kTileH - 1, w0 = c.tw * kTileW - 1;
       base = in_bytes + (((long long)c.n * a.H + h0) * a.W + w0) * (long long)(CIN * 2) + kc * 128;
-      const uint32_t all = (1u << nvec) - 1u;
-      const bool interior = c.th > 0 && c.th < tiles_h - 1 && c.tw > 0 && c.tw < a.tiles_w - 1;
-      if (interior) { okmask = all; return; }
-      okmask = 0;
-#pragma unroll
-      for (int i = 0; i < kVecs; ++i) {
-        const int r = col + 16 * i, hr = r / kHaloW, wr = r - hr * kHaloW;
-        if (i < nvec && (h0 + hr) >= 0 && (h0 + hr) < a.H && (w0 + wr) >= 0 && (w0 + wr) < a.W) okmask |= 1u << i;
-      }
+      uint32_t lost = 0;  // (the per-vector compare loop this replaces cost ~170 instructions on every border item)
+      if (c.th == 0) lost |= m_top;
+      if (c.th == tiles_h - 1) lost |= m_bot;
+      if (c.tw == 0) lost |= m_left;
+      if (c.tw == a.tiles_w - 1) lost |= m_right;
+      okmask = ((1u << nvec) - 1u) & ~lost;
     };
     uint4 r[kVecs];
     auto issue_loads = [&](const uint8_t* base, uint32_t okmask) {
@@ -585,6 +611,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(SDD_TMEM_BASE()), "n"(kTmemCols) : "memory");
 #undef SDD_TMEM_BASE
+#undef SDD_CFG
   }
 }
 

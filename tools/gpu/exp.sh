@@ -1,11 +1,8 @@
 #!/bin/bash
-# does the fp16-math transform build hold every bound of the test suite?  (+ same-box bench A/B)
+# same-box A/B: baseline library (tools/_lib_base.so, built from HEAD) vs the working tree's library
 mkdir -p gpurun_out
-H=$PWD/tools/_lib_half.so
-rm -f gpurun_out/parity_report.jsonl gpurun_out/parity_growth.json
-SDD_LIB=$H timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_half.log 2>&1; echo "pytest rc=$?"; tail -8 gpurun_out/pytest_half.log | cut -c1-300
-cp gpurun_out/parity_report.jsonl gpurun_out/parity_report_half.jsonl; cp gpurun_out/parity_growth.json gpurun_out/parity_growth_half.json
-timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_f32m.log 2>&1; head -c 250 gpurun_out/bench_f32m.log; echo
-SDD_LIB=$H timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_halfm.log 2>&1; head -c 250 gpurun_out/bench_halfm.log; echo
-timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_f32m_2.log 2>&1; head -c 250 gpurun_out/bench_f32m_2.log; echo
-SDD_LIB=$H timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_halfm_2.log 2>&1; head -c 250 gpurun_out/bench_halfm_2.log; echo
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "conv or unet_forward or border or nonsquare or non_square" 2>&1 | tail -3
+for i in 1 2; do
+  SDD_LIB=$PWD/tools/_lib_base.so timeout 200 python tools/conv_layers.py > gpurun_out/ab_base_$i.txt 2>&1; cat gpurun_out/ab_base_$i.txt
+  timeout 200 python tools/conv_layers.py > gpurun_out/ab_new_$i.txt 2>&1; cat gpurun_out/ab_new_$i.txt
+done
