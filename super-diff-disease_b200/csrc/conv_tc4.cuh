@@ -112,7 +112,8 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1 && lane == 0) {
     // ready: one loader group (4 warps) per CTA and item -> 8 arrivals
     for (int s = 0; s < a.stages; ++s) { mbar_init(ready_bar(s), kC3LoaderWarps); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < kAccs; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 16); }
+    // tempty: every epilogue warp that drains the accumulator, in both CTAs (Cout = 64: four warps per tile, see there)
+    for (int s = 0; s < kAccs; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), COUT == 64 ? 8 : 16); }
     mbar_init(w_bar, 1);
     if constexpr (kRaw)
       for (int s = 0; s < a.raw_slots; ++s) { mbar_init(raw_full_bar(s), 1); mbar_init(raw_empty_bar(s), 4); }
@@ -231,11 +232,18 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   }
   } else if (warp < 12) {
-    // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 column halves =====================
+    // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 =====================
+    // Cout = 128: x 2 column halves of every tile.  Cout = 64 (kSplit): x 2 TILE PARITIES -- a warp drains all 64 columns of
+    // its quadrant, of every other tile.  Per warp and tile the work is then the same 64 columns in both cases, but a
+    // Cout = 64 tile pays the per-tile fixed costs (cursor, waits, bias row, statistics reduction, addresses: ~2/3 of the
+    // ~290 instructions a warp spent on 32 columns) four times instead of eight.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    constexpr int COLS = COUT / 2;  // columns drained by this warp (two GroupNorm groups)
-    constexpr int G = COLS / 16;    // 16-channel chunks per pixel and warp: 4 (Cout = 128) or 2 (Cout = 64)
-    const int e = warp - 4, q = e & 3, hcol = e >> 2;
+    constexpr bool kSplit = COUT == 64;
+    constexpr int COLS = 64;        // columns drained by this warp
+    constexpr int G = COLS / 16;    // 16-channel chunks per pixel and warp
+    constexpr int kGroups = kSplit ? 4 : 2;  // GroupNorm groups inside the warp's columns (16 / 32 channels each)
+    const int e = warp - 4, q = e & 3, hcol = kSplit ? 0 : (e >> 2);
+    const int par = kSplit ? (e >> 2) : 0, it_step = kSplit ? 2 : 1;
     const int col0 = hcol * COLS;
     const int m = q * 32 + lane;  // accumulator row = pixel within the tile
     const float* bias_row = a.bias.base + (a.bias.row_ptr ? (int64_t)(*a.bias.row_ptr) : 0) * a.bias.row_stride + col0;
@@ -246,17 +254,17 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     int n, th, tw;
     {
       bool v0;
-      const int tile0 = tile_of(pair0, v0);
+      const int tile0 = tile_of(pair0 + par * pair_stride, v0);
       n = tile0 / a.tiles_per_sample;
       const int tr = tile0 - n * a.tiles_per_sample;
       th = tr / a.tiles_w; tw = tr - th * a.tiles_w;
     }
     const int tiles_h_e = a.H / kTileH;
-    const int tstep = 2 * pair_step();
+    const int tstep = 2 * it_step * pair_step();
     const int e_dn = tstep / a.tiles_per_sample, e_dr = tstep - e_dn * a.tiles_per_sample;
     const int e_dth = e_dr / a.tiles_w, e_dtw = e_dr - e_dth * a.tiles_w;
     SDD_PROF_DECL(4);
-    for (int it = 0; it < (int)SDD_CFG(5); ++it) {
+    for (int it = par; it < (int)SDD_CFG(5); it += it_step) {
       SDD_PROF_LAP(3);
       const int acc = it & (kAccs - 1);
       const uint32_t acc_phase = (uint32_t)(it / kAccs) & 1u;
@@ -280,7 +288,9 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       SDD_PROF_LAP(0);
       tc_fence_after();
       const uint32_t taddr = SDD_TMEM_BASE() + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT + col0);
-      float sg[2] = {0.f, 0.f}, ssg[2] = {0.f, 0.f};
+      float sg[kGroups], ssg[kGroups];
+#pragma unroll
+      for (int g = 0; g < kGroups; ++g) { sg[g] = 0.f; ssg[g] = 0.f; }
       uint32_t v[2][16];
       uint32_t pk[G][8];  // this lane's pixel: G chunks of 16 channels (32 B each), packed fp16
       tmem_ld_32x16(taddr, v[0]);
@@ -302,8 +312,9 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           f2[2 * j + 1] = add_f32x2(pack_f32x2(__uint_as_float(vv[4 * j + 2]), __uint_as_float(vv[4 * j + 3])),
                                     pack_f32x2(b4[j].z, b4[j].w));
         }
-        // two GroupNorm groups per warp; two independent pair accumulators per statistic
-        const int g = (st * 16 >= COLS / 2) ? 1 : 0;
+        // GroupNorm group of this 16-column chunk (Cout = 128: 32-channel groups, Cout = 64: 16-channel groups); two
+        // independent pair accumulators per statistic
+        const int g = kSplit ? st : (st >> 1);
         uint64_t p01 = f2[0], p23 = f2[1];
         uint64_t r01 = fma_f32x2(f2[0], f2[0], 0ull), r23 = fma_f32x2(f2[1], f2[1], 0ull);
 #pragma unroll
@@ -333,7 +344,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       // the 256-bit stores' data registers it reuses -- a write-after-read stall worth 9 % of the epilogue's samples.)
       // warp reduction of (sg0, ssg0, sg1, ssg1) in 6 shuffles: halve the value count while halving the lanes.
       // lane bit 4 selects the group it keeps, bit 3 the statistic; bits 2..0 are summed out.
-      {
+      if constexpr (!kSplit) {
         const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
         const float keep_s = up16 ? sg[1] : sg[0], keep_ss = up16 ? ssg[1] : ssg[0];
         const float send_s = up16 ? sg[0] : sg[1], send_ss = up16 ? ssg[0] : ssg[1];
@@ -345,6 +356,25 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         val += __shfl_xor_sync(0xffffffffu, val, 1);
         if ((lane & 7) == 0 && valid && a.out_sums)
           gn_red_add(a.out_sums + ((size_t)n * 4 + hcol * 2 + (lane >> 4)) * 2 + ((lane >> 3) & 1), val);
+      } else {
+        // four groups x (sum, sum of squares) in 9 shuffles: lane bit 4 selects the group PAIR it keeps, bit 3 the group of
+        // the pair, bit 2 the statistic; bits 1..0 are summed out
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+        float k_s[2], k_ss[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float keep_s = up16 ? sg[2 + j] : sg[j], send_s = up16 ? sg[j] : sg[2 + j];
+          const float keep_ss = up16 ? ssg[2 + j] : ssg[j], send_ss = up16 ? ssg[j] : ssg[2 + j];
+          k_s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, 16);
+          k_ss[j] = keep_ss + __shfl_xor_sync(0xffffffffu, send_ss, 16);
+        }
+        const float s2 = (up8 ? k_s[1] : k_s[0]) + __shfl_xor_sync(0xffffffffu, up8 ? k_s[0] : k_s[1], 8);
+        const float ss2 = (up8 ? k_ss[1] : k_ss[0]) + __shfl_xor_sync(0xffffffffu, up8 ? k_ss[0] : k_ss[1], 8);
+        float val = (up4 ? ss2 : s2) + __shfl_xor_sync(0xffffffffu, up4 ? s2 : ss2, 4);
+        val += __shfl_xor_sync(0xffffffffu, val, 2);
+        val += __shfl_xor_sync(0xffffffffu, val, 1);
+        if ((lane & 3) == 0 && valid && a.out_sums)
+          gn_red_add(a.out_sums + ((size_t)n * 4 + ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)) * 2 + ((lane >> 2) & 1), val);
       }
       if (do_store) {
         // G x G transpose of 32-byte chunks inside each group of G lanes (G consecutive pixels of one image row): lane j
@@ -371,7 +401,7 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int i = 0; i < G; ++i) st_global_v8(obase + (size_t)i * COUT, pk[i]);
       }
       SDD_PROF_LAP(2);
-      if (it + 1 < (int)SDD_CFG(6)) {  // advance to this CTA's next (valid) tile
+      if (it + it_step < (int)SDD_CFG(6)) {  // advance to this warp's next (valid) tile
         tw += e_dtw; th += e_dth; n += e_dn;
         if (tw >= a.tiles_w) { tw -= a.tiles_w; ++th; }
         if (th >= tiles_h_e) { th -= tiles_h_e; ++n; }
