@@ -574,32 +574,61 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       SDD_PROF_LAP(2);
 #endif
       const uint32_t dst = a_base + (uint32_t)stage * kHaloBytes + soff;
-      if (fuse && ok_c == (1u << nvec) - 1u) {
-        // interior tile: straight-line code, the vectors' chains interleave freely.  (Three of a group's four warps own
-        // eleven vectors, not twelve -- rows >= 180 do not exist -- and used to fall into the masked path below on every
-        // item: 78 % of all loader executions, ~1.7x the instructions.)
+      if constexpr (!kRaw) {
+        if (!fuse) {
+          // un-fused launches: padding pixels hold the zeros they were "loaded" as
 #pragma unroll
-        for (int i = 0; i < kVecs - 1; ++i)
-          sts_v4(dst + (uint32_t)i * 2048u,
-                 make_uint4(xform_pair(r[i].x, 0), xform_pair(r[i].y, 1), xform_pair(r[i].z, 2), xform_pair(r[i].w, 3)));
-        if (nvec == kVecs)  // warp-uniform: col = tg >> 3, so only the first warp of a group has the twelfth vector
-          sts_v4(dst + (uint32_t)(kVecs - 1) * 2048u,
-                 make_uint4(xform_pair(r[kVecs - 1].x, 0), xform_pair(r[kVecs - 1].y, 1), xform_pair(r[kVecs - 1].z, 2),
-                            xform_pair(r[kVecs - 1].w, 3)));
+          for (int i = 0; i < kVecs; ++i)
+            if (i < nvec) sts_v4(dst + (uint32_t)i * 2048u, r[i]);
+        } else if (ok_c == (1u << nvec) - 1u) {
+          // interior tile: straight-line code, the vectors' chains interleave freely.  (Three of a group's four warps own
+          // eleven vectors, not twelve -- rows >= 180 do not exist -- and used to fall into the masked path below on every
+          // item: 78 % of all loader executions, ~1.7x the instructions.)
+#pragma unroll
+          for (int i = 0; i < kVecs - 1; ++i)
+            sts_v4(dst + (uint32_t)i * 2048u,
+                   make_uint4(xform_pair(r[i].x, 0), xform_pair(r[i].y, 1), xform_pair(r[i].z, 2), xform_pair(r[i].w, 3)));
+          if (nvec == kVecs)  // warp-uniform: col = tg >> 3, so only the first warp of a group has the twelfth vector
+            sts_v4(dst + (uint32_t)(kVecs - 1) * 2048u,
+                   make_uint4(xform_pair(r[kVecs - 1].x, 0), xform_pair(r[kVecs - 1].y, 1), xform_pair(r[kVecs - 1].z, 2),
+                              xform_pair(r[kVecs - 1].w, 3)));
+        } else {
+          // border tile (18 % of the tiles at 256^2): the SAME straight-line transform, then out-of-image vectors are zeroed
+          // with a mask -- padding must be zero AFTER the activation.  No branch inside the unrolled loop: with the `fuse`
+          // test per vector ptxas kept the twelve chains serial (MUFU latency exposed: a border item cost 2.1x an interior
+          // one in the round-2 128->128 capture, profiles/r2_stalls_conv.md).
+          auto xform_masked = [&](int i) {
+            const uint32_t m = 0u - ((ok_c >> i) & 1u);
+            sts_v4(dst + (uint32_t)i * 2048u, make_uint4(xform_pair(r[i].x, 0) & m, xform_pair(r[i].y, 1) & m,
+                                                        xform_pair(r[i].z, 2) & m, xform_pair(r[i].w, 3) & m));
+          };
+#pragma unroll
+          for (int i = 0; i < kVecs - 1; ++i) xform_masked(i);
+          if (nvec == kVecs) xform_masked(kVecs - 1);
+        }
       } else {
-        // border tile (18 % of the tiles at 256^2, and they come in runs: a whole tile row at the top / bottom of a sample):
-        // the SAME straight-line transform, then out-of-image vectors are zeroed with a mask -- padding must be zero AFTER
-        // the activation.  (The first version branched per vector on its in-image bit: ~1.7x the instructions of the
-        // interior path exactly where 16 consecutive items of a CTA pair are border tiles, which starves the MMA.)
+        // raw-ring layers (the vectors come from shared memory): per-vector guards, which ptxas schedules next to each
+        // vector's LDS -- same-box A/B, the straight-line border form above is 1.3 % slower here
+        if (fuse && ok_c == (1u << nvec) - 1u) {
 #pragma unroll
-        for (int i = 0; i < kVecs; ++i) {
-          if (i < nvec) {
-            uint4 v = r[i];
-            if (fuse) {
-              const uint32_t m = ((ok_c >> i) & 1u) ? 0xffffffffu : 0u;
-              v = make_uint4(xform_pair(v.x, 0) & m, xform_pair(v.y, 1) & m, xform_pair(v.z, 2) & m, xform_pair(v.w, 3) & m);
+          for (int i = 0; i < kVecs - 1; ++i)
+            sts_v4(dst + (uint32_t)i * 2048u,
+                   make_uint4(xform_pair(r[i].x, 0), xform_pair(r[i].y, 1), xform_pair(r[i].z, 2), xform_pair(r[i].w, 3)));
+          if (nvec == kVecs)
+            sts_v4(dst + (uint32_t)(kVecs - 1) * 2048u,
+                   make_uint4(xform_pair(r[kVecs - 1].x, 0), xform_pair(r[kVecs - 1].y, 1), xform_pair(r[kVecs - 1].z, 2),
+                              xform_pair(r[kVecs - 1].w, 3)));
+        } else {
+#pragma unroll
+          for (int i = 0; i < kVecs; ++i) {
+            if (i < nvec) {
+              uint4 v = r[i];
+              if (fuse) {
+                const uint32_t m = ((ok_c >> i) & 1u) ? 0xffffffffu : 0u;
+                v = make_uint4(xform_pair(v.x, 0) & m, xform_pair(v.y, 1) & m, xform_pair(v.z, 2) & m, xform_pair(v.w, 3) & m);
+              }
+              sts_v4(dst + (uint32_t)i * 2048u, v);
             }
-            sts_v4(dst + (uint32_t)i * 2048u, v);  // un-fused launches: padding pixels hold the zeros they were "loaded" as
           }
         }
       }
