@@ -1,8 +1,10 @@
 #!/bin/bash
-# same-box A/B: baseline library (tools/_lib_base.so, built from HEAD) vs the working tree's library
+# same-box A/B of the whole sampler: baseline library (tools/_lib_base.so) vs the working tree's library
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "conv or unet_forward or border or nonsquare or non_square" 2>&1 | tail -3
+A="--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-roofline"
 for i in 1 2; do
-  SDD_LIB=$PWD/tools/_lib_base.so timeout 200 python tools/conv_layers.py > gpurun_out/ab_base_$i.txt 2>&1; cat gpurun_out/ab_base_$i.txt
-  timeout 200 python tools/conv_layers.py > gpurun_out/ab_new_$i.txt 2>&1; cat gpurun_out/ab_new_$i.txt
+  SDD_LIB=$PWD/tools/_lib_base.so timeout 300 python bench.py $A > gpurun_out/ab_bench_base_$i.json 2>gpurun_out/err.log; python -c "import json; d=json.load(open('gpurun_out/ab_bench_base_$i.json')); print('base', d['value'], d['clocks'])"
+  timeout 300 python bench.py $A > gpurun_out/ab_bench_new_$i.json 2>gpurun_out/err.log; python -c "import json; d=json.load(open('gpurun_out/ab_bench_new_$i.json')); print('new ', d['value'], d['clocks'])"
 done
+SDD_LIB=$PWD/tools/_lib_base.so timeout 300 python bench.py $A --batch 8 > gpurun_out/ab_bench_base_b8.json 2>gpurun_out/err.log; python -c "import json; d=json.load(open('gpurun_out/ab_bench_base_b8.json')); print('base b8', d['value'])"
+timeout 300 python bench.py $A --batch 8 > gpurun_out/ab_bench_new_b8.json 2>gpurun_out/err.log; python -c "import json; d=json.load(open('gpurun_out/ab_bench_new_b8.json')); print('new  b8', d['value'])"
