@@ -109,7 +109,7 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
 }
 constexpr int kCinTS = 40;  // tile row stride in floats: the four tap groups of a warp's gather hit disjoint banks
 
-// PERSISTENT (like conv_out1_mma_kernel): a CTA walks a contiguous range of (sample, 8 x 32 pixel) tiles; the weight
+// PERSISTENT (like conv_out1_tma_kernel): a CTA walks a contiguous range of (sample, 8 x 32 pixel) tiles; the weight
 // fragments are loaded once per CTA, the bias row / GroupNorm(1,1) scalars once per sample, and the next tile's x values
 // are already in flight (two registers per thread) while the current tile is multiplied and stored.  Two CTAs per SM
 // (~100 live registers: three at the 80-register cap spill).  Measured per 16 samples at 256^2: 48.4 -> 42.1 us.
@@ -268,161 +268,8 @@ __device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// PERSISTENT: a CTA walks a CONTIGUOUS range of tiles (tile = (sample, 8 x 32 pixel block); a range rarely crosses a
-// sample, so the per-sample scale/shift is rebuilt about once per CTA).  The weight
-// fragments are loaded once per CTA and the GroupNorm scale/shift once per sample, and each warp issues the raw loads of
-// its first m-tile of the NEXT tile before the current tile's barrier + 9-tap gather, so the tile-to-tile critical path no
-// longer contains a global-load latency.  Measured per 16 samples at 256^2: 84.8 us with one CTA per tile (the ~70 parameter
-// loads of the prologue and three exposed load latencies per 340-pixel tile dominated) -> 63.0 us (2.1 TB/s of input).
-template <int CPS>
-__global__ void __launch_bounds__(256, CPS) conv_out1_mma_kernel(const act_t* __restrict__ raw,
-                                                            const long long* __restrict__ in_sums /*[B][4][2]*/,
-                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            const float* __restrict__ w /*[1][64][3][3]*/,
-                                                            const float* __restrict__ bias, float* __restrict__ out,
-                                                            long long* out_sums /*[B][8], first two used*/, int H, int W,
-                                                            int tiles_x, int tiles_y, int num_tiles) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int t = lane & 3, j = lane >> 2;
-  __shared__ float tb[kO1MT * 16][kO1Taps + 1];  // T[halo pixel][tap], padded against bank conflicts
-  __shared__ float red[2][8][2];
-
-  // weight fragments in the permuted K order: once per CTA
-  uint32_t bw[2][4][2];
-#pragma unroll
-  for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int tap = nt * 8 + j, c = t * 16 + ks * 4 + h * 2;
-        const float w0v = tap < kO1Taps ? w[c * 9 + tap] : 0.f, w1v = tap < kO1Taps ? w[(c + 1) * 9 + tap] : 0.f;
-        bw[nt][ks][h] = pack_act2(w0v, w1v);
-      }
-  const float bias0 = bias[0];
-
-  auto tile_coords = [&](int tile, int& b, int& h0, int& w0) {
-    const int per = tiles_x * tiles_y;
-    b = tile / per;
-    const int r = tile - b * per;
-    const int ty = r / tiles_x;
-    h0 = ty * kO1TH; w0 = (r - ty * tiles_x) * kO1TW;
-  };
-  auto load_mt = [&](const act_t* img, int h0, int w0, int mt, uint4 (&v)[2][2], bool (&ok)[2]) {
-#pragma unroll
-    for (int rh = 0; rh < 2; ++rh) {
-      const int p = mt * 16 + j + 8 * rh;
-      const int hr = p / kO1HW, wr = p - hr * kO1HW;
-      const int hh = h0 - 1 + hr, ww = w0 - 1 + wr;
-      ok[rh] = p < kO1Pix && hh >= 0 && hh < H && ww >= 0 && ww < W;
-      v[rh][0] = make_uint4(0u, 0u, 0u, 0u);
-      v[rh][1] = v[rh][0];
-      if (ok[rh]) {
-        const uint4* src = reinterpret_cast<const uint4*>(img + ((size_t)hh * W + ww) * 64);
-        v[rh][0] = __ldg(src);
-        v[rh][1] = __ldg(src + 1);
-      }
-    }
-  };
-
-  int tile = (int)(((long long)blockIdx.x * num_tiles) / gridDim.x);
-  const int tile_end = (int)(((long long)(blockIdx.x + 1) * num_tiles) / gridDim.x);
-  if (tile >= tile_end) return;
-  int b, h0, w0;
-  tile_coords(tile, b, h0, w0);
-  const act_t* img = raw + (size_t)b * H * W * 64 + t * 16;
-  uint4 vc[2][2], vn[2][2];
-  bool okc[2], okn[2] = {false, false};
-  load_mt(img, h0, w0, warp, vc, okc);
-  int cur_b = -1;
-  float ga[16], gb[16];
-  int it = 0;
-
-  for (; tile < tile_end; ++tile, ++it) {
-    if (b != cur_b) {  // lane t owns channels [16t, 16t+16) = exactly GroupNorm group t
-      float mean, rstd;
-      gn_mean_rstd_from_sums(in_sums + ((size_t)b * 4 + t) * 2, (double)H * (double)W * 16.0, kGnEps, mean, rstd);
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        ga[i] = rstd * gamma[t * 16 + i];
-        gb[i] = beta[t * 16 + i] - mean * ga[i];
-      }
-      cur_b = b;
-    }
-    // coordinates of this CTA's next tile (its first m-tile is prefetched at the end of the m-tile loop)
-    const int ntile = tile + 1;
-    int nb = b, nh0 = h0, nw0 = w0;
-    if (ntile < tile_end) tile_coords(ntile, nb, nh0, nw0);
-    const act_t* nimg = raw + (size_t)nb * H * W * 64 + t * 16;
-
-    for (int mt = warp; mt < kO1MT; mt += 8) {
-      if (mt + 8 < kO1MT) load_mt(img, h0, w0, mt + 8, vn, okn);
-      else if (ntile < tile_end) load_mt(nimg, nh0, nw0, warp, vn, okn);  // next tile's first m-tile
-      uint32_t a[2][8];  // [row half][ks*2+h]
-#pragma unroll
-      for (int rh = 0; rh < 2; ++rh) {
-        uint32_t u[8] = {vc[rh][0].x, vc[rh][0].y, vc[rh][0].z, vc[rh][0].w, vc[rh][1].x, vc[rh][1].y, vc[rh][1].z, vc[rh][1].w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (okc[rh]) {
-            float vl, vh;
-            unpack_act2(u[i], vl, vh);
-            const float lo = silu_tanh(fmaf(vl, ga[2 * i], gb[2 * i]));
-            const float hi = silu_tanh(fmaf(vh, ga[2 * i + 1], gb[2 * i + 1]));
-            u[i] = pack_act2(lo, hi);
-          }
-          a[rh][i] = u[i];
-        }
-      }
-      float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint32_t af[4] = {a[0][ks * 2], a[1][ks * 2], a[0][ks * 2 + 1], a[1][ks * 2 + 1]};
-#ifndef SDD_ACT_BF16
-        mma_f16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
-        mma_f16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
-#else
-        mma_bf16_16816(d0, af, bw[0][ks][0], bw[0][ks][1]);
-        mma_bf16_16816(d1, af, bw[1][ks][0], bw[1][ks][1]);
-#endif
-      }
-      // d0: taps 2t, 2t+1 of rows j and j+8; d1: taps 8+2t, 9+2t (only tap 8 exists)
-      const int r0 = mt * 16 + j;
-      tb[r0][2 * t] = d0[0]; tb[r0][2 * t + 1] = d0[1];
-      tb[r0 + 8][2 * t] = d0[2]; tb[r0 + 8][2 * t + 1] = d0[3];
-      if (t == 0) { tb[r0][8] = d1[0]; tb[r0 + 8][8] = d1[2]; }
-#pragma unroll
-      for (int rh = 0; rh < 2; ++rh) { vc[rh][0] = vn[rh][0]; vc[rh][1] = vn[rh][1]; okc[rh] = okn[rh]; }
-    }
-    __syncthreads();  // tb complete
-
-    const int r = tid / kO1TW, c = tid % kO1TW;
-    const int h = h0 + r, ww = w0 + c;
-    float s = 0.f, ss = 0.f;
-    if (h < H && ww < W) {
-      float acc = bias0;
-#pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) acc += tb[(r + ky) * kO1HW + (c + kx)][ky * 3 + kx];
-      out[((size_t)b * H + h) * W + ww] = acc;
-      s = acc; ss = acc * acc;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-    if (lane == 0) { red[it & 1][warp][0] = s; red[it & 1][warp][1] = ss; }
-    __syncthreads();  // gather reads of tb done (the next tile may overwrite it); red[it & 1] complete
-    if (tid < 2) {
-      float x0 = 0.f;
-      for (int wq = 0; wq < 8; ++wq) x0 += red[it & 1][wq][tid];
-      gn_red_add(out_sums + (size_t)b * 8 + tid, x0);
-    }
-    b = nb; h0 = nh0; w0 = nw0; img = nimg;
-  }
-}
-
 // ------------------------------------------------------------------ the same layer with TMA-staged input (product path)
-// Same contract and arithmetic as conv_out1_mma_kernel; what changes is how the raw activations reach the warps.  The
+// (Round 1's version, conv_out1_mma_kernel, fed the warps with their own global loads; deleted in round 2.)  The
 // register-prefetch version keeps one 2 KB m-tile per warp in flight (32 KB per SM): at ~1.5 us of loaded latency that
 // caps the input stream at ~2.1 TB/s (0.33 of the HBM peak; 252 us per 64 samples at 256^2).  Here one thread fetches
 // the WHOLE (10 x 34 pixel x 64 channel) halo box of the CTA's next tile with a single TMA (43.5 KB, SWIZZLE_128B, zero
@@ -487,7 +334,9 @@ __global__ void __launch_bounds__(256, 2) conv_out1_tma_kernel(const __grid_cons
   if (tile >= tile_end) return;
   if (tid == 0) issue(tile, 0);
   int cur_b = -1;
-  float ga[16], gb[16];
+  // pre-halved scale / shift as packed fp32 pairs: silu(v) = h + h tanh(h), h = v / 2 -- per pair 2 cvt + FFMA2 + 2 MUFU +
+  // FFMA2 + cvt.f16x2 (the scalar form spent 11 instructions per pair; halving is exact, the values are bit-identical)
+  uint64_t ga2[8], gb2[8];
 
   for (int it = 0; tile < tile_end; ++tile, ++it) {
     const int stage = it & 1;
@@ -499,9 +348,10 @@ __global__ void __launch_bounds__(256, 2) conv_out1_tma_kernel(const __grid_cons
       float mean, rstd;
       gn_mean_rstd_from_sums(in_sums + ((size_t)b * 4 + t) * 2, (double)H * (double)W * 16.0, kGnEps, mean, rstd);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        ga[i] = rstd * gamma[t * 16 + i];
-        gb[i] = beta[t * 16 + i] - mean * ga[i];
+      for (int i = 0; i < 8; ++i) {
+        const float a0 = rstd * gamma[t * 16 + 2 * i], a1 = rstd * gamma[t * 16 + 2 * i + 1];
+        ga2[i] = pack_f32x2(0.5f * a0, 0.5f * a1);
+        gb2[i] = pack_f32x2(0.5f * (beta[t * 16 + 2 * i] - mean * a0), 0.5f * (beta[t * 16 + 2 * i + 1] - mean * a1));
       }
       cur_b = b;
     }
@@ -524,9 +374,12 @@ __global__ void __launch_bounds__(256, 2) conv_out1_tma_kernel(const __grid_cons
           u[0] = v0.x; u[1] = v0.y; u[2] = v0.z; u[3] = v0.w; u[4] = v1.x; u[5] = v1.y; u[6] = v1.z; u[7] = v1.w;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            float vl, vh;
+            float vl, vh, hl, hh, rl, rh;
             unpack_act2(u[i], vl, vh);
-            u[i] = pack_act2(silu_tanh(fmaf(vl, ga[2 * i], gb[2 * i])), silu_tanh(fmaf(vh, ga[2 * i + 1], gb[2 * i + 1])));
+            const uint64_t h = fma_f32x2(pack_f32x2(vl, vh), ga2[i], gb2[i]);
+            unpack_f32x2(h, hl, hh);
+            unpack_f32x2(fma_f32x2(h, pack_f32x2(tanh_approx(hl), tanh_approx(hh)), h), rl, rh);
+            u[i] = pack_act2(rl, rh);
           }
         }
 #pragma unroll
