@@ -22,6 +22,9 @@ timeout 600 python bench.py $RED --arch attn > gpurun_out/plain_attn.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 1130 -c 360 --csv --log-file gpurun_out/launches_attn.csv python bench.py $RED --arch attn > gpurun_out/ncu_launches_attn.log 2>&1; echo "ncu launches(attn) rc=$?"
 CHUNK=64 ITERS=2 timeout 300 python tools/conv_one.py > gpurun_out/one.log 2>&1 && \
 CHUNK=64 ITERS=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc4_kernel -s 3 -c 1 -o gpurun_out/prof_conv_128_r2 -f python tools/conv_one.py > gpurun_out/ncu_one.log 2>&1; echo "ncu conv rc=$?"
+CIN=64 COUT=64 CHUNK=64 ITERS=2 timeout 300 python tools/conv_one.py > gpurun_out/one64.log 2>&1 && \
+CIN=64 COUT=64 CHUNK=64 ITERS=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3x3_tc4_kernel -s 3 -c 1 -o gpurun_out/prof_conv_64_r2 -f python tools/conv_one.py > gpurun_out/ncu_one64.log 2>&1; echo "ncu conv64 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attention_fwd_kernel -s 5 -c 1 -o gpurun_out/prof_attn_r2 -f python tools/attn_bench.py > gpurun_out/ncu_attn.log 2>&1; echo "ncu attn rc=$?"
 B=64 timeout 300 python tools/update_one.py > gpurun_out/upd_one.log 2>&1 && \
 B=64 timeout 600 ncu --set full --clock-control none --import-source on -k regex:superpose_update_kernel -s 12 -c 1 -o gpurun_out/prof_update_r2 -f python tools/update_one.py > gpurun_out/ncu_upd.log 2>&1; echo "ncu upd rc=$?"
 # DRAM traffic of the update step INCLUDING write-back: 20 launches deep inside the rotating sequence (buffer sets >> L2, so
