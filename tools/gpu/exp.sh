@@ -1,9 +1,8 @@
 #!/bin/bash
-# same-box A/B of the whole sampler: baseline library (tools/_lib_base.so, built from HEAD) vs the working tree's library
+# same-box A/B: working-tree library vs the -DSDD_CONV_XFORM_FIRST=1 build (tools/_lib_xf.so)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider 2>&1 | tail -3
-A="--steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-roofline"
+SDD_LIB=$PWD/tools/_lib_xf.so timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -p no:cacheprovider -k "conv or unet_forward or border or nonsquare or non_square" 2>&1 | tail -2
 for i in 1 2; do
-  SDD_LIB=$PWD/tools/_lib_base.so timeout 300 python bench.py $A > gpurun_out/ab_bench_base_$i.json 2>gpurun_out/err.log; python -c "import json; d=json.load(open('gpurun_out/ab_bench_base_$i.json')); print('base', d['value'], d['clocks'])"
-  timeout 300 python bench.py $A > gpurun_out/ab_bench_new_$i.json 2>gpurun_out/err.log; python -c "import json; d=json.load(open('gpurun_out/ab_bench_new_$i.json')); print('new ', d['value'], d['clocks'])"
+  timeout 200 python tools/conv_layers.py > gpurun_out/ab_base_$i.txt 2>&1; grep -v "^lib" gpurun_out/ab_base_$i.txt
+  SDD_LIB=$PWD/tools/_lib_xf.so timeout 200 python tools/conv_layers.py > gpurun_out/ab_new_$i.txt 2>&1; grep -v "^lib" gpurun_out/ab_new_$i.txt
 done
