@@ -181,7 +181,9 @@ typedef struct {
                                streamed to the device in step-range chunks on a copy stream while earlier steps compute,
                                through a two-chunk device ring -- O(chunk) device memory instead of the [T,B,D] stack,
                                and the host->device copy overlaps the loop instead of preceding it (ddpm.py:36 draws
-                               one z per step; this is the explicit-noise equivalent of that O(B*D) footprint) */
+                               one z per step; this is the explicit-noise equivalent of that O(B*D) footprint).  The
+                               call returns with the copies still enqueued: the stack must stay valid and unmodified
+                               until the work this call put on `stream` has completed */
   int noise_host_chunk;     /* slices per chunk of the streamed path; 0 = auto (~64 MB per chunk, at least one slice) */
 } sdd_sample_args;
 
