@@ -234,9 +234,11 @@ conv3x3_tc4_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp < 12) {
     // ===================== epilogue: 8 warps = 4 TMEM lane quadrants x 2 =====================
     // Cout = 128: x 2 column halves of every tile.  Cout = 64 (kSplit): x 2 TILE PARITIES -- a warp drains all 64 columns of
-    // its quadrant, of every other tile.  Per warp and tile the work is then the same 64 columns in both cases, but a
-    // Cout = 64 tile pays the per-tile fixed costs (cursor, waits, bias row, statistics reduction, addresses: ~2/3 of the
-    // ~290 instructions a warp spent on 32 columns) four times instead of eight.
+    // its quadrant, of every other tile.  Per warp and tile the work is then the same 64 columns in both cases; what changes
+    // for Cout = 64 is that a warp has TWO tile periods (2 x 1152..1440 MMA cycles) for its dependent chain -- accumulator
+    // wake-up, two-deep tcgen05.ld pipeline, statistics shuffles, stores -- instead of one, with the chain's fixed latencies
+    // paid once per 64 columns instead of once per 32.  (The instruction count per tile is unchanged: measured, 586 per
+    // warp and 64 columns against 2 x 290.)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     constexpr bool kSplit = COUT == 64;
     constexpr int COLS = 64;        // columns drained by this warp
