@@ -1260,7 +1260,10 @@ int sdd_sampler_run(sdd_sampler_t* s, const sdd_sample_args* args, void* stream)
     }
     nchunks = (s->T + S - 1) / S;
     noise_dev = s->ring;
-    SDD_CUDA(cudaStreamWaitEvent(s->copy, s->ev_in, 0));  // the previous run's readers of the ring are behind ev_in
+    // the ring's previous readers: the last run on this sampler (ev_out: recorded on the work stream at its end; a no-op
+    // before the first run) and whatever the caller ordered before this call (ev_in)
+    SDD_CUDA(cudaStreamWaitEvent(s->copy, s->ev_out, 0));
+    SDD_CUDA(cudaStreamWaitEvent(s->copy, s->ev_in, 0));
   }
   auto enqueue_chunk = [&](int c) -> int {  // H2D copy of chunk c into its ring half
     if (c >= nchunks) return SDD_OK;

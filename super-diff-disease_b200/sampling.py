@@ -33,7 +33,7 @@ class _Sampler:
         with torch.cuda.device(device):
             _lib.check(L.sdd_sampler_create(ctypes.byref(self.ptr), arr, self.M, a.data_ptr(), ab.data_ptr(),
                                             b.data_ptr(), self.T, B, H, W, _lib.stream_ptr(device)))
-        self.keep = None  # tensors whose pointers are baked into the captured step graph
+        self.pending = []  # (event, tensors) of calls whose asynchronous work may still be reading the tensors
 
     def launches(self):
         return int(_lib.lib().sdd_sampler_launches_per_run(self.ptr))
@@ -159,7 +159,11 @@ def superposed_sample(models, ddpm, image_shape, device, *, temperature=1.0, bia
     args.mode = _MODES[mode]
     with torch.cuda.device(device):
         _lib.check(_lib.lib().sdd_sampler_run(s.ptr, ctypes.byref(args), _lib.stream_ptr(device)))
-    s.keep = keep  # the stream may still be reading these
+    # the streams may still be reading these (the noise stack, possibly in pinned host memory that the library copies from
+    # asynchronously): they stay referenced until an event recorded behind the call has completed
+    done = torch.cuda.Event()
+    done.record(torch.cuda.current_stream(device))
+    s.pending = [(e, k) for (e, k) in s.pending if not e.query()] + [(done, keep)]
     out = (x, kap, lq) if return_trajectory else x
     if return_x_trajectory:
         out = (out + (xs,)) if isinstance(out, tuple) else (out, xs)

@@ -565,6 +565,19 @@ def test_streamed_host_noise_equals_device_stack(S, dev):
     x1 = d.sample(models[0], shape, dev, noise=stacks[0].to(dev))
     x2 = d.sample(models[0], shape, dev, noise=pinned[0])
     assert torch.equal(x1, x2)
+    # two calls from two streams with no synchronisation between them share the sampler's ring: the second run's copies
+    # wait for the first run's readers, and a host stack dropped by the caller right after the call stays alive
+    refs = [S.superposed_sample(models, d, shape, dev, noise=st.to(dev)) for st in stacks]
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        tmp = stacks[0].clone().pin_memory()
+        a = S.superposed_sample(models, d, shape, dev, noise=tmp, noise_chunk_steps=1)
+        del tmp
+    with torch.cuda.stream(s2):
+        b = S.superposed_sample(models, d, shape, dev, noise=pinned[1], noise_chunk_steps=1)
+    torch.cuda.synchronize()
+    assert torch.equal(a, refs[0]) and torch.equal(b, refs[1])
     # the C ABI refuses pageable host memory and both stacks at once
     import ctypes
     from super_diff_disease_b200 import _lib
